@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""Benchmark of the log-mel front end (the one hot path; BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A step = one pass of the hot path (LogMelSpec.forward semantics: log-mel + batch scalar mean) over
+one batch of synthetic audio.  At N = 1 the workload is BASELINE.json configs[1]: 64 x 30 s segments
+(the ASR training chunk shape), 80 mel, 25 ms / 10 ms.  At N > 1 (torchrun, one rank per GPU) every
+rank processes its own batch of the same shape (episode-sharded, weak scaling, no data-path
+collective — the reference's mean is rank-local); value = frames of all ranks / max time.
+
+Prints ONE JSON line (rank 0).  Keys beyond the base contract:
+  roofline      dominant kernel (logmel_kernel) vs the measured HBM copy bandwidth
+  cpu_baseline  the oracle's fp32 port of the reference op sequence, timed on this box's host cores
+  e2e           same metric through the public call with HOST (pinned) buffers, copies inside the timing
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH, SECONDS, SR, HOP, N_MELS = 64, 30, 16000, 160, 80
+N_SAMPLES = SECONDS * SR
+N_FRAMES = 1 + N_SAMPLES // HOP
+FRAMES_PER_STEP = BATCH * N_FRAMES
+ALGO_BYTES_PER_FRAME = 4 * HOP + 4 * N_MELS          # each sample read once, each feature written once
+WORKLOAD = "configs[1]: batch of 64 x 30 s segments, 16 kHz mono, 80 mel, 25 ms/10 ms, batch scalar mean"
+FALLBACK_HBM_GBS = 6650.0                            # B200_PROFILING.md fallback
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return json.load(fh), "measured"
+    except Exception:
+        return {"hbm_gbs": FALLBACK_HBM_GBS}, "fallback"
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {
+            nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+            nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+            nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def __enter__(self):
+        if self.nv:
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread:
+            self._thread.join()
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def cpu_reference_rate(steps: int, warmup: int, batch_np=None):
+    """Times the oracle's fp32 port of the reference op sequence (oracle/logmel_oracle.py:logmel_port_f32,
+    the restatement of tal/asr/models.py:36-53) on the host cores.  Returns (frames/s, ms/step, threads)."""
+    import torch
+    from oracle import logmel_oracle as O
+    from tal_asrd_b200 import synth
+    if batch_np is None:
+        batch_np = synth.batch(2020, BATCH, N_SAMPLES)
+    x = torch.from_numpy(batch_np)
+    threads = torch.get_num_threads()
+    for _ in range(warmup):
+        O.logmel_port_f32(x)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        O.logmel_port_f32(x)
+        times.append(time.perf_counter() - t0)
+    mean_s = sum(times) / len(times)
+    return FRAMES_PER_STEP / mean_s, mean_s * 1e3, threads, min(times)
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the reference is
+    Python and cannot travel to the GPU box, and its arithmetic is the same torch.stft/matmul sequence)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, args.steps)
+    fps, ms, threads, best = cpu_reference_rate(steps, max(1, min(args.warmup, 3)))
+    line = {
+        "impl": "reference", "metric": "log-mel frames/sec", "value": fps, "unit": "frames/s",
+        "realtime_factor": fps * 0.010, "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": WORKLOAD, "frames_per_step": FRAMES_PER_STEP},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                         "sample": f"full 64 x 30 s batch per step, {steps} steps, torch CPU threads={threads}"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from tal_asrd_b200 import LogMelSpec, _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the front end has no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    lib = _lib.load()
+    mod = LogMelSpec(n_mels=N_MELS).to(dev)
+    stream = torch.cuda.current_stream(dev)
+
+    # synthetic inputs resident in HBM: NBUF distinct batches rotated so that a step never re-reads
+    # what the previous two steps left in L2 (3 x 123 MB of input + 2 x 61 MB of output > 126 MB L2)
+    NBUF = 3
+    waves = []
+    for i in range(NBUF):
+        w = torch.empty(BATCH, N_SAMPLES, dtype=torch.float32, device=dev)
+        _lib.check(lib.talfe_synth_fill(w.data_ptr(), _lib.F32, BATCH, N_SAMPLES, N_SAMPLES, 2020,
+                                        (rank * NBUF + i) * BATCH, 0, stream.cuda_stream))
+        waves.append(w)
+    outs = [torch.empty(BATCH, N_FRAMES, N_MELS, dtype=torch.float32, device=dev) for _ in range(2)]
+    torch.cuda.synchronize()
+
+    def step(i, norm="batch"):
+        return mod.features(waves[i % NBUF], norm=norm, out=outs[i % 2])
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        ev0.record()
+        for i in range(args.steps):
+            step(i)
+        ev1.record()
+        barrier()
+        # keep the same load running a little longer so that NVML (ms-scale sampling) sees clocks under it
+        t_end = time.time() + 0.5
+        j = 0
+        while time.time() < t_end:
+            step(j); j += 1
+            if j % 50 == 0:
+                torch.cuda.synchronize()
+        torch.cuda.synchronize()
+    ms_total = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = world * FRAMES_PER_STEP / (ms_per_step * 1e-3)
+
+    # dominant kernel alone (same launch geometry, un-normalised output): CUDA events on the launching stream
+    for i in range(3):
+        step(i, "none")
+    torch.cuda.synchronize()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for i in range(args.steps):
+        step(i, "none")
+    k1.record()
+    torch.cuda.synchronize()
+    kernel_ms = k0.elapsed_time(k1) / args.steps
+    peaks, peak_kind = measured_peaks()
+    achieved = FRAMES_PER_STEP * ALGO_BYTES_PER_FRAME / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "dram_traffic.json")) as fh:
+            traffic = json.load(fh).get("logmel_kernel_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "logmel_kernel", "achieved": achieved, "peak": peaks["hbm_gbs"],
+                "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_kind": peak_kind,
+                "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / ms_per_step,
+                "algorithmic_bytes_per_launch": FRAMES_PER_STEP * ALGO_BYTES_PER_FRAME}
+
+    # end to end through the public call with HOST buffers: pinned H2D of the step's waveforms, forward,
+    # D2H of the step's features, all inside the timed region
+    host_in = torch.empty(BATCH, N_SAMPLES, dtype=torch.float32).pin_memory()
+    host_in.copy_(waves[0].cpu())
+    host_out = torch.empty(BATCH, N_FRAMES, N_MELS, dtype=torch.float32).pin_memory()
+    e2e_steps = max(3, min(args.steps, 10))
+
+    def e2e_step():
+        mod.forward_host(host_in, host_out, device=dev)
+
+    e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item()) / e2e_steps
+    e2e = {"value": world * FRAMES_PER_STEP / (e2e_ms * 1e-3), "unit": "frames/s", "ms_per_step": e2e_ms,
+           "h2d_bytes_per_step": host_in.numel() * 4, "d2h_bytes_per_step": host_out.numel() * 4, "steps": e2e_steps}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        fps, ms, threads, best = cpu_reference_rate(5, 2, host_in.numpy())
+        cpu = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "ms_per_step": ms,
+               "sample": "the full 64 x 30 s batch (same samples as the GPU step), mean of 5 passes after 2 warm-ups"}
+
+    if rank == 0:
+        line = {
+            "metric": "log-mel frames/sec", "value": value, "unit": "frames/s", "realtime_factor": value * 0.010,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": FRAMES_PER_STEP,
+                       "l2_policy": "3 rotating input batches (369 MB) + 2 output buffers (123 MB) > 126 MB L2",
+                       "parallelism": f"episode-sharded x{world}, no data-path collective"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": 3 * args.steps, "clocks": clocks.summary(),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,150 @@
+/* talfe.h — C ABI of the B200-native log-mel acoustic front end ("talfe" = TAL front end).
+ *
+ * Drop-in boundary for ONE path of calclavia/tal-asrd: the waveform -> (T, n_mels) log-mel
+ * feature extraction the reference performs in
+ *     /root/reference/tal/asr/models.py:15-53   class LogMelSpec  (__init__ :22-33, forward :36-53)
+ * called from
+ *     /root/reference/tal/asr/models.py:154-162 ASRModel.extract_features
+ *     /root/reference/tal/asr/models.py:430-438 SDModel.extract_features
+ * The reference is pure Python and has no FFI of its own for this path; the entry points below
+ * are what a ctypes binding placed inside LogMelSpec.forward would call.
+ *
+ * Conventions
+ *   - plain C, no torch types; every pointer is either a HOST pointer or a DEVICE pointer as
+ *     stated per argument; sizes are int64_t / size_t.
+ *   - the caller owns every buffer including the workspace; the library never allocates, frees
+ *     or synchronises on the hot path (talfe_plan_create / _destroy are the only allocating calls).
+ *   - all work is enqueued on the CUDA stream passed in (cudaStream_t as void*); asynchronous
+ *     CUDA errors surface at the caller's next synchronisation.
+ *   - return value 0 on success, negative talfe_status on error; no exceptions cross the ABI.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef TALFE_H_
+#define TALFE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TALFE_VERSION 100 /* major * 100 + minor */
+
+typedef enum talfe_status {
+    TALFE_OK = 0,
+    TALFE_ERR_INVALID = -1,     /* bad argument (null pointer, negative size, unknown enum) */
+    TALFE_ERR_TOO_SHORT = -2,   /* n_samples <= 200: reflect padding undefined (reference raises RuntimeError) */
+    TALFE_ERR_UNSUPPORTED = -3, /* configuration outside what the sm_100a kernels implement */
+    TALFE_ERR_WORKSPACE = -4,   /* workspace missing or smaller than talfe_workspace_bytes() */
+    TALFE_ERR_CUDA = -5,        /* a CUDA runtime call failed (talfe_last_cuda_error() has the code) */
+    TALFE_ERR_NCCL = -6         /* NCCL unavailable or a collective failed */
+} talfe_status;
+
+/* Waveform element types.  F32 is what the reference feeds (models.py:36-45); F16 is what its
+ * decoding paths produce with .half() (tal/asr/system.py:92,285); I16 is the on-disk PCM format
+ * (tal/utils/audio.py:12-13), scaled by 1/32768 exactly as torchaudio.load normalises
+ * (tal/asr/data/util.py:43). */
+typedef enum talfe_dtype { TALFE_F32 = 0, TALFE_F16 = 1, TALFE_I16 = 2 } talfe_dtype;
+
+/* Normalisation applied after log(mel + eps).
+ *   BATCH_MEAN is the reference: one scalar mean over every element of the [B, T, M] result,
+ *   padding frames included (models.py:52 `mel -= mel.mean()`).  The others are extensions. */
+typedef enum talfe_norm {
+    TALFE_NORM_NONE = 0,
+    TALFE_NORM_BATCH_MEAN = 1,
+    TALFE_NORM_ROW_MEAN = 2,        /* per-row scalar mean over that row's valid frames            */
+    TALFE_NORM_ROW_MEL_MEAN = 3,    /* per-row, per-mel mean (CMN)                                   */
+    TALFE_NORM_ROW_MEL_MEANVAR = 4  /* per-row, per-mel mean and variance (CMVN)                     */
+} talfe_norm;
+
+/* Output layout: TM = [B, T, M] (what LogMelSpec.forward returns, models.py:48);
+ * MT = [B, M, T] (what encode_features permutes to next, models.py:167,443). */
+typedef enum talfe_layout { TALFE_LAYOUT_TM = 0, TALFE_LAYOUT_MT = 1 } talfe_layout;
+
+typedef struct talfe_plan talfe_plan; /* opaque: device-resident tables for one (device, n_mels) */
+
+/* Statistics block layout (doubles): [0] = element count, [1] = sum, [2] = sum of squares,
+ * then per-mel sums [3 .. 3+M) and per-mel sums of squares [3+M .. 3+2M).  One block per row for
+ * the ROW_* modes, one block in total for NONE / BATCH_MEAN. */
+#define TALFE_STATS_DOUBLES(n_mels) (3 + 2 * (n_mels))
+
+/* One unit of work: `batch` rows, frames [frame0, frame0 + n_frames) of each row. */
+typedef struct talfe_job {
+    const void* wave;        /* DEVICE: batch rows of samples, row r at wave + r * row_stride elements        */
+    int32_t wave_dtype;      /* talfe_dtype                                                                  */
+    int32_t norm;            /* talfe_norm                                                                   */
+    int64_t batch;           /* B >= 1                                                                       */
+    int64_t row_stride;      /* elements between consecutive rows (>= buf_len)                               */
+    int64_t buf_len;         /* samples present per row in `wave`                                            */
+    int64_t origin;          /* index, within the full row/episode, of wave[r][0] (0 unless streaming chunks)*/
+    int64_t total_len;       /* full length L of every row: frame count 1 + L/160 and the reflection point;  */
+                             /*   rows shorter than L are expected zero-padded by the caller (reference       */
+                             /*   collater semantics, tal/asr/data/aligned.py:246-270)                        */
+    const int64_t* lens;     /* DEVICE or NULL: per-row true lengths -> "each row as if alone" semantics      */
+                             /*   (own frame count, reflection at its own end, frames beyond written as 0)    */
+    int64_t frame0;          /* first frame to produce                                                        */
+    int64_t n_frames;        /* frames to produce per row                                                     */
+    float* out;              /* DEVICE: [B, n_frames, M] or [B, M, n_frames] float32                          */
+    int64_t out_row_stride;  /* floats between rows of out; 0 = dense (n_frames * M)                          */
+    int32_t out_layout;      /* talfe_layout                                                                  */
+    int32_t accumulate_stats;/* nonzero: add this call's sums into `stats` instead of overwriting (streaming) */
+    float eps;               /* additive floor inside the log (reference 1e-6, models.py:22)                  */
+    int32_t defer_normalise; /* nonzero: compute `stats` but leave `out` un-normalised (apply later)          */
+    double* stats;           /* DEVICE or NULL: TALFE_STATS_DOUBLES(M) doubles (x B for ROW_* modes)          */
+    void* workspace;         /* DEVICE: at least talfe_workspace_bytes() bytes                                */
+    size_t workspace_bytes;
+    void* stream;            /* cudaStream_t                                                                  */
+} talfe_job;
+
+int talfe_version(void);
+const char* talfe_strerror(int status);
+int talfe_last_cuda_error(void); /* cudaError_t of the most recent TALFE_ERR_CUDA on this thread */
+
+/* 1 + n_samples / 160, or TALFE_ERR_TOO_SHORT when n_samples <= 200
+ * (torch.stft(center=True, pad_mode="reflect") inside MelSpectrogram, models.py:24-32;
+ *  models.py:91 "15999 frames => 100 frames"). */
+int64_t talfe_num_frames(int64_t n_samples);
+
+/* Builds the device tables.  window_host: 400 floats or NULL (periodic Hann computed here);
+ * fb_host: [201, n_mels] row-major floats or NULL (HTK triangular filters 0..8000 Hz computed here).
+ * Passing the reference module's own buffers makes the tables bit-identical to the reference's.
+ * n_mels in 1..80; fb rows 0 and 200 must be all zero and every filter's support contiguous,
+ * otherwise TALFE_ERR_UNSUPPORTED. */
+int talfe_plan_create(talfe_plan** plan, int device, int n_mels, const float* window_host, const float* fb_host);
+void talfe_plan_destroy(talfe_plan* plan);
+int talfe_plan_n_mels(const talfe_plan* plan);
+
+/* Bytes of workspace talfe_run needs for `batch` rows of `n_frames` frames. */
+size_t talfe_workspace_bytes(const talfe_plan* plan, int64_t batch, int64_t n_frames);
+
+/* The hot path. */
+int talfe_run(const talfe_plan* plan, const talfe_job* job);
+
+/* Convenience wrapper with the exact semantics of LogMelSpec.forward (models.py:36-53):
+ * wave[B, n_samples] (row stride row_stride) -> out[B, 1 + n_samples/160, M], minus the batch scalar mean. */
+int talfe_logmel_forward(const talfe_plan* plan, const void* wave, int wave_dtype, int64_t batch,
+                         int64_t n_samples, int64_t row_stride, float* out, float eps, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
+/* Normalise features in place from a statistics block (e.g. after summing blocks of several chunks,
+ * or after an all-reduce across ranks).  `norm` selects which entries of stats are used; for the
+ * ROW_* modes stats holds one block per row.  valid_frames (DEVICE or NULL) limits each row. */
+int talfe_apply_stats(const talfe_plan* plan, float* feats, int64_t batch, int64_t n_frames,
+                      int64_t out_row_stride, int out_layout, int norm, const double* stats,
+                      const int64_t* valid_frames, void* stream);
+
+/* Dataset-level statistics across ranks: in-place sum of `count` doubles over the communicator.
+ * nccl_comm is an ncclComm_t created by the caller; NCCL is resolved at run time with dlopen
+ * ("libnccl.so.2"), so the library itself has no link-time dependency on it. */
+int talfe_allreduce_stats(double* stats_dev, int64_t count, void* nccl_comm, void* stream);
+
+/* Deterministic synthetic audio (bench / tests): fills wave[rows, n_samples] with episode
+ * (first_episode + r), samples [start, start + n_samples); bit-identical to tal_asrd_b200/synth.py. */
+int talfe_synth_fill(void* wave, int wave_dtype, int64_t rows, int64_t n_samples, int64_t row_stride,
+                     uint64_t seed, int64_t first_episode, int64_t start, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TALFE_H_ */

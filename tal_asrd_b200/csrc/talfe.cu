@@ -1,0 +1,590 @@
+// talfe.cu — fused log-mel front end for NVIDIA B200 (sm_100a) and its C ABI (include/talfe.h).
+//
+// Replaces, for one path only, /root/reference/tal/asr/models.py:36-53 (LogMelSpec.forward), i.e.
+// the ~10 library launches torchaudio/torch make for reflect-pad -> frame x Hann -> rFFT-400 ->
+// |.|^2 -> [201x80] mel matmul -> log(.+eps) -> mean subtraction, with
+//   K1  logmel_kernel        everything up to un-normalised log-mel, written to HBM once, plus
+//                            per-warp partial sums of the output (deterministic, no atomics);
+//   K2  reduce_partials      fixed-order reduction of those partials into the statistics block;
+//   K3  apply_stats          in-place (x - mean) [* rstd] sweep (L2-resident for batch-sized outputs).
+//
+// K1 work decomposition: one CTA = 16 groups of 20 threads = 16 frame pairs = 32 consecutive frames
+// of one row per tile; persistent CTAs stride over the tiles.  Math per group: talfe_core.cuh.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <algorithm>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "../../include/talfe.h"
+#include "talfe_core.cuh"
+#include "talfe_tables.h"
+
+using namespace talfe;
+
+namespace {
+
+constexpr int kGroupsPerCta = 16;
+constexpr int kThreads = kGroupsPerCta * kGroup;            // 320
+constexpr int kWarps = kThreads / 32;                       // 10
+constexpr int kFramesPerTile = 2 * kGroupsPerCta;           // 32
+constexpr int kTileSamples = kHop * kFramesPerTile + (kNfft - kHop);   // 5360
+constexpr int kNormalThreads = 18 * kGroupsPerCta;          // 288 = 9 full warps; warp 9 = packed rows 0/10
+constexpr int kColChunk = 2048;                             // frames per block in the per-mel statistics pass
+static_assert(kNormalThreads % 32 == 0, "special rows must fill whole warps");
+
+thread_local int g_last_cuda_error = 0;
+
+struct talfe_plan_impl {
+    int device;
+    int n_mels;
+    int sm_count;
+    int ctas_per_sm;
+    MelLayout layout;
+    int pstride;
+    size_t off_tw, off_w, off_lo, blob_bytes;
+    unsigned char* blob_dev;
+    size_t smem_bytes;
+};
+
+struct KernelArgs {
+    const void* wave;
+    int dtype;
+    long long batch, row_stride, buf_len, origin, total_len;
+    const long long* lens;
+    long long frame0, n_frames;
+    float* out;
+    long long out_row_stride;
+    int out_layout;
+    float eps;
+    long long tiles_per_row, n_tiles;
+    double2* partials;             // [n_tiles][kWarps]
+    const unsigned char* blob;
+    int blob_bytes, off_tw, off_w, off_lo;
+    MelLayout layout;
+    int pstride;
+};
+
+__device__ __forceinline__ float load_sample(const void* base, int dtype, long long idx) {
+    if (dtype == TALFE_F32) return __ldg(reinterpret_cast<const float*>(base) + idx);
+    if (dtype == TALFE_F16) return __half2float(__ldg(reinterpret_cast<const __half*>(base) + idx));
+    return (float)__ldg(reinterpret_cast<const short*>(base) + idx) * (1.0f / 32768.0f);
+}
+
+// ------------------------------------------------------------------------------------------ K1
+__global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const KernelArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    // shared-memory carve-up (all offsets multiples of 16 bytes)
+    const float* s_win = reinterpret_cast<const float*>(smem);
+    const cf* s_tw = reinterpret_cast<const cf*>(smem + a.off_tw);
+    const float* s_w = reinterpret_cast<const float*>(smem + a.off_w);
+    const int* s_lo = reinterpret_cast<const int*>(smem + a.off_lo);
+    float* s_x = reinterpret_cast<float*>(smem + a.blob_bytes);
+    cf* s_e = reinterpret_cast<cf*>(s_x + ((kTileSamples + 3) & ~3));
+    cf* s_p = s_e + kGroupsPerCta * kEGroup;
+
+    const int tid = threadIdx.x;
+    {   // constant tables -> shared memory; power array (incl. its padding) zeroed once
+        const int4* src = reinterpret_cast<const int4*>(a.blob);
+        int4* dst = reinterpret_cast<int4*>(smem);
+        for (int i = tid; i < a.blob_bytes / 16; i += kThreads) dst[i] = __ldg(src + i);
+        for (int i = tid; i < kGroupsPerCta * a.pstride; i += kThreads) s_p[i] = make_float2(0.f, 0.f);
+    }
+    // roles
+    const int g1 = tid / kGroup, j = tid - g1 * kGroup;                 // stage 1 and mel stage
+    int g2, c;                                                          // stage 2
+    if (tid < kNormalThreads) { g2 = tid / 18; int r = tid - g2 * 18; c = r < 9 ? r + 1 : r + 2; }
+    else { int s = tid - kNormalThreads; g2 = s >> 1; c = (s & 1) ? 10 : 0; }
+    const int warp = tid >> 5, lane = tid & 31;
+    const int M = a.layout.n_mels;
+
+    for (long long tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        const long long row = tile / a.tiles_per_row;
+        const long long tq = tile - row * a.tiles_per_row;
+        const long long t0 = a.frame0 + tq * kFramesPerTile;            // first frame of the tile
+        const long long L = a.lens ? a.lens[row] : a.total_len;
+        const long long T_row = L > kHalf ? 1 + L / kHop : 0;           // frames this row really has
+        const long long t_end = min(a.frame0 + a.n_frames, T_row);      // valid frames are t < t_end
+        float* out_row = a.out + row * a.out_row_stride;
+
+        float sum = 0.f, sumsq = 0.f;
+        if (t0 < t_end) {
+            // ---- stage 0: waveform tile -> shared memory (each sample read from HBM once per tile)
+            const long long s0 = kHop * t0 - kHalf;                     // episode index of s_x[0]
+            const long long b0 = s0 - a.origin;                         // buffer index of s_x[0]
+            const char* rowp = reinterpret_cast<const char*>(a.wave) +
+                               row * a.row_stride * (a.dtype == TALFE_F32 ? 4 : 2);
+            const bool interior = s0 >= 0 && s0 + kTileSamples <= L && b0 >= 0 && b0 + kTileSamples <= a.buf_len;
+            if (interior && a.dtype == TALFE_F32 &&
+                ((reinterpret_cast<unsigned long long>(rowp) + 4ull * (unsigned long long)b0) & 15ull) == 0) {
+                const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(rowp) + b0);
+                float4* dst = reinterpret_cast<float4*>(s_x);
+                for (int i = tid; i < kTileSamples / 4; i += kThreads) dst[i] = __ldg(src + i);
+            } else {
+                for (int i = tid; i < kTileSamples; i += kThreads) {
+                    long long g = s0 + i;
+                    if (g < 0) g = -g;                                  // reflect, no edge repeat
+                    if (g >= L) g = 2 * (L - 1) - g;
+                    const long long bi = g - a.origin;
+                    float v = 0.f;
+                    if (g >= 0 && g < L && bi >= 0 && bi < a.buf_len) v = load_sample(rowp, a.dtype, bi);
+                    s_x[i] = v;
+                }
+            }
+            __syncthreads();
+            // ---- stage 1: windowed real FFT-20 of both frames of the pair, twiddle, exchange
+            stage1(j, s_x + 2 * kHop * g1, s_win, s_tw, s_e + g1 * kEGroup);
+            __syncthreads();
+            // ---- stage 2: FFT-20 across the group, power spectrum into s_p
+            {
+                cf v[20];
+                stage2_load(c, s_e + g2 * kEGroup, v);
+                float* p2 = reinterpret_cast<float*>(s_p + g2 * a.pstride);
+                if (tid < kNormalThreads) stage2_normal(c, v, p2);
+                else stage2_special(c, v, p2);
+            }
+            __syncthreads();
+            // ---- mel projection, log, store, statistics
+            float y[2 * kMelSlots];
+            mel_log(j, a.layout, s_p + g1 * a.pstride, s_w, s_lo, a.eps, y);
+            const long long ta = t0 + 2 * g1;
+#pragma unroll
+            for (int f = 0; f < 2; ++f) {
+                const long long t = ta + f;
+                if (t < a.frame0 + a.n_frames) {
+                    const bool valid = t < t_end;
+#pragma unroll
+                    for (int i = 0; i < kMelSlots; ++i) {
+                        const int m = j + 20 * i;
+                        if (m < M) {
+                            const float v = valid ? y[2 * i + f] : 0.f;
+                            if (valid) { sum += v; sumsq = fmaf(v, v, sumsq); }
+                            if (a.out_layout == TALFE_LAYOUT_TM) out_row[(t - a.frame0) * M + m] = v;
+                            else out_row[(long long)m * a.n_frames + (t - a.frame0)] = v;
+                        }
+                    }
+                }
+            }
+        } else {
+            // tile lies entirely beyond this row's own frames ("each row as if alone"): zero fill
+            const long long nfr = min((long long)kFramesPerTile, a.frame0 + a.n_frames - t0);
+            for (long long i = tid; i < nfr * M; i += kThreads) {
+                const long long f = i / M, m = i - f * M;
+                if (a.out_layout == TALFE_LAYOUT_TM) out_row[(t0 - a.frame0 + f) * M + m] = 0.f;
+                else out_row[m * a.n_frames + (t0 - a.frame0 + f)] = 0.f;
+            }
+        }
+        // per-warp partial sums (fixed shuffle tree -> bit-reproducible), one slot per (tile, warp)
+        double ds = (double)sum, dq = (double)sumsq;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            ds += __shfl_xor_sync(0xffffffffu, ds, o);
+            dq += __shfl_xor_sync(0xffffffffu, dq, o);
+        }
+        if (lane == 0) a.partials[tile * kWarps + warp] = make_double2(ds, dq);
+        // the next iteration's stage 0 overwrites s_x, which nobody reads after the stage-1 barrier;
+        // s_e / s_p are rewritten only after the next two barriers.
+    }
+}
+
+// ------------------------------------------------------------------------------------------ K2
+// One block per statistics block (1 for batch-wide, B for per-row).  Fixed-order tree in shared
+// memory: the result does not depend on scheduling.
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const double2* __restrict__ partials, long long slots_per_block,
+                                                              const long long* __restrict__ lens, long long total_len,
+                                                              long long frame0, long long n_frames, long long rows_per_block,
+                                                              int n_mels, int accumulate, double* __restrict__ stats) {
+    __shared__ double s_a[256], s_b[256];
+    const long long blk = blockIdx.x;
+    const double2* p = partials + blk * slots_per_block;
+    double a = 0.0, b = 0.0;
+    for (long long i = threadIdx.x; i < slots_per_block; i += 256) { double2 v = p[i]; a += v.x; b += v.y; }
+    s_a[threadIdx.x] = a; s_b[threadIdx.x] = b;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) { s_a[threadIdx.x] += s_a[threadIdx.x + o]; s_b[threadIdx.x] += s_b[threadIdx.x + o]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        double count = 0.0;
+        for (long long r = blk * rows_per_block; r < (blk + 1) * rows_per_block; ++r) {
+            const long long L = lens ? lens[r] : total_len;
+            const long long T_row = L > kHalf ? 1 + L / kHop : 0;
+            long long v = min(frame0 + n_frames, T_row) - frame0;
+            if (v < 0) v = 0;
+            count += (double)v * n_mels;
+        }
+        double* s = stats + blk * TALFE_STATS_DOUBLES(n_mels);
+        if (accumulate) { s[0] += count; s[1] += s_a[0]; s[2] += s_b[0]; }
+        else { s[0] = count; s[1] = s_a[0]; s[2] = s_b[0]; }
+    }
+}
+
+// Per-mel column sums of un-normalised features (extension modes 3/4).  grid (chunks, B).
+__global__ void __launch_bounds__(320) colstats_kernel(const float* __restrict__ feats, long long out_row_stride, int out_layout,
+                                                       long long n_frames, int n_mels, const long long* __restrict__ lens,
+                                                       long long total_len, long long frame0, double* __restrict__ colpart) {
+    __shared__ double s_sum[4][kMaxMels], s_sq[4][kMaxMels];
+    const long long row = blockIdx.y, chunk = blockIdx.x;
+    const long long L = lens ? lens[row] : total_len;
+    const long long T_row = L > kHalf ? 1 + L / kHop : 0;
+    long long valid = min(frame0 + n_frames, T_row) - frame0;
+    if (valid < 0) valid = 0;
+    const int m = threadIdx.x % kMaxMels, lane_f = threadIdx.x / kMaxMels;       // 80 mels x 4 frame lanes
+    const long long f_lo = chunk * kColChunk, f_hi = min(f_lo + kColChunk, valid);
+    const float* base = feats + row * out_row_stride;
+    double a = 0.0, b = 0.0;
+    if (m < n_mels)
+        for (long long f = f_lo + lane_f; f < f_hi; f += 4) {
+            const float v = out_layout == TALFE_LAYOUT_TM ? base[f * n_mels + m] : base[(long long)m * n_frames + f];
+            a += v; b += (double)v * v;
+        }
+    s_sum[lane_f][m] = a; s_sq[lane_f][m] = b;
+    __syncthreads();
+    if (lane_f == 0 && m < n_mels) {
+        double* o = colpart + (row * gridDim.x + chunk) * 2 * kMaxMels;
+        o[m] = (s_sum[0][m] + s_sum[1][m]) + (s_sum[2][m] + s_sum[3][m]);
+        o[kMaxMels + m] = (s_sq[0][m] + s_sq[1][m]) + (s_sq[2][m] + s_sq[3][m]);
+    }
+}
+
+__global__ void colstats_finish_kernel(const double* __restrict__ colpart, int chunks, int n_mels, int accumulate,
+                                       double* __restrict__ stats) {
+    const long long row = blockIdx.x;
+    const int m = threadIdx.x;
+    if (m >= n_mels) return;
+    double a = 0.0, b = 0.0;
+    for (int ch = 0; ch < chunks; ++ch) {
+        const double* o = colpart + (row * chunks + ch) * 2 * kMaxMels;
+        a += o[m]; b += o[kMaxMels + m];
+    }
+    double* s = stats + row * TALFE_STATS_DOUBLES(n_mels);
+    if (accumulate) { s[3 + m] += a; s[3 + n_mels + m] += b; }
+    else { s[3 + m] = a; s[3 + n_mels + m] = b; }
+}
+
+// ------------------------------------------------------------------------------------------ K3
+__global__ void __launch_bounds__(256) apply_stats_kernel(float* __restrict__ feats, long long batch, long long n_frames,
+                                                          long long out_row_stride, int out_layout, int n_mels, int norm,
+                                                          const double* __restrict__ stats, const long long* __restrict__ valid_frames,
+                                                          const long long* __restrict__ lens, long long frame0) {
+    __shared__ float s_mean[kMaxMels], s_rstd[kMaxMels];
+    const long long row = blockIdx.y;
+    const double* s = stats + (norm == TALFE_NORM_BATCH_MEAN ? 0 : row * TALFE_STATS_DOUBLES(n_mels));
+    long long valid = n_frames;
+    if (valid_frames) valid = min(valid_frames[row], n_frames);
+    else if (lens) {
+        const long long L = lens[row];
+        valid = max(0ll, min(frame0 + n_frames, L > kHalf ? 1 + L / kHop : 0ll) - frame0);
+    }
+    if (threadIdx.x < n_mels) {
+        float mean = 0.f, rstd = 1.f;
+        if (norm == TALFE_NORM_BATCH_MEAN || norm == TALFE_NORM_ROW_MEAN) {
+            mean = s[0] > 0.0 ? (float)(s[1] / s[0]) : 0.f;
+        } else if (norm == TALFE_NORM_ROW_MEL_MEAN || norm == TALFE_NORM_ROW_MEL_MEANVAR) {
+            const double n = s[0] / n_mels;
+            const double mu = n > 0.0 ? s[3 + threadIdx.x] / n : 0.0;
+            mean = (float)mu;
+            if (norm == TALFE_NORM_ROW_MEL_MEANVAR && n > 0.0) {
+                double var = s[3 + n_mels + threadIdx.x] / n - mu * mu;
+                if (var < 1e-10) var = 1e-10;
+                rstd = (float)rsqrt(var);
+            }
+        }
+        s_mean[threadIdx.x] = mean; s_rstd[threadIdx.x] = rstd;
+    }
+    __syncthreads();
+    float* base = feats + row * out_row_stride;
+    const long long total = valid * n_mels;
+    if (out_layout == TALFE_LAYOUT_TM && (n_mels & 3) == 0 && ((reinterpret_cast<unsigned long long>(base) & 15ull) == 0)) {
+        float4* b4 = reinterpret_cast<float4*>(base);
+        const int m4 = n_mels >> 2;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total / 4; i += (long long)gridDim.x * blockDim.x) {
+            const int m = (int)(i % m4) * 4;
+            float4 v = b4[i];
+            v.x = (v.x - s_mean[m]) * s_rstd[m];
+            v.y = (v.y - s_mean[m + 1]) * s_rstd[m + 1];
+            v.z = (v.z - s_mean[m + 2]) * s_rstd[m + 2];
+            v.w = (v.w - s_mean[m + 3]) * s_rstd[m + 3];
+            b4[i] = v;
+        }
+    } else if (out_layout == TALFE_LAYOUT_TM) {
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+            const int m = (int)(i % n_mels);
+            base[i] = (base[i] - s_mean[m]) * s_rstd[m];
+        }
+    } else {
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)n_mels * n_frames;
+             i += (long long)gridDim.x * blockDim.x) {
+            const int m = (int)(i / n_frames);
+            const long long f = i - (long long)m * n_frames;
+            if (f < valid) base[i] = (base[i] - s_mean[m]) * s_rstd[m];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ synthetic audio
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+__global__ void synth_kernel(void* wave, int dtype, long long rows, long long n, long long row_stride,
+                             unsigned long long seed, long long first_episode, long long start) {
+    const long long total = rows * n;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long r = idx / n, col = idx - r * n;
+        const unsigned long long key = splitmix64(seed ^ ((unsigned long long)(first_episode + r) * 0xD1B54A32D192ED03ull));
+        const unsigned long long i = (unsigned long long)(start + col);
+        const unsigned long long h = splitmix64(key + i);
+        const long long s = (long long)((h & 0xFFFF) + ((h >> 16) & 0xFFFF) + ((h >> 32) & 0xFFFF) + (h >> 48)) - 131070;
+        const long long amp = (s * 2838) >> 15;
+        const unsigned long long eoff = (key >> 40) % 53333ull;
+        const long long ph = (long long)((i + eoff) % 53333ull);
+        long long tri = 2 * ph - 53333; if (tri < 0) tri = -tri;
+        const long long env = 3277 + (62259 * tri) / 53333;
+        long long k = (amp * env) >> 16;
+        const unsigned long long g = splitmix64(key + 0x5851F42D4C957F2Dull * (i / 4000ull + 1ull));
+        if ((g >> 32) % 10ull == 0ull) k = 0;
+        k = max(-32767ll, min(32767ll, k));
+        const long long o = r * row_stride + col;
+        if (dtype == TALFE_F32) reinterpret_cast<float*>(wave)[o] = (float)k * (1.0f / 32768.0f);
+        else if (dtype == TALFE_F16) reinterpret_cast<__half*>(wave)[o] = __float2half((float)k * (1.0f / 32768.0f));
+        else reinterpret_cast<short*>(wave)[o] = (short)k;
+    }
+}
+
+int cuda_fail(cudaError_t e) { g_last_cuda_error = (int)e; return TALFE_ERR_CUDA; }
+#define TALFE_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return cuda_fail(e__); } while (0)
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// blocks along x for the in-place sweep: enough to fill the GPU ~8 deep across all rows
+unsigned sweep_blocks(int sm_count, long long batch, long long dense_per_row) {
+    long long want = (dense_per_row / 4 + 255) / 256;
+    long long cap = std::max<long long>(1, (long long)sm_count * 8 / std::max<long long>(1, batch));
+    return (unsigned)std::max<long long>(1, std::min(want, cap));
+}
+
+struct WorkspaceLayout { size_t partials, colpart, scratch_stats, total; long long tiles_per_row, n_tiles; int chunks; };
+
+WorkspaceLayout workspace_layout(int n_mels, long long batch, long long n_frames) {
+    WorkspaceLayout w{};
+    w.tiles_per_row = (n_frames + kFramesPerTile - 1) / kFramesPerTile;
+    w.n_tiles = w.tiles_per_row * batch;
+    w.chunks = (int)((n_frames + kColChunk - 1) / kColChunk);
+    if (w.chunks < 1) w.chunks = 1;
+    w.partials = 0;
+    size_t off = align_up((size_t)w.n_tiles * kWarps * sizeof(double2), 256);
+    w.colpart = off;
+    off += align_up((size_t)batch * w.chunks * 2 * kMaxMels * sizeof(double), 256);
+    w.scratch_stats = off;
+    off += align_up((size_t)batch * TALFE_STATS_DOUBLES(n_mels) * sizeof(double), 256);
+    w.total = off;
+    return w;
+}
+
+}  // namespace
+
+struct talfe_plan : talfe_plan_impl {};
+
+extern "C" {
+
+int talfe_version(void) { return TALFE_VERSION; }
+
+const char* talfe_strerror(int status) {
+    switch (status) {
+        case TALFE_OK: return "ok";
+        case TALFE_ERR_INVALID: return "invalid argument";
+        case TALFE_ERR_TOO_SHORT: return "waveform too short: reflect padding of 200 needs more than 200 samples";
+        case TALFE_ERR_UNSUPPORTED: return "configuration not supported by the sm_100a kernels";
+        case TALFE_ERR_WORKSPACE: return "workspace missing or too small";
+        case TALFE_ERR_CUDA: return "CUDA runtime error";
+        case TALFE_ERR_NCCL: return "NCCL unavailable or collective failed";
+        default: return "unknown status";
+    }
+}
+
+int talfe_last_cuda_error(void) { return g_last_cuda_error; }
+
+int64_t talfe_num_frames(int64_t n_samples) {
+    if (n_samples <= kHalf) return TALFE_ERR_TOO_SHORT;
+    return 1 + n_samples / kHop;
+}
+
+int talfe_plan_create(talfe_plan** plan_out, int device, int n_mels, const float* window_host, const float* fb_host) {
+    if (!plan_out) return TALFE_ERR_INVALID;
+    *plan_out = nullptr;
+    if (n_mels < 1 || n_mels > kMaxMels) return TALFE_ERR_UNSUPPORTED;
+    std::vector<float> win(kNfft), fb((size_t)kBins * n_mels);
+    if (window_host) win.assign(window_host, window_host + kNfft); else default_window(win.data());
+    if (fb_host) fb.assign(fb_host, fb_host + (size_t)kBins * n_mels); else default_filterbank(n_mels, fb.data());
+    HostTables t;
+    int rc = build_tables(n_mels, win.data(), fb.data(), t);
+    if (rc) return rc;
+
+    int prev = 0;
+    TALFE_CUDA(cudaGetDevice(&prev));
+    TALFE_CUDA(cudaSetDevice(device));
+    talfe_plan* p = new (std::nothrow) talfe_plan();
+    if (!p) return TALFE_ERR_INVALID;
+    p->device = device;
+    p->n_mels = n_mels;
+    p->layout = t.layout;
+    p->pstride = t.pstride;
+    p->off_tw = t.off_tw; p->off_w = t.off_w; p->off_lo = t.off_lo; p->blob_bytes = t.blob_bytes;
+    p->smem_bytes = t.blob_bytes + (size_t)((kTileSamples + 3) & ~3) * sizeof(float) +
+                    (size_t)kGroupsPerCta * kEGroup * sizeof(cf) + (size_t)kGroupsPerCta * t.pstride * sizeof(cf);
+    cudaError_t e = cudaMalloc(&p->blob_dev, t.blob_bytes);
+    if (e == cudaSuccess) e = cudaMemcpy(p->blob_dev, t.blob.data(), t.blob_bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p->ctas_per_sm, logmel_kernel, kThreads, p->smem_bytes);
+    cudaSetDevice(prev);
+    if (e != cudaSuccess) { if (p->blob_dev) cudaFree(p->blob_dev); delete p; return cuda_fail(e); }
+    if (p->ctas_per_sm < 1) { cudaFree(p->blob_dev); delete p; return TALFE_ERR_UNSUPPORTED; }
+    *plan_out = p;
+    return TALFE_OK;
+}
+
+void talfe_plan_destroy(talfe_plan* plan) {
+    if (!plan) return;
+    if (plan->blob_dev) cudaFree(plan->blob_dev);
+    delete plan;
+}
+
+int talfe_plan_n_mels(const talfe_plan* plan) { return plan ? plan->n_mels : TALFE_ERR_INVALID; }
+
+size_t talfe_workspace_bytes(const talfe_plan* plan, int64_t batch, int64_t n_frames) {
+    if (!plan || batch < 1 || n_frames < 1) return 0;
+    return workspace_layout(plan->n_mels, batch, n_frames).total;
+}
+
+int talfe_run(const talfe_plan* plan, const talfe_job* job) {
+    if (!plan || !job || !job->wave || !job->out) return TALFE_ERR_INVALID;
+    if (job->batch < 1 || job->n_frames < 1 || job->frame0 < 0 || job->buf_len < 1 || job->origin < 0) return TALFE_ERR_INVALID;
+    if (job->wave_dtype < TALFE_F32 || job->wave_dtype > TALFE_I16) return TALFE_ERR_INVALID;
+    if (job->norm < TALFE_NORM_NONE || job->norm > TALFE_NORM_ROW_MEL_MEANVAR) return TALFE_ERR_INVALID;
+    if (job->out_layout != TALFE_LAYOUT_TM && job->out_layout != TALFE_LAYOUT_MT) return TALFE_ERR_INVALID;
+    if (job->row_stride < job->buf_len) return TALFE_ERR_INVALID;
+    if (!job->lens) {
+        if (job->total_len <= kHalf) return TALFE_ERR_TOO_SHORT;
+        if (job->frame0 + job->n_frames > 1 + job->total_len / kHop) return TALFE_ERR_INVALID;
+    }
+    const int M = plan->n_mels;
+    const long long dense = job->n_frames * M;
+    const long long ors = job->out_row_stride ? job->out_row_stride : dense;
+    if (ors < dense) return TALFE_ERR_INVALID;
+    const WorkspaceLayout w = workspace_layout(M, job->batch, job->n_frames);
+    if (!job->workspace || job->workspace_bytes < w.total) return TALFE_ERR_WORKSPACE;
+    if ((reinterpret_cast<uintptr_t>(job->workspace) & 15) != 0) return TALFE_ERR_WORKSPACE;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(job->stream);
+    unsigned char* ws = reinterpret_cast<unsigned char*>(job->workspace);
+
+    KernelArgs a{};
+    a.wave = job->wave; a.dtype = job->wave_dtype;
+    a.batch = job->batch; a.row_stride = job->row_stride; a.buf_len = job->buf_len; a.origin = job->origin;
+    a.total_len = job->total_len; a.lens = reinterpret_cast<const long long*>(job->lens);
+    a.frame0 = job->frame0; a.n_frames = job->n_frames;
+    a.out = job->out; a.out_row_stride = ors; a.out_layout = job->out_layout; a.eps = job->eps;
+    a.tiles_per_row = w.tiles_per_row; a.n_tiles = w.n_tiles;
+    a.partials = reinterpret_cast<double2*>(ws + w.partials);
+    a.blob = plan->blob_dev; a.blob_bytes = (int)plan->blob_bytes;
+    a.off_tw = (int)plan->off_tw; a.off_w = (int)plan->off_w; a.off_lo = (int)plan->off_lo;
+    a.layout = plan->layout; a.pstride = plan->pstride;
+
+    long long grid = (long long)plan->sm_count * plan->ctas_per_sm;
+    if (grid > w.n_tiles) grid = w.n_tiles;
+    logmel_kernel<<<(unsigned)grid, kThreads, plan->smem_bytes, stream>>>(a);
+    TALFE_CUDA(cudaGetLastError());
+
+    const bool want_stats = job->stats != nullptr || job->norm != TALFE_NORM_NONE;
+    if (!want_stats) return TALFE_OK;
+    double* stats = job->stats ? job->stats : reinterpret_cast<double*>(ws + w.scratch_stats);
+    const bool per_row = job->norm >= TALFE_NORM_ROW_MEAN;
+    const int accumulate = (job->accumulate_stats && job->stats) ? 1 : 0;
+    const long long blocks = per_row ? job->batch : 1;
+    const long long rows_per_block = per_row ? 1 : job->batch;
+    reduce_partials_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a.partials, (w.n_tiles / blocks) * kWarps, a.lens, a.total_len,
+                                                                  a.frame0, a.n_frames, rows_per_block, M, accumulate, stats);
+    TALFE_CUDA(cudaGetLastError());
+    if (job->norm == TALFE_NORM_ROW_MEL_MEAN || job->norm == TALFE_NORM_ROW_MEL_MEANVAR) {
+        double* colpart = reinterpret_cast<double*>(ws + w.colpart);
+        colstats_kernel<<<dim3((unsigned)w.chunks, (unsigned)job->batch), 320, 0, stream>>>(job->out, ors, job->out_layout, job->n_frames, M,
+                                                                                           a.lens, a.total_len, a.frame0, colpart);
+        TALFE_CUDA(cudaGetLastError());
+        colstats_finish_kernel<<<(unsigned)job->batch, 96, 0, stream>>>(colpart, w.chunks, M, accumulate, stats);
+        TALFE_CUDA(cudaGetLastError());
+    }
+    if (job->norm == TALFE_NORM_NONE || job->defer_normalise) return TALFE_OK;
+    // rows keep their zero fill beyond their own length: the sweep derives valid frames from lens
+    apply_stats_kernel<<<dim3(sweep_blocks(plan->sm_count, job->batch, dense), (unsigned)job->batch), 256, 0, stream>>>(
+        job->out, job->batch, job->n_frames, ors, job->out_layout, M, job->norm, stats, nullptr, a.lens, a.frame0);
+    TALFE_CUDA(cudaGetLastError());
+    return TALFE_OK;
+}
+
+int talfe_logmel_forward(const talfe_plan* plan, const void* wave, int wave_dtype, int64_t batch, int64_t n_samples,
+                         int64_t row_stride, float* out, float eps, void* workspace, size_t workspace_bytes, void* stream) {
+    if (n_samples <= kHalf) return TALFE_ERR_TOO_SHORT;
+    talfe_job job{};
+    job.wave = wave; job.wave_dtype = wave_dtype; job.norm = TALFE_NORM_BATCH_MEAN;
+    job.batch = batch; job.row_stride = row_stride; job.buf_len = n_samples; job.origin = 0; job.total_len = n_samples;
+    job.lens = nullptr; job.frame0 = 0; job.n_frames = 1 + n_samples / kHop;
+    job.out = out; job.out_row_stride = 0; job.out_layout = TALFE_LAYOUT_TM; job.accumulate_stats = 0;
+    job.eps = eps; job.defer_normalise = 0; job.stats = nullptr;
+    job.workspace = workspace; job.workspace_bytes = workspace_bytes; job.stream = stream;
+    return talfe_run(plan, &job);
+}
+
+int talfe_apply_stats(const talfe_plan* plan, float* feats, int64_t batch, int64_t n_frames, int64_t out_row_stride,
+                      int out_layout, int norm, const double* stats, const int64_t* valid_frames, void* stream) {
+    if (!plan || !feats || !stats || batch < 1 || n_frames < 1) return TALFE_ERR_INVALID;
+    if (norm <= TALFE_NORM_NONE || norm > TALFE_NORM_ROW_MEL_MEANVAR) return TALFE_ERR_INVALID;
+    const int M = plan->n_mels;
+    const long long dense = n_frames * M;
+    const long long ors = out_row_stride ? out_row_stride : dense;
+    apply_stats_kernel<<<dim3(sweep_blocks(plan->sm_count, batch, dense), (unsigned)batch), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        feats, batch, n_frames, ors, out_layout, M, norm, stats, reinterpret_cast<const long long*>(valid_frames), nullptr, 0);
+    TALFE_CUDA(cudaGetLastError());
+    return TALFE_OK;
+}
+
+// ---- NCCL, resolved at run time so that the library has no link-time dependency on it
+typedef int (*nccl_allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+static nccl_allreduce_fn g_nccl_allreduce = nullptr;
+static std::once_flag g_nccl_once;
+
+int talfe_allreduce_stats(double* stats_dev, int64_t count, void* nccl_comm, void* stream) {
+    if (!stats_dev || count < 1 || !nccl_comm) return TALFE_ERR_INVALID;
+    std::call_once(g_nccl_once, [] {
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (h) g_nccl_allreduce = reinterpret_cast<nccl_allreduce_fn>(dlsym(h, "ncclAllReduce"));
+    });
+    if (!g_nccl_allreduce) return TALFE_ERR_NCCL;
+    // ncclDouble = 8 (ncclFloat64), ncclSum = 0 in every NCCL 2.x release
+    const int rc = g_nccl_allreduce(stats_dev, stats_dev, (size_t)count, 8, 0, nccl_comm, reinterpret_cast<cudaStream_t>(stream));
+    return rc == 0 ? TALFE_OK : TALFE_ERR_NCCL;
+}
+
+int talfe_synth_fill(void* wave, int wave_dtype, int64_t rows, int64_t n_samples, int64_t row_stride, uint64_t seed,
+                     int64_t first_episode, int64_t start, void* stream) {
+    if (!wave || rows < 1 || n_samples < 1 || row_stride < n_samples) return TALFE_ERR_INVALID;
+    if (wave_dtype < TALFE_F32 || wave_dtype > TALFE_I16) return TALFE_ERR_INVALID;
+    const long long total = rows * n_samples;
+    const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148 * 16);
+    synth_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(wave, wave_dtype, rows, n_samples, row_stride, seed,
+                                                                         first_episode, start);
+    TALFE_CUDA(cudaGetLastError());
+    return TALFE_OK;
+}
+
+}  // extern "C"

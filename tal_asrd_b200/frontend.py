@@ -1,0 +1,267 @@
+"""Host-side mirror of the reference's feature-extraction interface.
+
+``LogMelSpec`` here has the constructor, call signature, output shape/dtype/contiguity, error
+behaviour and (for checkpoint compatibility) buffer names of
+``/root/reference/tal/asr/models.py:15-53``; swap it in with
+
+    import tal.asr.models as ref_models
+    ref_models.LogMelSpec = tal_asrd_b200.LogMelSpec          # before constructing ASRModel / SDModel
+    # or, on an existing model:   model.logmelspec = tal_asrd_b200.LogMelSpec(n_mels=80)
+
+and ``ASRModel.extract_features`` (models.py:154-162) / ``SDModel.extract_features`` (:430-438)
+run unchanged.  All arithmetic happens in the sm_100a kernels of ``csrc/talfe.cu`` behind the C ABI
+in ``include/talfe.h``; PyTorch only provides device memory and the current stream.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+DEFAULT_SR = 16000          # /root/reference/tal/asr/data/__init__.py:6
+HOP = 160
+N_FFT = 400
+_NORMS = {"none": _lib.NORM_NONE, "batch": _lib.NORM_BATCH_MEAN, "row": _lib.NORM_ROW_MEAN,
+          "row_mel": _lib.NORM_ROW_MEL_MEAN, "row_mel_var": _lib.NORM_ROW_MEL_MEANVAR}
+_LAYOUTS = {"tm": _lib.LAYOUT_TM, "mt": _lib.LAYOUT_MT}
+_DTYPES = {torch.float32: _lib.F32, torch.float16: _lib.F16, torch.int16: _lib.I16}
+
+
+def num_frames(n_samples: int) -> int:
+    """T = 1 + L // 160; RuntimeError for L <= 200 like the reference's reflect pad."""
+    if n_samples <= N_FFT // 2:
+        raise RuntimeError(f"Argument #4: Padding size should be less than the corresponding input dimension, "
+                           f"but got: padding ({N_FFT // 2}, {N_FFT // 2}) at dimension 2 of input of length {n_samples}")
+    return 1 + n_samples // HOP
+
+
+def reference_tables(n_mels: int = 80, sr: int = DEFAULT_SR):
+    """(window[400], fb[201, n_mels]) evaluated with the same fp32 torch ops as the reference's
+    buffers (torch.hann_window; torchaudio's HTK filterbank recipe), hence bit-identical to them."""
+    n_fft = int(25 / 1000 * sr)
+    window = torch.hann_window(n_fft, periodic=True, dtype=torch.float32)
+    freqs = torch.linspace(0, sr // 2, n_fft // 2 + 1)
+    top = 2595.0 * math.log10(1.0 + (sr // 2) / 700.0)
+    mel_pts = torch.linspace(0.0, top, n_mels + 2)
+    hz_pts = 700.0 * (10.0 ** (mel_pts / 2595.0) - 1.0)
+    width = hz_pts[1:] - hz_pts[:-1]
+    delta = hz_pts.unsqueeze(0) - freqs.unsqueeze(1)
+    fb = torch.clamp(torch.minimum((-1.0 * delta[:, :-2]) / width[:-1], delta[:, 2:] / width[1:]), min=0.0)
+    return window, fb.contiguous()
+
+
+class _Plan:
+    """Owns one talfe_plan (device tables) and frees it with the object."""
+
+    def __init__(self, device: torch.device, n_mels: int, window: torch.Tensor, fb: torch.Tensor):
+        import ctypes
+        self.lib = _lib.load()
+        self.handle = ctypes.c_void_p()
+        self.n_mels = n_mels
+        self.device = device
+        win = window.detach().to("cpu", torch.float32).contiguous()
+        fbc = fb.detach().to("cpu", torch.float32).contiguous()
+        if win.numel() != N_FFT or tuple(fbc.shape) != (N_FFT // 2 + 1, n_mels):
+            raise ValueError("window must have 400 elements and fb must be [201, n_mels]")
+        _lib.check(self.lib.talfe_plan_create(ctypes.byref(self.handle), device.index, n_mels,
+                                              win.data_ptr(), fbc.data_ptr()), "talfe_plan_create")
+
+    def workspace_bytes(self, batch: int, n_frames: int) -> int:
+        return int(self.lib.talfe_workspace_bytes(self.handle, batch, n_frames))
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.lib.talfe_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+def _require_cuda(t: torch.Tensor) -> torch.device:
+    if not t.is_cuda:
+        raise RuntimeError("tal_asrd_b200 front end runs only on a CUDA device (sm_100a); "
+                           "there is no CPU implementation — move the waveform to the GPU")
+    return t.device
+
+
+def _run(plan: _Plan, audio: torch.Tensor, *, norm: int, layout: int, eps: float, lens: Optional[torch.Tensor],
+         origin: int = 0, total_len: Optional[int] = None, frame0: int = 0, n_frames: Optional[int] = None,
+         out: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None, accumulate: bool = False,
+         defer: bool = False) -> torch.Tensor:
+    device = audio.device
+    B, buf_len = audio.shape
+    if total_len is None:
+        total_len = buf_len
+    if n_frames is None:
+        n_frames = num_frames(total_len) - frame0
+    M = plan.n_mels
+    shape = (B, n_frames, M) if layout == _lib.LAYOUT_TM else (B, M, n_frames)
+    if out is None:
+        out = torch.empty(shape, dtype=torch.float32, device=device)
+    elif tuple(out.shape) != shape or out.dtype != torch.float32 or not out.is_contiguous() or out.device != device:
+        raise ValueError(f"out must be a contiguous float32 tensor of shape {shape} on {device}")
+    ws_bytes = plan.workspace_bytes(B, n_frames)
+    workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+    job = _lib.Job()
+    job.wave = audio.data_ptr()
+    job.wave_dtype = _DTYPES[audio.dtype]
+    job.norm = norm
+    job.batch = B
+    job.row_stride = audio.stride(0) if B > 1 else max(audio.stride(0), buf_len)
+    job.buf_len = buf_len
+    job.origin = origin
+    job.total_len = total_len
+    job.lens = lens.data_ptr() if lens is not None else None
+    job.frame0 = frame0
+    job.n_frames = n_frames
+    job.out = out.data_ptr()
+    job.out_row_stride = 0
+    job.out_layout = layout
+    job.accumulate_stats = 1 if accumulate else 0
+    job.eps = eps
+    job.defer_normalise = 1 if defer else 0
+    job.stats = stats.data_ptr() if stats is not None else None
+    job.workspace = workspace.data_ptr()
+    job.workspace_bytes = ws_bytes
+    with torch.cuda.device(device):
+        job.stream = torch.cuda.current_stream(device).cuda_stream
+        _lib.check(plan.lib.talfe_run(plan.handle, job), "talfe_run")
+    return out
+
+
+def _prepare_audio(audio: torch.Tensor) -> torch.Tensor:
+    if audio.dim() != 2:
+        raise ValueError(f"audio must be [batch, audio_len] (tal/asr/models.py:36-40), got shape {tuple(audio.shape)}")
+    if audio.dtype not in _DTYPES:
+        audio = audio.float()
+    if audio.stride(-1) != 1 or (audio.shape[0] > 1 and audio.stride(0) < audio.shape[1]):
+        audio = audio.contiguous()
+    return audio
+
+
+class _Buffers(nn.Module):
+    def __init__(self, name: str, value: torch.Tensor):
+        super().__init__()
+        self.register_buffer(name, value)
+
+
+class _MelTransformBuffers(nn.Module):
+    """Keeps the reference's state_dict keys alive:
+    ``mel_transform.spectrogram.window`` and ``mel_transform.mel_scale.fb``."""
+
+    def __init__(self, window: torch.Tensor, fb: torch.Tensor):
+        super().__init__()
+        self.spectrogram = _Buffers("window", window)
+        self.mel_scale = _Buffers("fb", fb)
+
+
+class LogMelSpec(nn.Module):
+    """Drop-in for ``tal.asr.models.LogMelSpec`` (models.py:15-53) on a B200.
+
+    forward(audio[B, L]) -> float32 [B, 1 + L // 160, n_mels], contiguous, no grad:
+    log(mel_power + eps) minus ONE scalar mean over the whole batch result (models.py:50-52).
+    Input may be float32, float16 (what ``.half()`` callers pass, system.py:92) or int16 PCM.
+    """
+
+    def __init__(self, sr: int = DEFAULT_SR, n_mels: int = 80, eps: float = 1e-6):
+        super().__init__()
+        if int(25 / 1000 * sr) != N_FFT or int(10 / 1000 * sr) != HOP:
+            raise NotImplementedError("the sm_100a kernel is specialised for sr=16000 (n_fft=400, hop=160), "
+                                      "the only rate the reference uses (tal/asr/data/__init__.py:6)")
+        if not 1 <= n_mels <= 80:
+            raise NotImplementedError("n_mels must be in 1..80")
+        window, fb = reference_tables(n_mels, sr)
+        self.mel_transform = _MelTransformBuffers(window, fb)
+        self.sr, self.n_mels, self.eps = sr, n_mels, eps
+        self._plans = {}
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        super()._load_from_state_dict(*args, **kwargs)
+        self._plans = {}                       # tables may have been replaced by checkpoint values
+
+    def _apply(self, fn, *args, **kwargs):
+        self._plans = {}
+        return super()._apply(fn, *args, **kwargs)
+
+    def plan(self, device: torch.device) -> _Plan:
+        key = (device.type, device.index)
+        if key not in self._plans:
+            self._plans[key] = _Plan(device, self.n_mels, self.mel_transform.spectrogram.window,
+                                     self.mel_transform.mel_scale.fb)
+        return self._plans[key]
+
+    @torch.jit.ignore
+    def forward(self, audio: torch.Tensor) -> torch.Tensor:
+        with torch.no_grad():
+            audio = _prepare_audio(audio)
+            device = _require_cuda(audio)
+            num_frames(audio.shape[1])
+            return _run(self.plan(device), audio, norm=_lib.NORM_BATCH_MEAN, layout=_lib.LAYOUT_TM,
+                        eps=self.eps, lens=None)
+
+    @torch.jit.ignore
+    def features(self, audio: torch.Tensor, audio_lens: Optional[torch.Tensor] = None, norm: str = "batch",
+                 layout: str = "tm", out: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None,
+                 defer_normalise: bool = False) -> torch.Tensor:
+        """Extension surface on the same kernels.
+
+        audio_lens  int64 [B] true lengths (what the collaters emit next to the padded batch,
+                    tal/asr/data/aligned.py:246-270).  When given, every row is processed as if it were
+                    alone: own frame count 1 + len // 160, reflection at its own end, frames beyond
+                    written as 0 and excluded from statistics.  Without it rows are taken as padded
+                    (the reference's behaviour).
+        norm        'batch' (reference) | 'none' | 'row' | 'row_mel' | 'row_mel_var'
+        layout      'tm' -> [B, T, M] (reference) | 'mt' -> [B, M, T] (what encode_features wants, models.py:167)
+        stats       optional float64 tensor receiving the statistics block(s) (see include/talfe.h)
+        """
+        with torch.no_grad():
+            audio = _prepare_audio(audio)
+            device = _require_cuda(audio)
+            num_frames(audio.shape[1])
+            lens = None
+            if audio_lens is not None:
+                lens = audio_lens.to(device=device, dtype=torch.int64).contiguous()
+                if lens.numel() != audio.shape[0]:
+                    raise ValueError("audio_lens must have one entry per row")
+            return _run(self.plan(device), audio, norm=_NORMS[norm], layout=_LAYOUTS[layout], eps=self.eps,
+                        lens=lens, out=out, stats=stats, defer=defer_normalise)
+
+    @torch.jit.ignore
+    def forward_host(self, audio_host: torch.Tensor, out_host: Optional[torch.Tensor] = None,
+                     device: Optional[torch.device] = None) -> torch.Tensor:
+        """The same call for HOST buffers (ideally pinned): H2D of the waveforms, forward on the device,
+        D2H of the features into ``out_host``; returns after the copy has completed."""
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        with torch.no_grad():
+            x = audio_host.to(device, non_blocking=True)
+            y = self.forward(x)
+            if out_host is None:
+                out_host = torch.empty(y.shape, dtype=torch.float32, pin_memory=True)
+            out_host.copy_(y, non_blocking=True)
+            torch.cuda.current_stream(device).synchronize()
+        return out_host
+
+    def stats_block(self, device, rows: int = 1) -> torch.Tensor:
+        return torch.zeros(rows, _lib.stats_doubles(self.n_mels), dtype=torch.float64, device=device)
+
+    def apply_stats(self, feats: torch.Tensor, stats: torch.Tensor, norm: str = "batch", layout: str = "tm",
+                    valid_frames: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """In-place normalisation from a statistics block (after streaming or a cross-rank all-reduce)."""
+        device = _require_cuda(feats)
+        if feats.dim() != 3 or feats.dtype != torch.float32 or not feats.is_contiguous():
+            raise ValueError("feats must be a contiguous float32 [B, T, M] / [B, M, T] tensor")
+        B = feats.shape[0]
+        T = feats.shape[1] if layout == "tm" else feats.shape[2]
+        plan = self.plan(device)
+        vf = valid_frames.to(device=device, dtype=torch.int64).contiguous() if valid_frames is not None else None
+        with torch.cuda.device(device):
+            _lib.check(plan.lib.talfe_apply_stats(plan.handle, feats.data_ptr(), B, T, 0, _LAYOUTS[layout], _NORMS[norm],
+                                                  stats.data_ptr(), vf.data_ptr() if vf is not None else None,
+                                                  torch.cuda.current_stream(device).cuda_stream), "talfe_apply_stats")
+        return feats
