@@ -1,0 +1,97 @@
+"""Episode-sharded corpus pass with dataset-level statistics (BASELINE config 5).
+
+The path shards by independent units: frames depend only on their own 400 samples and episodes are
+independent, so each rank (one process per GPU, like the reference's DDP layout,
+``tal/asr/train.py:97-101``) transforms its own episodes with NO data-path communication.  The
+reference's normalisation is rank-local (``mel.mean()`` over the local batch).  The one exchange this
+module adds is the extension the north star asks for: a single all-reduce of the statistics block
+{count, sum, sumsq, per-mel sums, per-mel sumsq} (163 doubles = 1304 B) per corpus pass, over
+``torch.distributed`` (NCCL over NVLink on the GPUs; gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional, Sequence
+
+import torch
+
+
+def shard_episodes(lengths: Sequence[int], world_size: int, rank: int) -> List[int]:
+    """Greedy longest-first assignment balancing total samples per rank; deterministic on every rank.
+    Returns the episode indices owned by ``rank`` in increasing order."""
+    if not 0 <= rank < world_size:
+        raise ValueError("rank out of range")
+    order = sorted(range(len(lengths)), key=lambda i: (-int(lengths[i]), i))
+    load = [0] * world_size
+    owner = [0] * len(lengths)
+    for i in order:
+        r = min(range(world_size), key=lambda q: (load[q], q))
+        owner[i] = r
+        load[r] += int(lengths[i])
+    return [i for i in range(len(lengths)) if owner[i] == rank]
+
+
+class CorpusStats:
+    """Accumulates statistics blocks (layout of include/talfe.h: count, sum, sumsq, per-mel sums,
+    per-mel sumsq) and reduces them across ranks."""
+
+    def __init__(self, n_mels: int = 80, device: Optional[torch.device] = None):
+        self.n_mels = n_mels
+        self.block = torch.zeros(1, 3 + 2 * n_mels, dtype=torch.float64, device=device)
+
+    def add(self, block: torch.Tensor) -> None:
+        self.block += block.reshape(-1, self.block.shape[1]).sum(dim=0, keepdim=True).to(self.block.device)
+
+    def all_reduce(self, group=None) -> "CorpusStats":
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.block, op=dist.ReduceOp.SUM, group=group)
+        return self
+
+    # derived quantities (float64)
+    @property
+    def count(self) -> float:
+        return float(self.block[0, 0])
+
+    @property
+    def mean(self) -> float:
+        return float(self.block[0, 1] / self.block[0, 0])
+
+    @property
+    def var(self) -> float:
+        m = self.block[0, 1] / self.block[0, 0]
+        return float(self.block[0, 2] / self.block[0, 0] - m * m)
+
+    @property
+    def mel_mean(self) -> torch.Tensor:
+        n = self.block[0, 0] / self.n_mels
+        return self.block[0, 3:3 + self.n_mels] / n
+
+    @property
+    def mel_var(self) -> torch.Tensor:
+        n = self.block[0, 0] / self.n_mels
+        mu = self.mel_mean
+        return self.block[0, 3 + self.n_mels:3 + 2 * self.n_mels] / n - mu * mu
+
+
+def corpus_pass(frontend, episodes: Iterable[torch.Tensor], norm: str = "row_mel_var", group=None,
+                keep_features: bool = True, chunk_seconds: float = 30.0):
+    """Transforms this rank's episodes, all-reduces the statistics once, then normalises in place.
+
+    episodes: iterable of 1-D waveforms owned by this rank (host or device).
+    Returns (list of [1, T, M] feature tensors or [], CorpusStats with the GLOBAL sums).
+    """
+    from .streaming import stream_episode
+    device = torch.device("cuda", torch.cuda.current_device())
+    total = CorpusStats(frontend.n_mels, device)
+    feats = []
+    for ep in episodes:
+        block = frontend.stats_block(device)
+        f = stream_episode(frontend, ep, chunk_seconds=chunk_seconds, device=device, norm=norm,
+                           stats=block, normalise=False)
+        total.add(block)
+        if keep_features:
+            feats.append(f)
+    total.all_reduce(group)
+    for f in feats:
+        frontend.apply_stats(f, total.block, norm=norm)
+    return feats, total

@@ -1,0 +1,163 @@
+"""Streaming (config 3) and corpus sharding (config 5): host logic on CPU (gloo, world_size 2) and
+GPU equivalence of chunked streaming with the one-shot transform."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import rel_err
+
+
+def test_chunk_plan_covers_every_frame_once():
+    from tal_asrd_b200.streaming import chunk_plan
+    for L, cf in ((57_600_000, 3000), (16000, 7), (201, 3000), (480_123, 1000), (16000, 1), (3200, 2)):
+        plan = chunk_plan(L, cf)
+        T = 1 + L // 160
+        assert plan[0][0] == 0 and plan[-1][1] == T
+        for (a0, a1, lo, hi), (b0, _, _, _) in zip(plan, plan[1:]):
+            assert a1 == b0
+        for f0, f1, lo, hi in plan:
+            assert 0 <= lo < hi <= L
+            # every source sample of every frame of the chunk (after reflection) is inside [lo, hi)
+            g = np.arange(160 * f0 - 200, 160 * (f1 - 1) + 200)
+            g = np.where(g < 0, -g, g)
+            g = np.where(g >= L, 2 * (L - 1) - g, g)
+            assert g.min() >= lo and g.max() < hi
+            assert hi - lo <= 160 * (f1 - f0) + 240 + 200
+
+
+def test_shard_episodes_partitions_and_balances():
+    from tal_asrd_b200.corpus import shard_episodes
+    rng = np.random.default_rng(0)
+    lengths = rng.integers(16000, 9_600_000, size=97).tolist()
+    for world in (1, 2, 4, 8):
+        shards = [shard_episodes(lengths, world, r) for r in range(world)]
+        assert sorted(sum(shards, [])) == list(range(97))
+        loads = [sum(lengths[i] for i in s) for s in shards]
+        assert max(loads) - min(loads) <= max(lengths)
+    with pytest.raises(ValueError):
+        shard_episodes(lengths, 2, 2)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gloo_worker(rank, world, port, lengths, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tal_asrd_b200.corpus import CorpusStats, shard_episodes
+    mine = shard_episodes(lengths, world, rank)
+    stats = CorpusStats(n_mels=4)
+    for ep in mine:                                   # stand-in feature blocks: deterministic per episode
+        g = torch.Generator().manual_seed(ep)
+        feats = torch.randn(lengths[ep] // 1000, 4, generator=g, dtype=torch.float64) * 2 + 1
+        block = torch.zeros(1, 11, dtype=torch.float64)
+        block[0, 0] = feats.numel()
+        block[0, 1] = feats.sum()
+        block[0, 2] = (feats ** 2).sum()
+        block[0, 3:7] = feats.sum(0)
+        block[0, 7:11] = (feats ** 2).sum(0)
+        stats.add(block)
+    stats.all_reduce()
+    q.put((rank, mine, stats.block.clone().numpy(), stats.mean, stats.var, stats.mel_mean.numpy(), stats.mel_var.numpy()))
+    dist.destroy_process_group()
+
+
+def test_corpus_stats_allreduce_gloo_world2():
+    lengths = [20000, 5000, 9000, 14000, 3000, 11000, 7000]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, lengths, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(res[0][1] + res[1][1]) == list(range(len(lengths)))       # episodes partitioned
+    assert np.array_equal(res[0][2], res[1][2])                              # both ranks hold the global sums
+    allf = []
+    for ep in range(len(lengths)):
+        g = torch.Generator().manual_seed(ep)
+        allf.append(torch.randn(lengths[ep] // 1000, 4, generator=g, dtype=torch.float64) * 2 + 1)
+    allf = torch.cat(allf).numpy()
+    assert abs(res[0][3] - allf.mean()) < 1e-12 and abs(res[0][4] - allf.var()) < 1e-10
+    assert np.allclose(res[0][5], allf.mean(0), atol=1e-12) and np.allclose(res[0][6], allf.var(0), atol=1e-10)
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+def test_streamed_episode_equals_one_shot():
+    """Chunked streaming (host -> device, 30 s chunks with 200-sample halos) must give the one-shot grid."""
+    from oracle import logmel_oracle as O
+    from tal_asrd_b200 import LogMelSpec, synth
+    from tal_asrd_b200.streaming import stream_episode
+    dev = torch.device("cuda:0")
+    mod = LogMelSpec().to(dev)
+    L = 16000 * 200 + 77                                                     # 200 s, ragged tail
+    ep = torch.from_numpy(synth.waveform(2020, 9, 0, L))
+    one = mod(ep[None].to(dev))
+    for chunk_s in (30.0, 7.3, 0.5):
+        got = stream_episode(mod, ep.pin_memory(), chunk_seconds=chunk_s, device=dev)
+        torch.cuda.synchronize()
+        assert got.shape == one.shape
+        assert float((got - one).abs().max()) < 2e-5, chunk_s            # only the summation order of the mean differs
+    got = stream_episode(mod, ep.to(dev), chunk_seconds=11.0)               # device-resident episode
+    assert float((got - one).abs().max()) < 2e-5
+    ref = O.logmel_f64(ep[None, :160 * 300].numpy())                         # oracle on a prefix (interior frames agree up to the mean)
+    d = got[0, :250].cpu().numpy() - ref[0, :250]
+    assert np.abs(d - d.mean()).max() < 1e-4
+    # int16 PCM streamed
+    pcm = torch.from_numpy(synth.pcm16(2020, 9, 0, L))
+    got16 = stream_episode(mod, pcm, chunk_seconds=30.0, device=dev)
+    assert float((got16 - one).abs().max()) < 2e-5
+
+
+@pytest.mark.gpu
+def test_hour_long_episode_streams():
+    """BASELINE config 3 at full size: 1 h = 57.6 M samples -> 360 001 frames, streamed in 30 s chunks."""
+    from tal_asrd_b200 import LogMelSpec, _lib
+    from tal_asrd_b200.streaming import stream_episode
+    dev = torch.device("cuda:0")
+    mod = LogMelSpec().to(dev)
+    L = 57_600_000
+    ep = torch.empty(L, device=dev)
+    _lib.check(_lib.load().talfe_synth_fill(ep.data_ptr(), _lib.F32, 1, L, L, 2020, 1234, 0, None))
+    one = mod(ep[None])
+    got = stream_episode(mod, ep, chunk_seconds=30.0)
+    torch.cuda.synchronize()
+    assert got.shape == (1, 360001, 80)
+    assert float((got - one).abs().max()) < 2e-5
+    assert abs(float(got.double().mean())) < 2e-6
+
+
+@pytest.mark.gpu
+def test_corpus_pass_single_rank_global_cmvn():
+    from oracle import logmel_oracle as O
+    from tal_asrd_b200 import LogMelSpec, synth
+    from tal_asrd_b200.corpus import corpus_pass
+    dev = torch.device("cuda:0")
+    torch.cuda.set_device(0)
+    mod = LogMelSpec().to(dev)
+    lens = [48000, 100000, 16001]
+    eps_ = [torch.from_numpy(synth.waveform(1, i, 0, n)) for i, n in enumerate(lens)]
+    feats, stats = corpus_pass(mod, eps_, norm="row_mel_var", chunk_seconds=2.0)
+    torch.cuda.synchronize()
+    raw = np.concatenate([O.logmel_unnormalised_f64(e[None].numpy())[0] for e in eps_])
+    assert stats.count == raw.size
+    assert np.allclose(stats.mel_mean.cpu().numpy(), raw.mean(0), atol=1e-5)
+    assert np.allclose(stats.mel_var.cpu().numpy(), raw.var(0), rtol=1e-4)
+    got = np.concatenate([f[0].cpu().numpy() for f in feats])
+    want = (raw - raw.mean(0)) / raw.std(0)
+    assert rel_err(got, want) < 5e-4
