@@ -14,7 +14,7 @@
 using namespace talfe;
 
 extern "C" int talfe_emul_logmel(const float* x, int64_t n_samples, int n_mels, const float* window,
-                                 const float* fb, float eps, float* out /* [T][n_mels] un-normalised */) {
+                                 const float* fb, float eps, int force_generic, float* out /* [T][n_mels] un-normalised */) {
     if (n_samples <= kHalf) return -2;
     std::vector<float> win(kNfft), fbv;
     if (window) win.assign(window, window + kNfft); else default_window(win.data());
@@ -23,7 +23,7 @@ extern "C" int talfe_emul_logmel(const float* x, int64_t n_samples, int n_mels, 
     int rc = build_tables(n_mels, win.data(), fbv.data(), t);
     if (rc) return rc;
     const int64_t T = 1 + n_samples / kHop;
-    std::vector<float> xs(kNfft + kHop);
+    std::vector<float> xs(xskew(kNfft + kHop - 1) + 1);
     std::vector<cf> e(kEGroup), p2(t.pstride);
     const cf* tw = reinterpret_cast<const cf*>(t.tw_t.data());
     for (int64_t t0 = 0; t0 < T; t0 += 2) {
@@ -31,20 +31,25 @@ extern "C" int talfe_emul_logmel(const float* x, int64_t n_samples, int n_mels, 
             int64_t g = kHop * t0 - kHalf + i;
             if (g < 0) g = -g;
             if (g >= n_samples) g = 2 * (n_samples - 1) - g;
-            xs[i] = (g >= 0 && g < n_samples) ? x[g] : 0.f;
+            xs[xskew(i)] = (g >= 0 && g < n_samples) ? x[g] : 0.f;
         }
         for (auto& v : e) v = make_float2(0.f, 0.f);
         for (auto& v : p2) v = make_float2(0.f, 0.f);
         for (int j = 0; j < 20; ++j) stage1(j, xs.data(), t.win_t.data(), tw, e.data());
-        for (int c = 0; c < 20; ++c) {
+        for (int row = 0; row < 20; ++row) {
             cf v[20];
-            stage2_load(c, e.data(), v);
-            if (c == 0 || c == 10) stage2_special(c, v, reinterpret_cast<float*>(p2.data()));
-            else stage2_normal(c, v, reinterpret_cast<float*>(p2.data()));
+            stage2_load(row, e.data(), v);
+            if (row >= 18) stage2_special(row, v, reinterpret_cast<float*>(p2.data()));
+            else stage2_normal(row, v, reinterpret_cast<float*>(p2.data()));
         }
         for (int c = 0; c < 20; ++c) {
             float y[2 * kMelSlots];
-            mel_log(c, t.layout, p2.data(), t.w_t.data(), t.mel_lo.data(), eps, y);
+            if (is_reference_layout(t.layout) && !force_generic) {
+                const int lo[kMelSlots] = {t.mel_lo[c], t.mel_lo[c + 20], t.mel_lo[c + 40], t.mel_lo[c + 60]};
+                mel_log_ref(c, p2.data(), t.w_t.data(), lo, eps, y);
+            } else {
+                mel_log_generic(c, t.layout, p2.data(), t.w_t.data(), t.mel_lo.data(), eps, y);
+            }
             for (int i = 0; i < t.layout.n_slots; ++i) {
                 const int m = c + 20 * i;
                 if (m >= n_mels) continue;

@@ -34,6 +34,7 @@ constexpr int kThreads = kGroupsPerCta * kGroup;            // 320
 constexpr int kWarps = kThreads / 32;                       // 10
 constexpr int kFramesPerTile = 2 * kGroupsPerCta;           // 32
 constexpr int kTileSamples = kHop * kFramesPerTile + (kNfft - kHop);   // 5360
+constexpr int kXFloats = (kTileSamples + kXSkew * ((kTileSamples - 1) / kXBlock) + 3) & ~3;   // skewed tile, 5680
 constexpr int kNormalThreads = 18 * kGroupsPerCta;          // 288 = 9 full warps; warp 9 = packed rows 0/10
 constexpr int kColChunk = 2048;                             // frames per block in the per-mel statistics pass
 static_assert(kNormalThreads % 32 == 0, "special rows must fill whole warps");
@@ -45,6 +46,7 @@ struct talfe_plan_impl {
     int n_mels;
     int sm_count;
     int ctas_per_sm;
+    int ref_layout;                // 80-mel reference filterbank shape -> fully unrolled mel stage
     MelLayout layout;
     int pstride;
     size_t off_tw, off_w, off_lo, blob_bytes;
@@ -63,7 +65,9 @@ struct KernelArgs {
     int out_layout;
     float eps;
     long long tiles_per_row, n_tiles;
-    double2* partials;             // [n_tiles][kWarps]
+    double2* partials;             // [n_tiles][kWarps] (per-row statistics) or [grid][kWarps]
+    int partials_per_tile;
+    int want_sumsq;
     const unsigned char* blob;
     int blob_bytes, off_tw, off_w, off_lo;
     MelLayout layout;
@@ -77,6 +81,59 @@ __device__ __forceinline__ float load_sample(const void* base, int dtype, long l
 }
 
 // ------------------------------------------------------------------------------------------ K1
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+struct TileInfo {
+    long long row, t0, L, t_end;
+    bool active;                   // the tile has at least one frame the row really owns
+};
+
+__device__ __forceinline__ TileInfo tile_info(const KernelArgs& a, long long tile) {
+    TileInfo ti;
+    ti.row = tile / a.tiles_per_row;
+    ti.t0 = a.frame0 + (tile - ti.row * a.tiles_per_row) * kFramesPerTile;
+    ti.L = a.lens ? a.lens[ti.row] : a.total_len;
+    const long long T_row = ti.L > kHalf ? 1 + ti.L / kHop : 0;         // frames this row really has
+    ti.t_end = min(a.frame0 + a.n_frames, T_row);                       // valid frames are t < t_end
+    ti.active = ti.t0 < ti.t_end;
+    return ti;
+}
+
+// Stage 0: waveform tile -> shared memory, skewed layout (talfe_core.cuh).  Interior tiles of an
+// aligned fp32 row go through cp.async (asynchronous; completion is awaited at the top of the
+// iteration that consumes the tile); edge tiles (reflection), narrow dtypes and unaligned rows take
+// the synchronous element-wise path.
+__device__ __forceinline__ void load_tile(const KernelArgs& a, const TileInfo& ti, float* s_x, int tid) {
+    if (!ti.active) return;
+    const long long s0 = kHop * ti.t0 - kHalf;                          // episode index of tile sample 0
+    const long long b0 = s0 - a.origin;                                 // buffer index of tile sample 0
+    const char* rowp = reinterpret_cast<const char*>(a.wave) + ti.row * a.row_stride * (a.dtype == TALFE_F32 ? 4 : 2);
+    const bool interior = s0 >= 0 && s0 + kTileSamples <= ti.L && b0 >= 0 && b0 + kTileSamples <= a.buf_len;
+    if (interior && a.dtype == TALFE_F32 &&
+        ((reinterpret_cast<unsigned long long>(rowp) + 4ull * (unsigned long long)b0) & 15ull) == 0) {
+        const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(rowp) + b0);
+        float4* dst = reinterpret_cast<float4*>(s_x);
+        for (int q = tid; q < kTileSamples / 4; q += kThreads) cp_async_16(dst + q + (kXSkew / 4) * (q / (kXBlock / 4)), src + q);
+    } else {
+        for (int i = tid; i < kTileSamples; i += kThreads) {
+            long long g = s0 + i;
+            if (g < 0) g = -g;                                          // reflect, no edge repeat
+            if (g >= ti.L) g = 2 * (ti.L - 1) - g;
+            const long long bi = g - a.origin;
+            float v = 0.f;
+            if (g >= 0 && g < ti.L && bi >= 0 && bi < a.buf_len) v = load_sample(rowp, a.dtype, bi);
+            s_x[xskew(i)] = v;
+        }
+    }
+}
+
+template <bool kRef>
 __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const KernelArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     // shared-memory carve-up (all offsets multiples of 16 bytes)
@@ -85,85 +142,73 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const KernelArgs a)
     const float* s_w = reinterpret_cast<const float*>(smem + a.off_w);
     const int* s_lo = reinterpret_cast<const int*>(smem + a.off_lo);
     float* s_x = reinterpret_cast<float*>(smem + a.blob_bytes);
-    cf* s_e = reinterpret_cast<cf*>(s_x + ((kTileSamples + 3) & ~3));
+    cf* s_e = reinterpret_cast<cf*>(s_x + kXFloats);
     cf* s_p = s_e + kGroupsPerCta * kEGroup;
 
     const int tid = threadIdx.x;
+    long long tile = blockIdx.x;
+    TileInfo ti = tile_info(a, tile < a.n_tiles ? tile : 0);
+    if (tile < a.n_tiles) load_tile(a, ti, s_x, tid);                   // first tile in flight while tables load
     {   // constant tables -> shared memory; power array (incl. its padding) zeroed once
         const int4* src = reinterpret_cast<const int4*>(a.blob);
         int4* dst = reinterpret_cast<int4*>(smem);
         for (int i = tid; i < a.blob_bytes / 16; i += kThreads) dst[i] = __ldg(src + i);
         for (int i = tid; i < kGroupsPerCta * a.pstride; i += kThreads) s_p[i] = make_float2(0.f, 0.f);
     }
-    // roles
-    const int g1 = tid / kGroup, j = tid - g1 * kGroup;                 // stage 1 and mel stage
-    int g2, c;                                                          // stage 2
-    if (tid < kNormalThreads) { g2 = tid / 18; int r = tid - g2 * 18; c = r < 9 ? r + 1 : r + 2; }
-    else { int s = tid - kNormalThreads; g2 = s >> 1; c = (s & 1) ? 10 : 0; }
+    __syncthreads();
+    // roles: stage 1 and the mel stage use (pair g1, lane j); stage 2 uses (pair g2, exchange row)
+    const int g1 = tid / kGroup, j = tid - g1 * kGroup;
+    int g2, row;
+    if (tid < kNormalThreads) { g2 = tid / 18; row = tid - g2 * 18; }
+    else { const int s = tid - kNormalThreads; g2 = s >> 1; row = 18 + (s & 1); }
     const int warp = tid >> 5, lane = tid & 31;
     const int M = a.layout.n_mels;
+    const float* xg = s_x + kXGroup * g1;
+    cf* e1 = s_e + g1 * kEGroup;
+    const cf* e2 = s_e + g2 * kEGroup;
+    float* p2w = reinterpret_cast<float*>(s_p + g2 * a.pstride);
+    const cf* p2r = s_p + g1 * a.pstride;
+    int lo[kMelSlots];
+#pragma unroll
+    for (int i = 0; i < kMelSlots; ++i) lo[i] = s_lo[min(j + 20 * i, M - 1)];
+    double acc_s = 0.0, acc_q = 0.0;                                    // per-thread sums when partials are per CTA
 
-    for (long long tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-        const long long row = tile / a.tiles_per_row;
-        const long long tq = tile - row * a.tiles_per_row;
-        const long long t0 = a.frame0 + tq * kFramesPerTile;            // first frame of the tile
-        const long long L = a.lens ? a.lens[row] : a.total_len;
-        const long long T_row = L > kHalf ? 1 + L / kHop : 0;           // frames this row really has
-        const long long t_end = min(a.frame0 + a.n_frames, T_row);      // valid frames are t < t_end
-        float* out_row = a.out + row * a.out_row_stride;
-
+    for (; tile < a.n_tiles; tile += gridDim.x) {
+        cp_async_wait_all();
+        __syncthreads();                                                // B1: tile samples visible to all
+        if (ti.active) stage1(j, xg, s_win, s_tw, e1);
+        __syncthreads();                                                // B2: exchange rows complete, s_x dead
+        const TileInfo cur = ti;
+        if (tile + gridDim.x < a.n_tiles) {                             // prefetch overlaps stage 2 + mel
+            ti = tile_info(a, tile + gridDim.x);
+            load_tile(a, ti, s_x, tid);
+        }
+        if (cur.active) {
+            cf v[20];
+            stage2_load(row, e2, v);
+            if (tid < kNormalThreads) stage2_normal(row, v, p2w);
+            else stage2_special(row, v, p2w);
+        }
+        __syncthreads();                                                // B3: power spectra complete
+        float* out_row = a.out + cur.row * a.out_row_stride;
         float sum = 0.f, sumsq = 0.f;
-        if (t0 < t_end) {
-            // ---- stage 0: waveform tile -> shared memory (each sample read from HBM once per tile)
-            const long long s0 = kHop * t0 - kHalf;                     // episode index of s_x[0]
-            const long long b0 = s0 - a.origin;                         // buffer index of s_x[0]
-            const char* rowp = reinterpret_cast<const char*>(a.wave) +
-                               row * a.row_stride * (a.dtype == TALFE_F32 ? 4 : 2);
-            const bool interior = s0 >= 0 && s0 + kTileSamples <= L && b0 >= 0 && b0 + kTileSamples <= a.buf_len;
-            if (interior && a.dtype == TALFE_F32 &&
-                ((reinterpret_cast<unsigned long long>(rowp) + 4ull * (unsigned long long)b0) & 15ull) == 0) {
-                const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(rowp) + b0);
-                float4* dst = reinterpret_cast<float4*>(s_x);
-                for (int i = tid; i < kTileSamples / 4; i += kThreads) dst[i] = __ldg(src + i);
-            } else {
-                for (int i = tid; i < kTileSamples; i += kThreads) {
-                    long long g = s0 + i;
-                    if (g < 0) g = -g;                                  // reflect, no edge repeat
-                    if (g >= L) g = 2 * (L - 1) - g;
-                    const long long bi = g - a.origin;
-                    float v = 0.f;
-                    if (g >= 0 && g < L && bi >= 0 && bi < a.buf_len) v = load_sample(rowp, a.dtype, bi);
-                    s_x[i] = v;
-                }
-            }
-            __syncthreads();
-            // ---- stage 1: windowed real FFT-20 of both frames of the pair, twiddle, exchange
-            stage1(j, s_x + 2 * kHop * g1, s_win, s_tw, s_e + g1 * kEGroup);
-            __syncthreads();
-            // ---- stage 2: FFT-20 across the group, power spectrum into s_p
-            {
-                cf v[20];
-                stage2_load(c, s_e + g2 * kEGroup, v);
-                float* p2 = reinterpret_cast<float*>(s_p + g2 * a.pstride);
-                if (tid < kNormalThreads) stage2_normal(c, v, p2);
-                else stage2_special(c, v, p2);
-            }
-            __syncthreads();
-            // ---- mel projection, log, store, statistics
+        if (cur.active) {
             float y[2 * kMelSlots];
-            mel_log(j, a.layout, s_p + g1 * a.pstride, s_w, s_lo, a.eps, y);
-            const long long ta = t0 + 2 * g1;
+            if (kRef) mel_log_ref(j, p2r, s_w, lo, a.eps, y);
+            else mel_log_generic(j, a.layout, p2r, s_w, s_lo, a.eps, y);
+            const long long ta = cur.t0 + 2 * g1;
 #pragma unroll
             for (int f = 0; f < 2; ++f) {
                 const long long t = ta + f;
                 if (t < a.frame0 + a.n_frames) {
-                    const bool valid = t < t_end;
+                    const bool valid = t < cur.t_end;
 #pragma unroll
                     for (int i = 0; i < kMelSlots; ++i) {
                         const int m = j + 20 * i;
-                        if (m < M) {
+                        if (kRef || m < M) {
                             const float v = valid ? y[2 * i + f] : 0.f;
-                            if (valid) { sum += v; sumsq = fmaf(v, v, sumsq); }
+                            sum += v;
+                            if (a.want_sumsq) sumsq = fmaf(v, v, sumsq);
                             if (a.out_layout == TALFE_LAYOUT_TM) out_row[(t - a.frame0) * M + m] = v;
                             else out_row[(long long)m * a.n_frames + (t - a.frame0)] = v;
                         }
@@ -172,23 +217,35 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const KernelArgs a)
             }
         } else {
             // tile lies entirely beyond this row's own frames ("each row as if alone"): zero fill
-            const long long nfr = min((long long)kFramesPerTile, a.frame0 + a.n_frames - t0);
+            const long long nfr = min((long long)kFramesPerTile, a.frame0 + a.n_frames - cur.t0);
             for (long long i = tid; i < nfr * M; i += kThreads) {
                 const long long f = i / M, m = i - f * M;
-                if (a.out_layout == TALFE_LAYOUT_TM) out_row[(t0 - a.frame0 + f) * M + m] = 0.f;
-                else out_row[m * a.n_frames + (t0 - a.frame0 + f)] = 0.f;
+                if (a.out_layout == TALFE_LAYOUT_TM) out_row[(cur.t0 - a.frame0 + f) * M + m] = 0.f;
+                else out_row[m * a.n_frames + (cur.t0 - a.frame0 + f)] = 0.f;
             }
         }
-        // per-warp partial sums (fixed shuffle tree -> bit-reproducible), one slot per (tile, warp)
-        double ds = (double)sum, dq = (double)sumsq;
+        if (a.partials_per_tile) {
+            // per-warp partial sums (fixed shuffle tree -> bit-reproducible), one slot per (tile, warp)
+            double ds = (double)sum, dq = (double)sumsq;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                ds += __shfl_xor_sync(0xffffffffu, ds, o);
+                dq += __shfl_xor_sync(0xffffffffu, dq, o);
+            }
+            if (lane == 0) a.partials[tile * kWarps + warp] = make_double2(ds, dq);
+        } else {
+            acc_s += (double)sum;
+            acc_q += (double)sumsq;
+        }
+        // the prefetch above already targets s_x; s_e / s_p are rewritten only after the next B1 / B2
+    }
+    if (!a.partials_per_tile) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            ds += __shfl_xor_sync(0xffffffffu, ds, o);
-            dq += __shfl_xor_sync(0xffffffffu, dq, o);
+            acc_s += __shfl_xor_sync(0xffffffffu, acc_s, o);
+            acc_q += __shfl_xor_sync(0xffffffffu, acc_q, o);
         }
-        if (lane == 0) a.partials[tile * kWarps + warp] = make_double2(ds, dq);
-        // the next iteration's stage 0 overwrites s_x, which nobody reads after the stage-1 barrier;
-        // s_e / s_p are rewritten only after the next two barriers.
+        if (lane == 0) a.partials[(long long)blockIdx.x * kWarps + warp] = make_double2(acc_s, acc_q);
     }
 }
 
@@ -440,13 +497,15 @@ int talfe_plan_create(talfe_plan** plan_out, int device, int n_mels, const float
     p->layout = t.layout;
     p->pstride = t.pstride;
     p->off_tw = t.off_tw; p->off_w = t.off_w; p->off_lo = t.off_lo; p->blob_bytes = t.blob_bytes;
-    p->smem_bytes = t.blob_bytes + (size_t)((kTileSamples + 3) & ~3) * sizeof(float) +
+    p->ref_layout = is_reference_layout(t.layout) ? 1 : 0;
+    p->smem_bytes = t.blob_bytes + (size_t)kXFloats * sizeof(float) +
                     (size_t)kGroupsPerCta * kEGroup * sizeof(cf) + (size_t)kGroupsPerCta * t.pstride * sizeof(cf);
     cudaError_t e = cudaMalloc(&p->blob_dev, t.blob_bytes);
     if (e == cudaSuccess) e = cudaMemcpy(p->blob_dev, t.blob.data(), t.blob_bytes, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, device);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p->ctas_per_sm, logmel_kernel, kThreads, p->smem_bytes);
+    auto kern = p->ref_layout ? logmel_kernel<true> : logmel_kernel<false>;
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p->ctas_per_sm, kern, kThreads, p->smem_bytes);
     cudaSetDevice(prev);
     if (e != cudaSuccess) { if (p->blob_dev) cudaFree(p->blob_dev); delete p; return cuda_fail(e); }
     if (p->ctas_per_sm < 1) { cudaFree(p->blob_dev); delete p; return TALFE_ERR_UNSUPPORTED; }
@@ -502,17 +561,21 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
 
     long long grid = (long long)plan->sm_count * plan->ctas_per_sm;
     if (grid > w.n_tiles) grid = w.n_tiles;
-    logmel_kernel<<<(unsigned)grid, kThreads, plan->smem_bytes, stream>>>(a);
+    const bool want_stats = job->stats != nullptr || job->norm != TALFE_NORM_NONE;
+    const bool per_row = job->norm >= TALFE_NORM_ROW_MEAN;
+    a.partials_per_tile = per_row ? 1 : 0;                // batch-wide sums: one slot per (CTA, warp) is enough
+    a.want_sumsq = want_stats ? 1 : 0;
+    if (plan->ref_layout) logmel_kernel<true><<<(unsigned)grid, kThreads, plan->smem_bytes, stream>>>(a);
+    else logmel_kernel<false><<<(unsigned)grid, kThreads, plan->smem_bytes, stream>>>(a);
     TALFE_CUDA(cudaGetLastError());
 
-    const bool want_stats = job->stats != nullptr || job->norm != TALFE_NORM_NONE;
     if (!want_stats) return TALFE_OK;
     double* stats = job->stats ? job->stats : reinterpret_cast<double*>(ws + w.scratch_stats);
-    const bool per_row = job->norm >= TALFE_NORM_ROW_MEAN;
     const int accumulate = (job->accumulate_stats && job->stats) ? 1 : 0;
     const long long blocks = per_row ? job->batch : 1;
     const long long rows_per_block = per_row ? 1 : job->batch;
-    reduce_partials_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a.partials, (w.n_tiles / blocks) * kWarps, a.lens, a.total_len,
+    const long long slots_per_block = per_row ? w.tiles_per_row * kWarps : grid * kWarps;
+    reduce_partials_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a.partials, slots_per_block, a.lens, a.total_len,
                                                                   a.frame0, a.n_frames, rows_per_block, M, accumulate, stats);
     TALFE_CUDA(cudaGetLastError());
     if (job->norm == TALFE_NORM_ROW_MEL_MEAN || job->norm == TALFE_NORM_ROW_MEL_MEANVAR) {

@@ -2,7 +2,7 @@
 //
 // Everything here is __host__ __device__ and free of CUDA built-ins so that the exact code the
 // kernel inlines can also be driven, "thread" by "thread", by the host emulator in
-// csrc/host_emul.cpp (CPU unit test of index maps and arithmetic; it is NOT a product path).
+// csrc/host_emul.cu (CPU unit test of index maps and arithmetic; it is NOT a product path).
 //
 // Path being implemented (reference: /root/reference/tal/asr/models.py:22-53, whose arithmetic
 // is torchaudio MelSpectrogram(n_fft=400, win=400, hop=160, n_mels=80) -> log(.+eps)):
@@ -14,18 +14,25 @@
 //
 //   stage 1 (thread j):  ONE complex FFT-20 of (xa + i xb)[j + 20 m] yields, by conjugate
 //                        symmetry, the real-input FFT-20 of both frames: A_a[k1], A_b[k1],
-//                        k1 = 0..10.  Twiddle by W400^(j k1).  Rows for stage 2:
-//                          row 0      : A_a[0] + i A_b[0]            (both real  -> packed)
-//                          row 1..9   : A_a[k1] W^(j k1)             (frame a)
-//                          row 10     : (A_a[10] + i A_b[10]) W^(10 j) (both real -> packed)
-//                          row 11..19 : A_b[k1-10] W^(j (k1-10))     (frame b)
-//   stage 2 (thread c = row): complex FFT-20 over j.  Rows 1..9 / 11..19 give 20 spectrum bins
-//                        of one frame each (k = k1 + 20 k2 for k2 < 10, and 400 - k by conjugate
-//                        symmetry for k2 >= 10); rows 0 and 10 give bins 20 q and 10 + 20 q of
-//                        BOTH frames after an in-register untangle.  Exactly 20 FFTs for 20
-//                        threads, 199 power bins per frame, no second exchange.
+//                        k1 = 0..10.  Twiddle by W400^(j k1).  Exchange rows for stage 2:
+//                          row 2(k1-1)   : A_a[k1] W^(j k1)   k1 = 1..9       (frame a)
+//                          row 2(k1-1)+1 : A_b[k1] W^(j k1)   k1 = 1..9       (frame b)
+//                          row 18        : A_a[0] + i A_b[0]                  (both real -> packed)
+//                          row 19        : (A_a[10] + i A_b[10]) W^(10 j)     (both real -> packed)
+//   stage 2 (thread = row): complex FFT-20 over j.  Rows 0..17 give 20 spectrum bins of one frame
+//                        each (k = k1 + 20 q for output q < 10, and 400 - k by conjugate symmetry
+//                        for q >= 10); rows 18 and 19 give bins 20 q and 10 + 20 q of BOTH frames
+//                        after an in-register untangle.  Exactly 20 FFTs for 20 threads, 199 power
+//                        bins per frame, no second exchange.
 //
 // The FFT-20 itself is a Good-Thomas (prime factor) 4 x 5 split: no internal twiddles.
+//
+// Shared-memory layouts (bank-conflict analysis in DESIGN.md §4):
+//   waveform tile : sample i of the tile lives at i + 20 * (i / 320)  -> thread (g, j) reads word
+//                   340 g + j + const, i.e. consecutive lanes hit consecutive banks;
+//   exchange      : row stride 22 complex, group stride 452 complex (904 words = 8 mod 32);
+//   power         : float2 (P_a[k], P_b[k]) at index k, group stride `pstride` = 9 (mod 16) so that
+//                   lane r of group g writes word 18 g + r + const.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -43,10 +50,15 @@ constexpr int kBins = 201;
 constexpr int kGroup = 20;            // threads per frame pair
 constexpr int kMaxMels = 80;
 constexpr int kMelSlots = 4;          // mel m is owned by thread m % 20, slot m / 20
-constexpr int kPStride = 212;         // power bins per pair in shared memory (float2 each), padded
 constexpr int kERow = 22;             // exchange row stride in float2 (20 + 2 pad -> conflict-free LDS.128)
 constexpr int kEGroup = 452;          // exchange group stride in float2 (= 904 words, 8 mod 32)
-constexpr int kMaxWeightsPerThread = 32;
+constexpr int kXBlock = 320;          // waveform tile: a skew of kXSkew floats after every kXBlock samples
+constexpr int kXSkew = 20;
+constexpr int kXGroup = kXBlock + kXSkew;   // 340: distance between the first samples of consecutive pairs
+
+// the reference configuration (80 HTK mels): common widths per slot, compile-time unrolled
+constexpr int kRefW0 = 2, kRefW1 = 4, kRefW2 = 7, kRefW3 = 13;
+constexpr int kRefWStride = 28;
 
 typedef float2 cf;
 
@@ -99,66 +111,75 @@ TALFE_HD void fft20(cf (&v)[20]) {
     }
 }
 
+// position of tile sample i inside the skewed waveform buffer
+TALFE_HD int xskew(int i) { return i + kXSkew * (i / kXBlock); }
+
 // ---------------------------------------------------------------------------------------------
-// Stage 1.  xs points at the first sample of frame a inside the staged tile (frame b starts kHop
-// later).  win_t[j*20 + m] = 0.5 * hann[j + 20 m]  (the 0.5 makes A_a = C[k] + conj C[20-k] exact
-// scale); tw_t[j*10 + (k1-1)] = W400^(j k1) for k1 = 1..9 and 2 * W400^(10 j) for k1 = 10.
+// Stage 1.  xg points at this pair's first sample inside the skewed tile (s_x + kXGroup * g);
+// frame a = samples 0..399 of the pair, frame b = samples 160..559.
+// win_t[j*20 + m] = 0.5 * hann[j + 20 m]  (the 0.5 makes A_a = C[k] + conj C[20-k] exact scale);
+// tw_t[j*10 + (k1-1)] = W400^(j k1) for k1 = 1..9 and 2 * W400^(10 j) for k1 = 10.
 // Writes this thread's column j of the 20 exchange rows.
-TALFE_HD void stage1(int j, const float* __restrict__ xs, const float* __restrict__ win_t,
+TALFE_HD void stage1(int j, const float* __restrict__ xg, const float* __restrict__ win_t,
                      const cf* __restrict__ tw_t, cf* __restrict__ e_group) {
     cf z[20];
     const float4* w4 = reinterpret_cast<const float4*>(win_t + j * 20);
+    const float* p = xg + j;
 #pragma unroll
     for (int q = 0; q < 5; ++q) {
-        float4 w = w4[q];
-        const float* p = xs + j + 80 * q;
-        z[4 * q + 0] = make_float2(w.x * p[0], w.x * p[kHop]);
-        z[4 * q + 1] = make_float2(w.y * p[20], w.y * p[20 + kHop]);
-        z[4 * q + 2] = make_float2(w.z * p[40], w.z * p[40 + kHop]);
-        z[4 * q + 3] = make_float2(w.w * p[60], w.w * p[60 + kHop]);
+        const float4 w = w4[q];
+        const float ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int m = 4 * q + u;
+            // sample j + 20 m of frame a, j + 20 m + 160 of the pair for frame b, with the block skew
+            const int ia = 20 * m + (20 * m >= kXBlock ? kXSkew : 0);
+            const int ib = 20 * m + kHop + (20 * m + kHop >= kXBlock ? kXSkew : 0);
+            z[m] = make_float2(ww[u] * p[ia], ww[u] * p[ib]);
+        }
     }
     fft20(z);
     const float4* t4 = reinterpret_cast<const float4*>(tw_t + j * 10);
     cf* col = e_group + j;
-    col[0] = make_float2(2.0f * z[0].x, 2.0f * z[0].y);                 // row 0: A_a[0] + i A_b[0]
+    col[18 * kERow] = make_float2(2.0f * z[0].x, 2.0f * z[0].y);       // row 18: A_a[0] + i A_b[0]
 #pragma unroll
     for (int h = 0; h < 5; ++h) {
-        float4 tt = t4[h];                                              // twiddles k1 = 2h+1, 2h+2
+        const float4 tt = t4[h];                                        // twiddles k1 = 2h+1, 2h+2
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const int k1 = 2 * h + 1 + u;
-            cf w = u == 0 ? make_float2(tt.x, tt.y) : make_float2(tt.z, tt.w);
+            const cf w = u == 0 ? make_float2(tt.x, tt.y) : make_float2(tt.z, tt.w);
             if (k1 < 10) {
-                cf p = z[k1], q = z[20 - k1];
-                cf aa = make_float2(p.x + q.x, p.y - q.y);              // A_a[k1] = C[k1] + conj C[20-k1]
-                cf ab = make_float2(p.y + q.y, q.x - p.x);              // A_b[k1] = (C[k1] - conj C[20-k1]) / i
-                col[k1 * kERow] = cmul(aa, w);
-                col[(k1 + 10) * kERow] = cmul(ab, w);
+                const cf p1 = z[k1], q1 = z[20 - k1];
+                const cf aa = make_float2(p1.x + q1.x, p1.y - q1.y);   // A_a[k1] = C[k1] + conj C[20-k1]
+                const cf ab = make_float2(p1.y + q1.y, q1.x - p1.x);   // A_b[k1] = (C[k1] - conj C[20-k1]) / i
+                col[(2 * (k1 - 1)) * kERow] = cmul(aa, w);
+                col[(2 * (k1 - 1) + 1) * kERow] = cmul(ab, w);
             } else {
-                col[10 * kERow] = cmul(z[10], w);                       // row 10 (w carries the factor 2)
+                col[19 * kERow] = cmul(z[10], w);                       // row 19 (w carries the factor 2)
             }
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// Stage 2.  Thread c transforms exchange row c and writes |X|^2 into the pair's power array
-// p2[k] = (P_a[k], P_b[k]).  `special` (c == 0 or c == 10) rows hold both frames packed.
-TALFE_HD void stage2_load(int c, const cf* __restrict__ e_group, cf (&v)[20]) {
-    const float4* row = reinterpret_cast<const float4*>(e_group + c * kERow);
+// Stage 2.  Thread `row` transforms exchange row `row` and writes |X|^2 into the pair's power array
+// p2[k] = (P_a[k], P_b[k]).  Rows 18 / 19 hold both frames packed.
+TALFE_HD void stage2_load(int row, const cf* __restrict__ e_group, cf (&v)[20]) {
+    const float4* src = reinterpret_cast<const float4*>(e_group + row * kERow);
 #pragma unroll
     for (int q = 0; q < 10; ++q) {
-        float4 r = row[q];
+        const float4 r = src[q];
         v[2 * q] = make_float2(r.x, r.y);
         v[2 * q + 1] = make_float2(r.z, r.w);
     }
 }
 
-TALFE_HD void stage2_normal(int c, cf (&v)[20], float* __restrict__ p2) {
+TALFE_HD void stage2_normal(int row, cf (&v)[20], float* __restrict__ p2) {
     fft20(v);
-    const int frame = c >= 10 ? 1 : 0;
-    const int k1 = c - 10 * frame;                                      // 1..9
-    float* lo = p2 + 2 * k1 + frame;                                    // bins k1 + 20 q
+    const int frame = row & 1;
+    const int k1 = 1 + (row >> 1);                                      // 1..9
+    float* lo = p2 + 2 * k1 + frame;                                    // bins k1 + 20 q          -> word row + 2 + 40 q
     float* hi = p2 + 2 * (20 - k1) + frame;                             // bins (20 - k1) + 20 q
 #pragma unroll
     for (int q = 0; q < 10; ++q) {
@@ -167,19 +188,20 @@ TALFE_HD void stage2_normal(int c, cf (&v)[20], float* __restrict__ p2) {
     }
 }
 
-TALFE_HD void stage2_special(int c, cf (&v)[20], float* __restrict__ p2) {
+TALFE_HD void stage2_special(int row, cf (&v)[20], float* __restrict__ p2) {
     fft20(v);
-    // c == 10: V[q] pairs with V[19-q] -> bins 10 + 20 q.   c == 0: V[q+1] pairs with V[19-q] -> bins 20 (q+1).
-    const bool zero = (c == 0);
+    // row 19: V[q] pairs with V[19-q] -> bins 10 + 20 q.   row 18: V[q+1] pairs with V[19-q] -> bins 20 (q+1).
+    const bool zero = (row == 18);
     cf* out = reinterpret_cast<cf*>(p2) + (zero ? 20 : 10);
 #pragma unroll
     for (int q = 0; q < 10; ++q) {
-        cf p = zero ? v[q + 1] : v[q];
-        cf r = v[19 - q];
-        float ar = p.x + r.x, ai = p.y - r.y;                           // 2 X_a
-        float br = p.x - r.x, bi = p.y + r.y;                           // 2 i X_b
-        // q == 9 with c == 0 is bin 200 (never weighted); it lands in a padding slot.
-        out[20 * q] = make_float2(0.25f * fmaf(ar, ar, ai * ai), 0.25f * fmaf(br, br, bi * bi));
+        const cf p = zero ? v[q + 1] : v[q];
+        const cf r = v[19 - q];
+        const float ar = p.x + r.x, ai = p.y - r.y;                     // 2 X_a
+        const float br = p.x - r.x, bi = p.y + r.y;                     // 2 i X_b
+        // q == 9 on row 18 would be bin 200, which carries no mel weight: not stored (padding stays 0)
+        if (!(zero && q == 9))
+            out[20 * q] = make_float2(0.25f * fmaf(ar, ar, ai * ai), 0.25f * fmaf(br, br, bi * bi));
     }
 }
 
@@ -195,6 +217,11 @@ struct MelLayout {
     int wstride;              // weights per thread (multiple of 4)
 };
 
+TALFE_HD bool is_reference_layout(const MelLayout& ml) {
+    return ml.n_mels == 80 && ml.n_slots == 4 && ml.width[0] == kRefW0 && ml.width[1] == kRefW1 &&
+           ml.width[2] == kRefW2 && ml.width[3] == kRefW3 && ml.wstride == kRefWStride;
+}
+
 TALFE_HD float fast_log(float x) {
 #ifdef __CUDA_ARCH__
     return __logf(x);
@@ -203,8 +230,9 @@ TALFE_HD float fast_log(float x) {
 #endif
 }
 
-TALFE_HD void mel_log(int c, const MelLayout& ml, const cf* __restrict__ p2, const float* __restrict__ w_t,
-                      const int* __restrict__ mel_lo, float eps, float (&y)[2 * kMelSlots]) {
+// generic widths (any n_mels <= 80 / any filterbank with bounded support)
+TALFE_HD void mel_log_generic(int c, const MelLayout& ml, const cf* __restrict__ p2, const float* __restrict__ w_t,
+                              const int* __restrict__ mel_lo, float eps, float (&y)[2 * kMelSlots]) {
     const float* w = w_t + c * ml.wstride;
 #pragma unroll
     for (int i = 0; i < kMelSlots; ++i) {
@@ -214,8 +242,8 @@ TALFE_HD void mel_log(int c, const MelLayout& ml, const cf* __restrict__ p2, con
             const cf* p = p2 + mel_lo[m < ml.n_mels ? m : 0];
             const float* wi = w + ml.offset[i];
             for (int r = 0; r < ml.width[i]; ++r) {
-                cf pw = p[r];
-                float wr = wi[r];
+                const cf pw = p[r];
+                const float wr = wi[r];
                 acc_a = fmaf(wr, pw.x, acc_a);
                 acc_b = fmaf(wr, pw.y, acc_b);
             }
@@ -223,6 +251,35 @@ TALFE_HD void mel_log(int c, const MelLayout& ml, const cf* __restrict__ p2, con
         y[2 * i] = fast_log(acc_a + eps);
         y[2 * i + 1] = fast_log(acc_b + eps);
     }
+}
+
+// reference layout: widths (2, 4, 7, 13), 28 weights per thread fetched as 7 x 128 bit, fully unrolled
+template <int W, int OFF>
+TALFE_HD void mel_slot_ref(const cf* __restrict__ p, const float (&w)[kRefWStride], float eps, float& ya, float& yb) {
+    float acc_a = 0.f, acc_b = 0.f;
+#pragma unroll
+    for (int r = 0; r < W; ++r) {
+        const cf pw = p[r];
+        acc_a = fmaf(w[OFF + r], pw.x, acc_a);
+        acc_b = fmaf(w[OFF + r], pw.y, acc_b);
+    }
+    ya = fast_log(acc_a + eps);
+    yb = fast_log(acc_b + eps);
+}
+
+TALFE_HD void mel_log_ref(int c, const cf* __restrict__ p2, const float* __restrict__ w_t, const int (&lo)[kMelSlots],
+                          float eps, float (&y)[2 * kMelSlots]) {
+    float w[kRefWStride];
+    const float4* w4 = reinterpret_cast<const float4*>(w_t + c * kRefWStride);
+#pragma unroll
+    for (int q = 0; q < kRefWStride / 4; ++q) {
+        const float4 t = w4[q];
+        w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
+    }
+    mel_slot_ref<kRefW0, 0>(p2 + lo[0], w, eps, y[0], y[1]);
+    mel_slot_ref<kRefW1, kRefW0>(p2 + lo[1], w, eps, y[2], y[3]);
+    mel_slot_ref<kRefW2, kRefW0 + kRefW1>(p2 + lo[2], w, eps, y[4], y[5]);
+    mel_slot_ref<kRefW3, kRefW0 + kRefW1 + kRefW2>(p2 + lo[3], w, eps, y[6], y[7]);
 }
 
 }  // namespace talfe

@@ -92,7 +92,7 @@ inline int build_tables(int n_mels, const float* window, const float* fb, HostTa
     L.wstride = (total + 3) & ~3;
     if (L.wstride > 256) return -3;
     t.pstride = 201 + max_w;
-    while (t.pstride % 16 != 4) ++t.pstride;                                       // 2*pstride = 8 (mod 32) words
+    while (t.pstride % 16 != 9) ++t.pstride;                                       // 2*pstride = 18 (mod 32) words
     t.w_t.assign(20 * L.wstride, 0.f);
     t.mel_lo.assign(kMaxMels, 1);
     for (int m = 0; m < n_mels; ++m) {

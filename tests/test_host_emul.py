@@ -28,19 +28,19 @@ def emul():
     lib = ctypes.CDLL(LIB)
     lib.talfe_emul_logmel.restype = ctypes.c_int
     lib.talfe_emul_logmel.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
-                                      ctypes.c_float, ctypes.c_void_p]
+                                      ctypes.c_float, ctypes.c_int, ctypes.c_void_p]
     return lib
 
 
-def emul_logmel(lib, x, n_mels=80, tables=True):
+def emul_logmel(lib, x, n_mels=80, tables=True, generic=0):
     x = np.ascontiguousarray(x, np.float32)
     T = 1 + x.shape[0] // 160
     out = np.zeros((T, n_mels), np.float32)
     if tables:
         win, fb = O.reference_tables(n_mels)
-        rc = lib.talfe_emul_logmel(x.ctypes.data, x.shape[0], n_mels, win.ctypes.data, fb.ctypes.data, 1e-6, out.ctypes.data)
+        rc = lib.talfe_emul_logmel(x.ctypes.data, x.shape[0], n_mels, win.ctypes.data, fb.ctypes.data, 1e-6, generic, out.ctypes.data)
     else:
-        rc = lib.talfe_emul_logmel(x.ctypes.data, x.shape[0], n_mels, None, None, 1e-6, out.ctypes.data)
+        rc = lib.talfe_emul_logmel(x.ctypes.data, x.shape[0], n_mels, None, None, 1e-6, generic, out.ctypes.data)
     assert rc == 0
     return out
 
@@ -80,5 +80,7 @@ def test_emulated_other_mel_counts_and_builtin_tables(emul):
         got = emul_logmel(emul, x, n_mels)
         ref = O.logmel_unnormalised_f64(x[None], n_mels=n_mels)[0]
         assert rel_err(got, ref) < 1e-4, n_mels
+    # the runtime-width mel loop (used for non-reference layouts) agrees with the unrolled one on 80 mels
+    assert np.array_equal(emul_logmel(emul, x, 80, generic=1), emul_logmel(emul, x, 80))
     # tables computed inside the C library (no torch): within tolerance of the reference's fp32 tables
     assert rel_err(emul_logmel(emul, x, 80, tables=False), O.logmel_unnormalised_f64(x[None])[0]) < 1e-4
