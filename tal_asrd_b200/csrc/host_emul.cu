@@ -45,14 +45,14 @@ extern "C" int talfe_emul_logmel(const float* x, int64_t n_samples, int n_mels, 
         for (int c = 0; c < 20; ++c) {
             float y[2 * kMelSlots];
             if (is_reference_layout(t.layout) && !force_generic) {
-                const int lo[kMelSlots] = {t.mel_lo[c], t.mel_lo[c + 20], t.mel_lo[c + 40], t.mel_lo[c + 60]};
+                const int lo[kMelSlots] = {t.mel_lo[c], t.mel_lo[c + 20], t.mel_lo[c + 40], t.mel_lo[c + 60]};   // slot-major
                 mel_log_ref(c, p2.data(), t.w_t.data(), lo, eps, y);
             } else {
                 mel_log_generic(c, t.layout, p2.data(), t.w_t.data(), t.mel_lo.data(), eps, y);
             }
             for (int i = 0; i < t.layout.n_slots; ++i) {
-                const int m = c + 20 * i;
-                if (m >= n_mels) continue;
+                const int m = t.mel_id[i * 20 + c];
+                if (m < 0) continue;
                 out[t0 * n_mels + m] = y[2 * i];
                 if (t0 + 1 < T) out[(t0 + 1) * n_mels + m] = y[2 * i + 1];
             }

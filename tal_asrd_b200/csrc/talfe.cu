@@ -49,7 +49,7 @@ struct talfe_plan_impl {
     int ref_layout;                // 80-mel reference filterbank shape -> fully unrolled mel stage
     MelLayout layout;
     int pstride;
-    size_t off_tw, off_w, off_lo, blob_bytes;
+    size_t off_tw, off_w, off_lo, off_id, blob_bytes;
     unsigned char* blob_dev;
     size_t smem_bytes;
 };
@@ -64,12 +64,12 @@ struct KernelArgs {
     long long out_row_stride;
     int out_layout;
     float eps;
-    long long tiles_per_row, n_tiles;
+    int tiles_per_row, n_tiles;
     double2* partials;             // [n_tiles][kWarps] (per-row statistics) or [grid][kWarps]
     int partials_per_tile;
     int want_sumsq;
     const unsigned char* blob;
-    int blob_bytes, off_tw, off_w, off_lo;
+    int blob_bytes, off_tw, off_w, off_lo, off_id;
     MelLayout layout;
     int pstride;
 };
@@ -81,45 +81,74 @@ __device__ __forceinline__ float load_sample(const void* base, int dtype, long l
 }
 
 // ------------------------------------------------------------------------------------------ K1
-__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+// mbarrier + bulk-copy (TMA, 1-D) helpers: the waveform tile of the NEXT iteration is fetched by the
+// copy engine straight into shared memory while the SMs work on the current one.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-__device__ __forceinline__ void cp_async_wait_all() {
-    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
 }
 
 struct TileInfo {
-    long long row, t0, L, t_end;
+    int row;
+    int tq;                        // tile index inside the row
+    long long t0, L, t_end;        // first frame, row length, end of the row's valid frames
     bool active;                   // the tile has at least one frame the row really owns
+    bool full;                     // every frame of the tile is valid and inside [frame0, frame0 + n_frames)
+    bool bulk;                     // staged by the copy engine (completion on the mbarrier)
 };
 
-__device__ __forceinline__ TileInfo tile_info(const KernelArgs& a, long long tile) {
-    TileInfo ti;
-    ti.row = tile / a.tiles_per_row;
-    ti.t0 = a.frame0 + (tile - ti.row * a.tiles_per_row) * kFramesPerTile;
+__device__ __forceinline__ void tile_fill(const KernelArgs& a, TileInfo& ti) {
+    ti.t0 = a.frame0 + (long long)ti.tq * kFramesPerTile;
     ti.L = a.lens ? a.lens[ti.row] : a.total_len;
     const long long T_row = ti.L > kHalf ? 1 + ti.L / kHop : 0;         // frames this row really has
     ti.t_end = min(a.frame0 + a.n_frames, T_row);                       // valid frames are t < t_end
     ti.active = ti.t0 < ti.t_end;
-    return ti;
+    ti.full = ti.t0 + kFramesPerTile <= ti.t_end;
+    ti.bulk = false;
 }
 
 // Stage 0: waveform tile -> shared memory, skewed layout (talfe_core.cuh).  Interior tiles of an
-// aligned fp32 row go through cp.async (asynchronous; completion is awaited at the top of the
-// iteration that consumes the tile); edge tiles (reflection), narrow dtypes and unaligned rows take
-// the synchronous element-wise path.
-__device__ __forceinline__ void load_tile(const KernelArgs& a, const TileInfo& ti, float* s_x, int tid) {
+// aligned fp32 row are fetched by the copy engine (cp.async.bulk, one 1280-byte piece per 320-sample
+// block so that the skew can be inserted; completion is signalled on `bar`).  Edge tiles (reflection),
+// narrow dtypes and unaligned rows take the synchronous element-wise path; the barrier that follows
+// in program order (B3, or the set-up barrier for the first tile) publishes them.
+__device__ __forceinline__ void load_tile(const KernelArgs& a, TileInfo& ti, float* s_x, unsigned long long* bar, int tid) {
     if (!ti.active) return;
     const long long s0 = kHop * ti.t0 - kHalf;                          // episode index of tile sample 0
     const long long b0 = s0 - a.origin;                                 // buffer index of tile sample 0
-    const char* rowp = reinterpret_cast<const char*>(a.wave) + ti.row * a.row_stride * (a.dtype == TALFE_F32 ? 4 : 2);
+    const char* rowp = reinterpret_cast<const char*>(a.wave) + (long long)ti.row * a.row_stride * (a.dtype == TALFE_F32 ? 4 : 2);
     const bool interior = s0 >= 0 && s0 + kTileSamples <= ti.L && b0 >= 0 && b0 + kTileSamples <= a.buf_len;
     if (interior && a.dtype == TALFE_F32 &&
         ((reinterpret_cast<unsigned long long>(rowp) + 4ull * (unsigned long long)b0) & 15ull) == 0) {
-        const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(rowp) + b0);
-        float4* dst = reinterpret_cast<float4*>(s_x);
-        for (int q = tid; q < kTileSamples / 4; q += kThreads) cp_async_16(dst + q + (kXSkew / 4) * (q / (kXBlock / 4)), src + q);
+        ti.bulk = true;
+        if (tid == 0) {
+            const float* src = reinterpret_cast<const float*>(rowp) + b0;
+            mbar_expect_tx(bar, kTileSamples * 4);
+#pragma unroll 1
+            for (int blk = 0; blk * kXBlock < kTileSamples; ++blk) {
+                const int n = min(kXBlock, kTileSamples - blk * kXBlock);
+                bulk_g2s(s_x + blk * kXGroup, src + blk * kXBlock, n * 4, bar);
+            }
+        }
     } else {
         for (int i = tid; i < kTileSamples; i += kThreads) {
             long long g = s0 + i;
@@ -141,21 +170,28 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const KernelArgs a)
     const cf* s_tw = reinterpret_cast<const cf*>(smem + a.off_tw);
     const float* s_w = reinterpret_cast<const float*>(smem + a.off_w);
     const int* s_lo = reinterpret_cast<const int*>(smem + a.off_lo);
+    const int* s_id = reinterpret_cast<const int*>(smem + a.off_id);
     float* s_x = reinterpret_cast<float*>(smem + a.blob_bytes);
     cf* s_e = reinterpret_cast<cf*>(s_x + kXFloats);
     cf* s_p = s_e + kGroupsPerCta * kEGroup;
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_p + kGroupsPerCta * a.pstride);
 
     const int tid = threadIdx.x;
-    long long tile = blockIdx.x;
-    TileInfo ti = tile_info(a, tile < a.n_tiles ? tile : 0);
-    if (tile < a.n_tiles) load_tile(a, ti, s_x, tid);                   // first tile in flight while tables load
+    if (tid == 0) mbar_init(s_bar, 1);
     {   // constant tables -> shared memory; power array (incl. its padding) zeroed once
         const int4* src = reinterpret_cast<const int4*>(a.blob);
         int4* dst = reinterpret_cast<int4*>(smem);
         for (int i = tid; i < a.blob_bytes / 16; i += kThreads) dst[i] = __ldg(src + i);
         for (int i = tid; i < kGroupsPerCta * a.pstride; i += kThreads) s_p[i] = make_float2(0.f, 0.f);
     }
-    __syncthreads();
+    __syncthreads();                                                    // tables + mbarrier visible
+    int tile = blockIdx.x;
+    TileInfo ti;
+    ti.row = tile / a.tiles_per_row;
+    ti.tq = tile - ti.row * a.tiles_per_row;
+    tile_fill(a, ti);
+    if (tile < a.n_tiles) load_tile(a, ti, s_x, s_bar, tid);
+    unsigned parity = 0;
     // roles: stage 1 and the mel stage use (pair g1, lane j); stage 2 uses (pair g2, exchange row)
     const int g1 = tid / kGroup, j = tid - g1 * kGroup;
     int g2, row;
@@ -168,20 +204,22 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const KernelArgs a)
     const cf* e2 = s_e + g2 * kEGroup;
     float* p2w = reinterpret_cast<float*>(s_p + g2 * a.pstride);
     const cf* p2r = s_p + g1 * a.pstride;
-    int lo[kMelSlots];
+    int lo[kMelSlots], mid[kMelSlots];
 #pragma unroll
-    for (int i = 0; i < kMelSlots; ++i) lo[i] = s_lo[min(j + 20 * i, M - 1)];
+    for (int i = 0; i < kMelSlots; ++i) { lo[i] = s_lo[i * 20 + j]; mid[i] = s_id[i * 20 + j]; }
     double acc_s = 0.0, acc_q = 0.0;                                    // per-thread sums when partials are per CTA
+    __syncthreads();                                                    // publishes an element-wise first tile
 
     for (; tile < a.n_tiles; tile += gridDim.x) {
-        cp_async_wait_all();
-        __syncthreads();                                                // B1: tile samples visible to all
+        if (ti.bulk) { mbar_wait(s_bar, parity); parity ^= 1; }
         if (ti.active) stage1(j, xg, s_win, s_tw, e1);
         __syncthreads();                                                // B2: exchange rows complete, s_x dead
         const TileInfo cur = ti;
-        if (tile + gridDim.x < a.n_tiles) {                             // prefetch overlaps stage 2 + mel
-            ti = tile_info(a, tile + gridDim.x);
-            load_tile(a, ti, s_x, tid);
+        if (tile + (int)gridDim.x < a.n_tiles) {                        // prefetch overlaps stage 2 + mel
+            ti.tq += gridDim.x;
+            while (ti.tq >= a.tiles_per_row) { ti.tq -= a.tiles_per_row; ++ti.row; }
+            tile_fill(a, ti);
+            load_tile(a, ti, s_x, s_bar, tid);
         }
         if (cur.active) {
             cf v[20];
@@ -189,28 +227,41 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const KernelArgs a)
             if (tid < kNormalThreads) stage2_normal(row, v, p2w);
             else stage2_special(row, v, p2w);
         }
-        __syncthreads();                                                // B3: power spectra complete
-        float* out_row = a.out + cur.row * a.out_row_stride;
+        __syncthreads();                                                // B3: power spectra complete (and edge tile published)
+        float* out_row = a.out + (long long)cur.row * a.out_row_stride;
         float sum = 0.f, sumsq = 0.f;
         if (cur.active) {
             float y[2 * kMelSlots];
             if (kRef) mel_log_ref(j, p2r, s_w, lo, a.eps, y);
             else mel_log_generic(j, a.layout, p2r, s_w, s_lo, a.eps, y);
-            const long long ta = cur.t0 + 2 * g1;
+            const long long fa = cur.t0 - a.frame0 + 2 * g1;           // output frame index of frame a
+            if (cur.full && a.out_layout == TALFE_LAYOUT_TM) {
+                float* o = out_row + fa * M;
 #pragma unroll
-            for (int f = 0; f < 2; ++f) {
-                const long long t = ta + f;
-                if (t < a.frame0 + a.n_frames) {
-                    const bool valid = t < cur.t_end;
+                for (int i = 0; i < kMelSlots; ++i) {
+                    if (kRef || mid[i] >= 0) {
+                        o[mid[i]] = y[2 * i];
+                        o[M + mid[i]] = y[2 * i + 1];
+                        sum += y[2 * i] + y[2 * i + 1];
+                        if (a.want_sumsq) sumsq = fmaf(y[2 * i], y[2 * i], fmaf(y[2 * i + 1], y[2 * i + 1], sumsq));
+                    }
+                }
+            } else {
 #pragma unroll
-                    for (int i = 0; i < kMelSlots; ++i) {
-                        const int m = j + 20 * i;
-                        if (kRef || m < M) {
-                            const float v = valid ? y[2 * i + f] : 0.f;
-                            sum += v;
-                            if (a.want_sumsq) sumsq = fmaf(v, v, sumsq);
-                            if (a.out_layout == TALFE_LAYOUT_TM) out_row[(t - a.frame0) * M + m] = v;
-                            else out_row[(long long)m * a.n_frames + (t - a.frame0)] = v;
+                for (int f = 0; f < 2; ++f) {
+                    const long long t = cur.t0 + 2 * g1 + f;
+                    if (t < a.frame0 + a.n_frames) {
+                        const bool valid = t < cur.t_end;
+#pragma unroll
+                        for (int i = 0; i < kMelSlots; ++i) {
+                            const int m = mid[i];
+                            if (m >= 0) {
+                                const float v = valid ? y[2 * i + f] : 0.f;
+                                sum += v;
+                                if (a.want_sumsq) sumsq = fmaf(v, v, sumsq);
+                                if (a.out_layout == TALFE_LAYOUT_TM) out_row[(fa + f) * M + m] = v;
+                                else out_row[(long long)m * a.n_frames + (fa + f)] = v;
+                            }
                         }
                     }
                 }
@@ -232,12 +283,13 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const KernelArgs a)
                 ds += __shfl_xor_sync(0xffffffffu, ds, o);
                 dq += __shfl_xor_sync(0xffffffffu, dq, o);
             }
-            if (lane == 0) a.partials[tile * kWarps + warp] = make_double2(ds, dq);
+            if (lane == 0) a.partials[(long long)tile * kWarps + warp] = make_double2(ds, dq);
         } else {
             acc_s += (double)sum;
             acc_q += (double)sumsq;
         }
-        // the prefetch above already targets s_x; s_e / s_p are rewritten only after the next B1 / B2
+        // hazards without a barrier at the loop top: stage 1 of the next tile writes s_e, last read before
+        // B3; stage 2 writes s_p only after the next B2, when every thread has left this mel stage.
     }
     if (!a.partials_per_tile) {
 #pragma unroll
@@ -496,10 +548,10 @@ int talfe_plan_create(talfe_plan** plan_out, int device, int n_mels, const float
     p->n_mels = n_mels;
     p->layout = t.layout;
     p->pstride = t.pstride;
-    p->off_tw = t.off_tw; p->off_w = t.off_w; p->off_lo = t.off_lo; p->blob_bytes = t.blob_bytes;
+    p->off_tw = t.off_tw; p->off_w = t.off_w; p->off_lo = t.off_lo; p->off_id = t.off_id; p->blob_bytes = t.blob_bytes;
     p->ref_layout = is_reference_layout(t.layout) ? 1 : 0;
     p->smem_bytes = t.blob_bytes + (size_t)kXFloats * sizeof(float) +
-                    (size_t)kGroupsPerCta * kEGroup * sizeof(cf) + (size_t)kGroupsPerCta * t.pstride * sizeof(cf);
+                    (size_t)kGroupsPerCta * kEGroup * sizeof(cf) + (size_t)kGroupsPerCta * t.pstride * sizeof(cf) + 16;
     cudaError_t e = cudaMalloc(&p->blob_dev, t.blob_bytes);
     if (e == cudaSuccess) e = cudaMemcpy(p->blob_dev, t.blob.data(), t.blob_bytes, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, device);
@@ -553,10 +605,11 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
     a.total_len = job->total_len; a.lens = reinterpret_cast<const long long*>(job->lens);
     a.frame0 = job->frame0; a.n_frames = job->n_frames;
     a.out = job->out; a.out_row_stride = ors; a.out_layout = job->out_layout; a.eps = job->eps;
-    a.tiles_per_row = w.tiles_per_row; a.n_tiles = w.n_tiles;
+    if (w.n_tiles > 0x7fffffffLL) return TALFE_ERR_UNSUPPORTED;
+    a.tiles_per_row = (int)w.tiles_per_row; a.n_tiles = (int)w.n_tiles;
     a.partials = reinterpret_cast<double2*>(ws + w.partials);
     a.blob = plan->blob_dev; a.blob_bytes = (int)plan->blob_bytes;
-    a.off_tw = (int)plan->off_tw; a.off_w = (int)plan->off_w; a.off_lo = (int)plan->off_lo;
+    a.off_tw = (int)plan->off_tw; a.off_w = (int)plan->off_w; a.off_lo = (int)plan->off_lo; a.off_id = (int)plan->off_id;
     a.layout = plan->layout; a.pstride = plan->pstride;
 
     long long grid = (long long)plan->sm_count * plan->ctas_per_sm;

@@ -206,9 +206,10 @@ TALFE_HD void stage2_special(int row, cf (&v)[20], float* __restrict__ p2) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Mel projection + log for the mels owned by thread c (m = c + 20 i).  mel_lo[m] = first bin,
-// w_t[c * wstride + off_i + r] = fb[lo[m] + r, m] (zero padded to the slot's common width R_i).
-// y[2*i + f] = log(mel_f[m] + eps) for frame f of the pair.
+// Mel projection + log.  Lane c owns one mel per slot i (which one: mel_id[i*20 + c], chosen on the
+// host to minimise bank conflicts); mel_lo[i*20 + c] = its first bin;
+// w_t[c * wstride + off_i + r] = fb[lo + r, mel] (zero padded to the slot's common width R_i).
+// y[2*i + f] = log(mel_f + eps) for frame f of the pair.
 struct MelLayout {
     int n_mels;
     int n_slots;
@@ -238,8 +239,7 @@ TALFE_HD void mel_log_generic(int c, const MelLayout& ml, const cf* __restrict__
     for (int i = 0; i < kMelSlots; ++i) {
         float acc_a = 0.f, acc_b = 0.f;
         if (i < ml.n_slots) {
-            const int m = c + 20 * i;
-            const cf* p = p2 + mel_lo[m < ml.n_mels ? m : 0];
+            const cf* p = p2 + mel_lo[i * 20 + c];
             const float* wi = w + ml.offset[i];
             for (int r = 0; r < ml.width[i]; ++r) {
                 const cf pw = p[r];

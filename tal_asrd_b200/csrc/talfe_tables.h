@@ -2,6 +2,7 @@
 // Used by talfe_plan_create (product) and by the CPU emulator test (csrc/host_emul.cu).
 #pragma once
 
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -42,9 +43,10 @@ struct HostTables {
     std::vector<float> win_t;       // [20][20]  0.5 * window[j + 20 m]
     std::vector<float> tw_t;        // [20][10] complex: W400^(j k1) k1=1..9, 2 W400^(10 j)
     std::vector<float> w_t;         // [20][wstride]
-    std::vector<int> mel_lo;        // [80]
+    std::vector<int> mel_lo;        // [4][20] slot-major: first bin of the mel owned by (slot i, lane c)
+    std::vector<int> mel_id;        // [4][20] slot-major: which mel (slot i, lane c) owns, -1 = none
     // byte offsets inside the blob that is copied to shared memory
-    size_t off_win, off_tw, off_w, off_lo, blob_bytes;
+    size_t off_win, off_tw, off_w, off_lo, off_id, blob_bytes;
     std::vector<unsigned char> blob;
 };
 
@@ -93,24 +95,74 @@ inline int build_tables(int n_mels, const float* window, const float* fb, HostTa
     if (L.wstride > 256) return -3;
     t.pstride = 201 + max_w;
     while (t.pstride % 16 != 9) ++t.pstride;                                       // 2*pstride = 18 (mod 32) words
+    // Which lane owns which mel inside a slot is free; choose it to minimise shared-memory bank
+    // conflicts of the mel-stage reads (LDS.64 of the power pairs, 16 lanes per wavefront, 16 banks of
+    // 8 bytes; lanes of a half-warp collide when their first bins are congruent mod 16).  Deterministic
+    // pairwise-swap descent from the identity; model and numbers in DESIGN.md §4 / tools/bank_search.py.
+    std::vector<int> owner(kMaxMels, -1);                      // owner[i*20 + c] = mel
+    for (int m = 0; m < n_mels; ++m) owner[(m / 20) * 20 + m % 20] = m;
+    const int gshift = t.pstride % 16;
+    auto read_cost = [&]() {
+        int total = 0;
+        for (int i = 0; i < L.n_slots; ++i)
+            for (int r = 0; r < L.width[i]; ++r)
+                for (int hw = 0; hw < 5; ++hw) {               // the 5 ways 16 consecutive threads straddle 20-thread groups
+                    int addr[16], nb = 0, worst = 1;
+                    for (int tt = 16 * hw; tt < 16 * hw + 16; ++tt) {
+                        const int g = tt / 20, c = tt % 20, m = owner[i * 20 + c];
+                        if (m < 0) continue;
+                        addr[nb++] = lo[m] + r + g * (16 * 1000 + gshift);   // distinct groups never share an address
+                    }
+                    for (int x = 0; x < nb; ++x) {
+                        int mult = 1;
+                        for (int y = 0; y < x; ++y)
+                            if (addr[y] != addr[x] && (addr[y] - addr[x]) % 16 == 0) {
+                                bool dup = false;                            // count distinct addresses only
+                                for (int z = 0; z < y; ++z) if (addr[z] == addr[y]) dup = true;
+                                if (!dup) ++mult;
+                            }
+                        worst = std::max(worst, mult);
+                    }
+                    total += worst;
+                }
+        return total;
+    };
+    int cost = read_cost();
+    for (bool improved = true; improved;) {
+        improved = false;
+        for (int i = 0; i < L.n_slots; ++i)
+            for (int a = 0; a < 20; ++a)
+                for (int b = a + 1; b < 20; ++b) {
+                    std::swap(owner[i * 20 + a], owner[i * 20 + b]);
+                    const int c2 = read_cost();
+                    if (c2 < cost) { cost = c2; improved = true; }
+                    else std::swap(owner[i * 20 + a], owner[i * 20 + b]);
+                }
+    }
     t.w_t.assign(20 * L.wstride, 0.f);
     t.mel_lo.assign(kMaxMels, 1);
-    for (int m = 0; m < n_mels; ++m) {
-        const int c = m % 20, i = m / 20;
-        t.mel_lo[m] = lo[m];
-        for (int f = lo[m]; f <= hi[m]; ++f) t.w_t[c * L.wstride + L.offset[i] + (f - lo[m])] = fb[f * n_mels + m];
-    }
+    t.mel_id.assign(kMaxMels, -1);
+    for (int i = 0; i < L.n_slots; ++i)
+        for (int c = 0; c < 20; ++c) {
+            const int m = owner[i * 20 + c];
+            t.mel_id[i * 20 + c] = m;
+            if (m < 0) continue;
+            t.mel_lo[i * 20 + c] = lo[m];
+            for (int f = lo[m]; f <= hi[m]; ++f) t.w_t[c * L.wstride + L.offset[i] + (f - lo[m])] = fb[f * n_mels + m];
+        }
     auto align16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
     t.off_win = 0;
     t.off_tw = align16(t.off_win + 400 * sizeof(float));
     t.off_w = align16(t.off_tw + 400 * sizeof(float));
     t.off_lo = align16(t.off_w + t.w_t.size() * sizeof(float));
-    t.blob_bytes = align16(t.off_lo + kMaxMels * sizeof(int));
+    t.off_id = align16(t.off_lo + kMaxMels * sizeof(int));
+    t.blob_bytes = align16(t.off_id + kMaxMels * sizeof(int));
     t.blob.assign(t.blob_bytes, 0);
     std::memcpy(t.blob.data() + t.off_win, t.win_t.data(), 400 * sizeof(float));
     std::memcpy(t.blob.data() + t.off_tw, t.tw_t.data(), 400 * sizeof(float));
     std::memcpy(t.blob.data() + t.off_w, t.w_t.data(), t.w_t.size() * sizeof(float));
     std::memcpy(t.blob.data() + t.off_lo, t.mel_lo.data(), kMaxMels * sizeof(int));
+    std::memcpy(t.blob.data() + t.off_id, t.mel_id.data(), kMaxMels * sizeof(int));
     return 0;
 }
 
