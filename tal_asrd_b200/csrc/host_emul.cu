@@ -38,7 +38,7 @@ extern "C" int talfe_emul_logmel(const float* x, int64_t n_samples, int n_mels, 
         for (int j = 0; j < 20; ++j) stage1(j, xs.data(), t.win_t.data(), tw, e.data());
         for (int row = 0; row < 20; ++row) {
             cf v[20];
-            stage2_load(row, e.data(), v);
+            stage2_load(e.data() + row_slot(row) * kERow, v);
             if (row >= 18) stage2_special(row, v, reinterpret_cast<float*>(p2.data()));
             else stage2_normal(row, v, reinterpret_cast<float*>(p2.data()));
         }

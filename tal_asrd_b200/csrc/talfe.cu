@@ -41,6 +41,9 @@ static_assert(kNormalThreads % 32 == 0, "special rows must fill whole warps");
 
 thread_local int g_last_cuda_error = 0;
 
+// runtime copy of talfe::row_slot() (the constexpr table would otherwise be materialised on the stack)
+__constant__ int c_row_slot[20] = {11, 16, 6, 17, 15, 4, 10, 13, 19, 8, 1, 14, 7, 12, 18, 5, 3, 0, 2, 9};
+
 struct talfe_plan_impl {
     int device;
     int n_mels;
@@ -140,11 +143,13 @@ __device__ __forceinline__ void load_tile(const KernelArgs& a, TileInfo& ti, flo
     if (interior && a.dtype == TALFE_F32 &&
         ((reinterpret_cast<unsigned long long>(rowp) + 4ull * (unsigned long long)b0) & 15ull) == 0) {
         ti.bulk = true;
-        if (tid == 0) {
+        // one elected lane per warp issues its share of the 17 pieces (a single thread issuing all of
+        // them sat on the critical path of the following barrier); thread 0 posts the byte count
+        if ((tid & 31) == 0) {
             const float* src = reinterpret_cast<const float*>(rowp) + b0;
-            mbar_expect_tx(bar, kTileSamples * 4);
+            if (tid == 0) mbar_expect_tx(bar, kTileSamples * 4);
 #pragma unroll 1
-            for (int blk = 0; blk * kXBlock < kTileSamples; ++blk) {
+            for (int blk = tid >> 5; blk * kXBlock < kTileSamples; blk += kWarps) {
                 const int n = min(kXBlock, kTileSamples - blk * kXBlock);
                 bulk_g2s(s_x + blk * kXGroup, src + blk * kXBlock, n * 4, bar);
             }
@@ -201,7 +206,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const KernelArgs a)
     const int M = a.layout.n_mels;
     const float* xg = s_x + kXGroup * g1;
     cf* e1 = s_e + g1 * kEGroup;
-    const cf* e2 = s_e + g2 * kEGroup;
+    const cf* e2 = s_e + g2 * kEGroup + c_row_slot[row] * kERow;
     float* p2w = reinterpret_cast<float*>(s_p + g2 * a.pstride);
     const cf* p2r = s_p + g1 * a.pstride;
     int lo[kMelSlots], mid[kMelSlots];
@@ -223,7 +228,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const KernelArgs a)
         }
         if (cur.active) {
             cf v[20];
-            stage2_load(row, e2, v);
+            stage2_load(e2, v);
             if (tid < kNormalThreads) stage2_normal(row, v, p2w);
             else stage2_special(row, v, p2w);
         }

@@ -111,6 +111,15 @@ TALFE_HD void fft20(cf (&v)[20]) {
     }
 }
 
+// Exchange rows are stored in permuted slots: stage-2 lane `row` (thread 18 g + row reads with LDS.128,
+// 8 lanes per wavefront) fetches slot row_slot(row).  The permutation makes every 8-lane window of the
+// thread order 18 g + row hit 8 distinct 16-byte bank groups ((11 slot + 226 g) mod 8); found by search,
+// see DESIGN.md §4.  Slots 2 and 9 hold the packed rows 18 and 19.
+TALFE_HD constexpr int row_slot(int row) {
+    constexpr int kSlot[20] = {11, 16, 6, 17, 15, 4, 10, 13, 19, 8, 1, 14, 7, 12, 18, 5, 3, 0, 2, 9};
+    return kSlot[row];
+}
+
 // position of tile sample i inside the skewed waveform buffer
 TALFE_HD int xskew(int i) { return i + kXSkew * (i / kXBlock); }
 
@@ -118,7 +127,8 @@ TALFE_HD int xskew(int i) { return i + kXSkew * (i / kXBlock); }
 // Stage 1.  xg points at this pair's first sample inside the skewed tile (s_x + kXGroup * g);
 // frame a = samples 0..399 of the pair, frame b = samples 160..559.
 // win_t[j*20 + m] = 0.5 * hann[j + 20 m]  (the 0.5 makes A_a = C[k] + conj C[20-k] exact scale);
-// tw_t[j*10 + (k1-1)] = W400^(j k1) for k1 = 1..9 and 2 * W400^(10 j) for k1 = 10.
+// tw_t[j*10 + (k1-1)] = W400^(j k1) for k1 = 1..10.  Rows 18 / 19 (the packed k1 = 0 / 10 rows) are left
+// at half scale, which the power computation of stage 2 absorbs ((X/2 + X/2)^2 = |X|^2).
 // Writes this thread's column j of the 20 exchange rows.
 TALFE_HD void stage1(int j, const float* __restrict__ xg, const float* __restrict__ win_t,
                      const cf* __restrict__ tw_t, cf* __restrict__ e_group) {
@@ -141,7 +151,7 @@ TALFE_HD void stage1(int j, const float* __restrict__ xg, const float* __restric
     fft20(z);
     const float4* t4 = reinterpret_cast<const float4*>(tw_t + j * 10);
     cf* col = e_group + j;
-    col[18 * kERow] = make_float2(2.0f * z[0].x, 2.0f * z[0].y);       // row 18: A_a[0] + i A_b[0]
+    col[row_slot(18) * kERow] = z[0];                                             // row 18: (A_a[0] + i A_b[0]) / 2
 #pragma unroll
     for (int h = 0; h < 5; ++h) {
         const float4 tt = t4[h];                                        // twiddles k1 = 2h+1, 2h+2
@@ -153,10 +163,10 @@ TALFE_HD void stage1(int j, const float* __restrict__ xg, const float* __restric
                 const cf p1 = z[k1], q1 = z[20 - k1];
                 const cf aa = make_float2(p1.x + q1.x, p1.y - q1.y);   // A_a[k1] = C[k1] + conj C[20-k1]
                 const cf ab = make_float2(p1.y + q1.y, q1.x - p1.x);   // A_b[k1] = (C[k1] - conj C[20-k1]) / i
-                col[(2 * (k1 - 1)) * kERow] = cmul(aa, w);
-                col[(2 * (k1 - 1) + 1) * kERow] = cmul(ab, w);
+                col[row_slot(2 * (k1 - 1)) * kERow] = cmul(aa, w);
+                col[row_slot(2 * (k1 - 1) + 1) * kERow] = cmul(ab, w);
             } else {
-                col[19 * kERow] = cmul(z[10], w);                       // row 19 (w carries the factor 2)
+                col[row_slot(19) * kERow] = cmul(z[10], w);                       // row 19: (A_a[10] + i A_b[10]) W^(10 j) / 2
             }
         }
     }
@@ -165,8 +175,8 @@ TALFE_HD void stage1(int j, const float* __restrict__ xg, const float* __restric
 // ---------------------------------------------------------------------------------------------
 // Stage 2.  Thread `row` transforms exchange row `row` and writes |X|^2 into the pair's power array
 // p2[k] = (P_a[k], P_b[k]).  Rows 18 / 19 hold both frames packed.
-TALFE_HD void stage2_load(int row, const cf* __restrict__ e_group, cf (&v)[20]) {
-    const float4* src = reinterpret_cast<const float4*>(e_group + row * kERow);
+TALFE_HD void stage2_load(const cf* __restrict__ e_row /* e_group + row_slot(row) * kERow */, cf (&v)[20]) {
+    const float4* src = reinterpret_cast<const float4*>(e_row);
 #pragma unroll
     for (int q = 0; q < 10; ++q) {
         const float4 r = src[q];
@@ -197,11 +207,11 @@ TALFE_HD void stage2_special(int row, cf (&v)[20], float* __restrict__ p2) {
     for (int q = 0; q < 10; ++q) {
         const cf p = zero ? v[q + 1] : v[q];
         const cf r = v[19 - q];
-        const float ar = p.x + r.x, ai = p.y - r.y;                     // 2 X_a
-        const float br = p.x - r.x, bi = p.y + r.y;                     // 2 i X_b
+        const float ar = p.x + r.x, ai = p.y - r.y;                     // X_a   (rows 18/19 carry half scale)
+        const float br = p.x - r.x, bi = p.y + r.y;                     // i X_b
         // q == 9 on row 18 would be bin 200, which carries no mel weight: not stored (padding stays 0)
         if (!(zero && q == 9))
-            out[20 * q] = make_float2(0.25f * fmaf(ar, ar, ai * ai), 0.25f * fmaf(br, br, bi * bi));
+            out[20 * q] = make_float2(fmaf(ar, ar, ai * ai), fmaf(br, br, bi * bi));
     }
 }
 
