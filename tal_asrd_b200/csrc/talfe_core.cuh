@@ -62,8 +62,42 @@ constexpr int kRefWStride = 28;
 
 typedef float2 cf;
 
+// Complex helpers.  On the device the two components of a complex number ride in one 64-bit register
+// pair and use Blackwell's packed fp32x2 arithmetic (add/sub/mul/fma.rn.f32x2 -> SASS FADD2 / FMUL2 /
+// FFMA2): the same IEEE operations as the scalar forms (bit-identical results), half the issue slots.
+// The host emulator compiles the scalar forms.
+#ifdef __CUDA_ARCH__
+TALFE_HD cf cadd(cf a, cf b) {
+    cf r;
+    asm("{ .reg .b64 ra, rb, rr; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; add.rn.f32x2 rr, ra, rb; mov.b64 {%0,%1}, rr; }"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+TALFE_HD cf csub(cf a, cf b) {
+    cf r;
+    asm("{ .reg .b64 ra, rb, rr; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; sub.rn.f32x2 rr, ra, rb; mov.b64 {%0,%1}, rr; }"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+// s * t + a and s * t for a real scalar s
+TALFE_HD cf cfma_s(float s, cf t, cf a) {
+    cf r;
+    asm("{ .reg .b64 rs, rt, ra, rr; mov.b64 rs, {%2,%2}; mov.b64 rt, {%3,%4}; mov.b64 ra, {%5,%6}; fma.rn.f32x2 rr, rs, rt, ra; mov.b64 {%0,%1}, rr; }"
+        : "=f"(r.x), "=f"(r.y) : "f"(s), "f"(t.x), "f"(t.y), "f"(a.x), "f"(a.y));
+    return r;
+}
+TALFE_HD cf cmul_s(float s, cf t) {
+    cf r;
+    asm("{ .reg .b64 rs, rt, rr; mov.b64 rs, {%2,%2}; mov.b64 rt, {%3,%4}; mul.rn.f32x2 rr, rs, rt; mov.b64 {%0,%1}, rr; }"
+        : "=f"(r.x), "=f"(r.y) : "f"(s), "f"(t.x), "f"(t.y));
+    return r;
+}
+#else
 TALFE_HD cf cadd(cf a, cf b) { return make_float2(a.x + b.x, a.y + b.y); }
 TALFE_HD cf csub(cf a, cf b) { return make_float2(a.x - b.x, a.y - b.y); }
+TALFE_HD cf cfma_s(float s, cf t, cf a) { return make_float2(fmaf(s, t.x, a.x), fmaf(s, t.y, a.y)); }
+TALFE_HD cf cmul_s(float s, cf t) { return make_float2(s * t.x, s * t.y); }
+#endif
 TALFE_HD cf cmul(cf a, cf b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 
 // 5-point DFT constants (forward transform, W5 = exp(-2 pi i / 5))
@@ -73,12 +107,12 @@ TALFE_HD cf cmul(cf a, cf b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b
 #define TALFE_S2 0.58778525229247313f    /* sin(4 pi / 5) */
 
 TALFE_HD void dft5(cf a0, cf a1, cf a2, cf a3, cf a4, cf& y0, cf& y1, cf& y2, cf& y3, cf& y4) {
-    cf t1 = cadd(a1, a4), t2 = cadd(a2, a3), t3 = csub(a1, a4), t4 = csub(a2, a3);
-    y0 = make_float2(a0.x + t1.x + t2.x, a0.y + t1.y + t2.y);
-    cf m1 = make_float2(fmaf(TALFE_C2, t2.x, fmaf(TALFE_C1, t1.x, a0.x)), fmaf(TALFE_C2, t2.y, fmaf(TALFE_C1, t1.y, a0.y)));
-    cf m2 = make_float2(fmaf(TALFE_C1, t2.x, fmaf(TALFE_C2, t1.x, a0.x)), fmaf(TALFE_C1, t2.y, fmaf(TALFE_C2, t1.y, a0.y)));
-    cf s1 = make_float2(fmaf(TALFE_S2, t4.x, TALFE_S1 * t3.x), fmaf(TALFE_S2, t4.y, TALFE_S1 * t3.y));
-    cf s2 = make_float2(fmaf(-TALFE_S1, t4.x, TALFE_S2 * t3.x), fmaf(-TALFE_S1, t4.y, TALFE_S2 * t3.y));
+    const cf t1 = cadd(a1, a4), t2 = cadd(a2, a3), t3 = csub(a1, a4), t4 = csub(a2, a3);
+    y0 = cadd(cadd(a0, t1), t2);
+    const cf m1 = cfma_s(TALFE_C2, t2, cfma_s(TALFE_C1, t1, a0));
+    const cf m2 = cfma_s(TALFE_C1, t2, cfma_s(TALFE_C2, t1, a0));
+    const cf s1 = cfma_s(TALFE_S2, t4, cmul_s(TALFE_S1, t3));
+    const cf s2 = cfma_s(-TALFE_S1, t4, cmul_s(TALFE_S2, t3));
     // y1 = m1 - i s1, y4 = m1 + i s1, y2 = m2 - i s2, y3 = m2 + i s2   ( -i (x + i y) = y - i x )
     y1 = make_float2(m1.x + s1.y, m1.y - s1.x);
     y4 = make_float2(m1.x - s1.y, m1.y + s1.x);
@@ -160,9 +194,9 @@ TALFE_HD void stage1(int j, const float* __restrict__ xg, const float* __restric
             const int k1 = 2 * h + 1 + u;
             const cf w = u == 0 ? make_float2(tt.x, tt.y) : make_float2(tt.z, tt.w);
             if (k1 < 10) {
-                const cf p1 = z[k1], q1 = z[20 - k1];
-                const cf aa = make_float2(p1.x + q1.x, p1.y - q1.y);   // A_a[k1] = C[k1] + conj C[20-k1]
-                const cf ab = make_float2(p1.y + q1.y, q1.x - p1.x);   // A_b[k1] = (C[k1] - conj C[20-k1]) / i
+                const cf sm = cadd(z[k1], z[20 - k1]), df = csub(z[k1], z[20 - k1]);
+                const cf aa = make_float2(sm.x, df.y);                  // A_a[k1] = C[k1] + conj C[20-k1]
+                const cf ab = make_float2(sm.y, -df.x);                 // A_b[k1] = (C[k1] - conj C[20-k1]) / i
                 col[row_slot(2 * (k1 - 1)) * kERow] = cmul(aa, w);
                 col[row_slot(2 * (k1 - 1) + 1) * kERow] = cmul(ab, w);
             } else {
@@ -207,8 +241,9 @@ TALFE_HD void stage2_special(int row, cf (&v)[20], float* __restrict__ p2) {
     for (int q = 0; q < 10; ++q) {
         const cf p = zero ? v[q + 1] : v[q];
         const cf r = v[19 - q];
-        const float ar = p.x + r.x, ai = p.y - r.y;                     // X_a   (rows 18/19 carry half scale)
-        const float br = p.x - r.x, bi = p.y + r.y;                     // i X_b
+        const cf sm = cadd(p, r), df = csub(p, r);
+        const float ar = sm.x, ai = df.y;                               // X_a   (rows 18/19 carry half scale)
+        const float br = df.x, bi = sm.y;                               // i X_b
         // q == 9 on row 18 would be bin 200, which carries no mel weight: not stored (padding stays 0)
         if (!(zero && q == 9))
             out[20 * q] = make_float2(fmaf(ar, ar, ai * ai), fmaf(br, br, bi * bi));
