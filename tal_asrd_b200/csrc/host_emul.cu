@@ -35,7 +35,11 @@ extern "C" int talfe_emul_logmel(const float* x, int64_t n_samples, int n_mels, 
         }
         for (auto& v : e) v = make_float2(0.f, 0.f);
         for (auto& v : p2) v = make_float2(0.f, 0.f);
-        for (int j = 0; j < 20; ++j) stage1(j, xs.data(), t.win_t.data(), tw, e.data());
+        for (int j = 0; j < 20; ++j) {
+            float win[20];
+            load_window(j, t.win_t.data(), win);
+            stage1(j, xs.data(), win, tw, e.data());
+        }
         for (int row = 0; row < 20; ++row) {
             cf v[20];
             stage2_load(e.data() + row_slot(row) * kERow, v);

@@ -212,12 +212,14 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const KernelArgs a)
     int lo[kMelSlots], mid[kMelSlots];
 #pragma unroll
     for (int i = 0; i < kMelSlots; ++i) { lo[i] = s_lo[i * 20 + j]; mid[i] = s_id[i * 20 + j]; }
+    float win[20];                                                      // this lane's 20 window taps stay in registers
+    load_window(j, s_win, win);
     double acc_s = 0.0, acc_q = 0.0;                                    // per-thread sums when partials are per CTA
     __syncthreads();                                                    // publishes an element-wise first tile
 
     for (; tile < a.n_tiles; tile += gridDim.x) {
         if (ti.bulk) { mbar_wait(s_bar, parity); parity ^= 1; }
-        if (ti.active) stage1(j, xg, s_win, s_tw, e1);
+        if (ti.active) stage1(j, xg, win, s_tw, e1);
         __syncthreads();                                                // B2: exchange rows complete, s_x dead
         const TileInfo cur = ti;
         if (tile + (int)gridDim.x < a.n_tiles) {                        // prefetch overlaps stage 2 + mel

@@ -164,23 +164,25 @@ TALFE_HD int xskew(int i) { return i + kXSkew * (i / kXBlock); }
 // tw_t[j*10 + (k1-1)] = W400^(j k1) for k1 = 1..10.  Rows 18 / 19 (the packed k1 = 0 / 10 rows) are left
 // at half scale, which the power computation of stage 2 absorbs ((X/2 + X/2)^2 = |X|^2).
 // Writes this thread's column j of the 20 exchange rows.
-TALFE_HD void stage1(int j, const float* __restrict__ xg, const float* __restrict__ win_t,
-                     const cf* __restrict__ tw_t, cf* __restrict__ e_group) {
-    cf z[20];
+TALFE_HD void load_window(int j, const float* __restrict__ win_t, float (&win)[20]) {
     const float4* w4 = reinterpret_cast<const float4*>(win_t + j * 20);
-    const float* p = xg + j;
 #pragma unroll
     for (int q = 0; q < 5; ++q) {
         const float4 w = w4[q];
-        const float ww[4] = {w.x, w.y, w.z, w.w};
+        win[4 * q] = w.x; win[4 * q + 1] = w.y; win[4 * q + 2] = w.z; win[4 * q + 3] = w.w;
+    }
+}
+
+TALFE_HD void stage1(int j, const float* __restrict__ xg, const float (&win)[20],
+                     const cf* __restrict__ tw_t, cf* __restrict__ e_group) {
+    cf z[20];
+    const float* p = xg + j;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int m = 4 * q + u;
-            // sample j + 20 m of frame a, j + 20 m + 160 of the pair for frame b, with the block skew
-            const int ia = 20 * m + (20 * m >= kXBlock ? kXSkew : 0);
-            const int ib = 20 * m + kHop + (20 * m + kHop >= kXBlock ? kXSkew : 0);
-            z[m] = make_float2(ww[u] * p[ia], ww[u] * p[ib]);
-        }
+    for (int m = 0; m < 20; ++m) {
+        // sample j + 20 m of frame a, j + 20 m + 160 of the pair for frame b, with the block skew
+        const int ia = 20 * m + (20 * m >= kXBlock ? kXSkew : 0);
+        const int ib = 20 * m + kHop + (20 * m + kHop >= kXBlock ? kXSkew : 0);
+        z[m] = make_float2(win[m] * p[ia], win[m] * p[ib]);
     }
     fft20(z);
     const float4* t4 = reinterpret_cast<const float4*>(tw_t + j * 10);
