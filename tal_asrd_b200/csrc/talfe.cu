@@ -36,6 +36,7 @@ constexpr int kFramesPerTile = 2 * kGroupsPerCta;           // 32
 constexpr int kTileSamples = kHop * kFramesPerTile + (kNfft - kHop);   // 5360
 constexpr int kXFloats = (kTileSamples + kXSkew * ((kTileSamples - 1) / kXBlock) + 3) & ~3;   // skewed tile, 5680
 constexpr int kNormalThreads = 18 * kGroupsPerCta;          // 288 = 9 full warps; warp 9 = packed rows 0/10
+constexpr int kMaxSamples = 0x7fff0000;                     // sample / frame indices are 32-bit on the device
 constexpr int kColChunk = 2048;                             // frames per block in the per-mel statistics pass
 static_assert(kNormalThreads % 32 == 0, "special rows must fill whole warps");
 
@@ -60,9 +61,10 @@ struct talfe_plan_impl {
 struct KernelArgs {
     const void* wave;
     int dtype;
-    long long batch, row_stride, buf_len, origin, total_len;
+    long long row_stride;          // elements between rows (pointer arithmetic only)
+    int batch, buf_len, origin, total_len;     // sample indices fit 31 bits (checked on the host; lens[] is clamped)
     const long long* lens;
-    long long frame0, n_frames;
+    int frame0, n_frames, frame_end;           // frame_end = frame0 + n_frames
     float* out;
     long long out_row_stride;
     int out_layout;
@@ -113,17 +115,17 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 struct TileInfo {
     int row;
     int tq;                        // tile index inside the row
-    long long t0, L, t_end;        // first frame, row length, end of the row's valid frames
+    int t0, L, t_end;              // first frame, row length, end of the row's valid frames
     bool active;                   // the tile has at least one frame the row really owns
     bool full;                     // every frame of the tile is valid and inside [frame0, frame0 + n_frames)
     bool bulk;                     // staged by the copy engine (completion on the mbarrier)
 };
 
 __device__ __forceinline__ void tile_fill(const KernelArgs& a, TileInfo& ti) {
-    ti.t0 = a.frame0 + (long long)ti.tq * kFramesPerTile;
-    ti.L = a.lens ? a.lens[ti.row] : a.total_len;
-    const long long T_row = ti.L > kHalf ? 1 + ti.L / kHop : 0;         // frames this row really has
-    ti.t_end = min(a.frame0 + a.n_frames, T_row);                       // valid frames are t < t_end
+    ti.t0 = a.frame0 + ti.tq * kFramesPerTile;
+    ti.L = a.lens ? (int)min(a.lens[ti.row], (long long)kMaxSamples) : a.total_len;
+    const int T_row = ti.L > kHalf ? 1 + ti.L / kHop : 0;               // frames this row really has
+    ti.t_end = min(a.frame_end, T_row);                                 // valid frames are t < t_end
     ti.active = ti.t0 < ti.t_end;
     ti.full = ti.t0 + kFramesPerTile <= ti.t_end;
     ti.bulk = false;
@@ -136,12 +138,12 @@ __device__ __forceinline__ void tile_fill(const KernelArgs& a, TileInfo& ti) {
 // in program order (B3, or the set-up barrier for the first tile) publishes them.
 __device__ __forceinline__ void load_tile(const KernelArgs& a, TileInfo& ti, float* s_x, unsigned long long* bar, int tid) {
     if (!ti.active) return;
-    const long long s0 = kHop * ti.t0 - kHalf;                          // episode index of tile sample 0
-    const long long b0 = s0 - a.origin;                                 // buffer index of tile sample 0
+    const int s0 = kHop * ti.t0 - kHalf;                                // episode index of tile sample 0
+    const int b0 = s0 - a.origin;                                       // buffer index of tile sample 0
     const char* rowp = reinterpret_cast<const char*>(a.wave) + (long long)ti.row * a.row_stride * (a.dtype == TALFE_F32 ? 4 : 2);
     const bool interior = s0 >= 0 && s0 + kTileSamples <= ti.L && b0 >= 0 && b0 + kTileSamples <= a.buf_len;
     if (interior && a.dtype == TALFE_F32 &&
-        ((reinterpret_cast<unsigned long long>(rowp) + 4ull * (unsigned long long)b0) & 15ull) == 0) {
+        ((reinterpret_cast<unsigned long long>(rowp) + 4ull * (unsigned long long)(unsigned)b0) & 15ull) == 0) {
         ti.bulk = true;
         // one elected lane per warp issues its share of the 17 pieces (a single thread issuing all of
         // them sat on the critical path of the following barrier); thread 0 posts the byte count
@@ -156,10 +158,10 @@ __device__ __forceinline__ void load_tile(const KernelArgs& a, TileInfo& ti, flo
         }
     } else {
         for (int i = tid; i < kTileSamples; i += kThreads) {
-            long long g = s0 + i;
+            int g = s0 + i;
             if (g < 0) g = -g;                                          // reflect, no edge repeat
             if (g >= ti.L) g = 2 * (ti.L - 1) - g;
-            const long long bi = g - a.origin;
+            const int bi = g - a.origin;
             float v = 0.f;
             if (g >= 0 && g < ti.L && bi >= 0 && bi < a.buf_len) v = load_sample(rowp, a.dtype, bi);
             s_x[xskew(i)] = v;
@@ -217,33 +219,25 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const KernelArgs a)
     double acc_s = 0.0, acc_q = 0.0;                                    // per-thread sums when partials are per CTA
     __syncthreads();                                                    // publishes an element-wise first tile
 
-    for (; tile < a.n_tiles; tile += gridDim.x) {
-        if (ti.bulk) { mbar_wait(s_bar, parity); parity ^= 1; }
-        if (ti.active) stage1(j, xg, win, s_tw, e1);
-        __syncthreads();                                                // B2: exchange rows complete, s_x dead
-        const TileInfo cur = ti;
-        if (tile + (int)gridDim.x < a.n_tiles) {                        // prefetch overlaps stage 2 + mel
-            ti.tq += gridDim.x;
-            while (ti.tq >= a.tiles_per_row) { ti.tq -= a.tiles_per_row; ++ti.row; }
-            tile_fill(a, ti);
-            load_tile(a, ti, s_x, s_bar, tid);
-        }
-        if (cur.active) {
-            cf v[20];
-            stage2_load(e2, v);
-            if (tid < kNormalThreads) stage2_normal(row, v, p2w);
-            else stage2_special(row, v, p2w);
-        }
-        __syncthreads();                                                // B3: power spectra complete (and edge tile published)
+    // Software pipeline over tiles n = 0, 1, ...:
+    //     phase A(n): stage 2 of tile n              (exchange rows -> power spectra; TMA fetch of tile n+1 in flight)
+    //     phase B(n): mel/log/store of tile n  +  stage 1 of tile n+1   (independent: P(n) vs x(n+1) -> E(n+1))
+    // one barrier after each phase.  In phase B even warps run the shared-memory-heavy mel stage first and
+    // odd warps the FP-heavy stage 1 first, so that the two kinds of work overlap on the SM's pipes.
+    auto run_stage1 = [&](const TileInfo& t) {
+        if (t.bulk) { mbar_wait(s_bar, parity); parity ^= 1; }
+        if (t.active) stage1(j, xg, win, s_tw, e1);
+    };
+    auto run_mel = [&](const TileInfo& cur, int cur_tile) {
         float* out_row = a.out + (long long)cur.row * a.out_row_stride;
         float sum = 0.f, sumsq = 0.f;
         if (cur.active) {
             float y[2 * kMelSlots];
             if (kRef) mel_log_ref(j, p2r, s_w, lo, a.eps, y);
             else mel_log_generic(j, a.layout, p2r, s_w, s_lo, a.eps, y);
-            const long long fa = cur.t0 - a.frame0 + 2 * g1;           // output frame index of frame a
+            const int fa = cur.t0 - a.frame0 + 2 * g1;                 // output frame index of frame a
             if (cur.full && a.out_layout == TALFE_LAYOUT_TM) {
-                float* o = out_row + fa * M;
+                float* o = out_row + (long long)fa * M;
 #pragma unroll
                 for (int i = 0; i < kMelSlots; ++i) {
                     if (kRef || mid[i] >= 0) {
@@ -256,8 +250,8 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const KernelArgs a)
             } else {
 #pragma unroll
                 for (int f = 0; f < 2; ++f) {
-                    const long long t = cur.t0 + 2 * g1 + f;
-                    if (t < a.frame0 + a.n_frames) {
+                    const int t = cur.t0 + 2 * g1 + f;
+                    if (t < a.frame_end) {
                         const bool valid = t < cur.t_end;
 #pragma unroll
                         for (int i = 0; i < kMelSlots; ++i) {
@@ -266,7 +260,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const KernelArgs a)
                                 const float v = valid ? y[2 * i + f] : 0.f;
                                 sum += v;
                                 if (a.want_sumsq) sumsq = fmaf(v, v, sumsq);
-                                if (a.out_layout == TALFE_LAYOUT_TM) out_row[(fa + f) * M + m] = v;
+                                if (a.out_layout == TALFE_LAYOUT_TM) out_row[(long long)(fa + f) * M + m] = v;
                                 else out_row[(long long)m * a.n_frames + (fa + f)] = v;
                             }
                         }
@@ -275,11 +269,11 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const KernelArgs a)
             }
         } else {
             // tile lies entirely beyond this row's own frames ("each row as if alone"): zero fill
-            const long long nfr = min((long long)kFramesPerTile, a.frame0 + a.n_frames - cur.t0);
-            for (long long i = tid; i < nfr * M; i += kThreads) {
-                const long long f = i / M, m = i - f * M;
-                if (a.out_layout == TALFE_LAYOUT_TM) out_row[(cur.t0 - a.frame0 + f) * M + m] = 0.f;
-                else out_row[m * a.n_frames + (cur.t0 - a.frame0 + f)] = 0.f;
+            const int nfr = min(kFramesPerTile, a.frame_end - cur.t0);
+            for (int i = tid; i < nfr * M; i += kThreads) {
+                const int f = i / M, m = i - f * M;
+                if (a.out_layout == TALFE_LAYOUT_TM) out_row[(long long)(cur.t0 - a.frame0 + f) * M + m] = 0.f;
+                else out_row[(long long)m * a.n_frames + (cur.t0 - a.frame0 + f)] = 0.f;
             }
         }
         if (a.partials_per_tile) {
@@ -290,13 +284,39 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const KernelArgs a)
                 ds += __shfl_xor_sync(0xffffffffu, ds, o);
                 dq += __shfl_xor_sync(0xffffffffu, dq, o);
             }
-            if (lane == 0) a.partials[(long long)tile * kWarps + warp] = make_double2(ds, dq);
+            if (lane == 0) a.partials[(long long)cur_tile * kWarps + warp] = make_double2(ds, dq);
         } else {
             acc_s += (double)sum;
             acc_q += (double)sumsq;
         }
-        // hazards without a barrier at the loop top: stage 1 of the next tile writes s_e, last read before
-        // B3; stage 2 writes s_p only after the next B2, when every thread has left this mel stage.
+    };
+
+    if (tile < a.n_tiles) run_stage1(ti);
+    __syncthreads();                                                    // E(0) complete, s_x free
+    for (; tile < a.n_tiles; tile += gridDim.x) {
+        const TileInfo cur = ti;
+        const bool has_next = tile + (int)gridDim.x < a.n_tiles;
+        if (has_next) {                                                 // fetch tile n+1 behind stage 2 of tile n
+            ti.tq += gridDim.x;
+            while (ti.tq >= a.tiles_per_row) { ti.tq -= a.tiles_per_row; ++ti.row; }
+            tile_fill(a, ti);
+            load_tile(a, ti, s_x, s_bar, tid);
+        }
+        if (cur.active) {                                               // phase A: stage 2
+            cf v[20];
+            stage2_load(e2, v);
+            if (tid < kNormalThreads) stage2_normal(row, v, p2w);
+            else stage2_special(row, v, p2w);
+        }
+        __syncthreads();                                                // P(n) complete, E free (and an element-wise x(n+1) published)
+        if (warp & 1) {                                                 // phase B
+            if (has_next) run_stage1(ti);
+            run_mel(cur, tile);
+        } else {
+            run_mel(cur, tile);
+            if (has_next) run_stage1(ti);
+        }
+        __syncthreads();                                                // E(n+1) complete, s_x and P free
     }
     if (!a.partials_per_tile) {
 #pragma unroll
@@ -608,9 +628,12 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
 
     KernelArgs a{};
     a.wave = job->wave; a.dtype = job->wave_dtype;
-    a.batch = job->batch; a.row_stride = job->row_stride; a.buf_len = job->buf_len; a.origin = job->origin;
-    a.total_len = job->total_len; a.lens = reinterpret_cast<const long long*>(job->lens);
-    a.frame0 = job->frame0; a.n_frames = job->n_frames;
+    if (job->buf_len > kMaxSamples || job->origin > kMaxSamples || job->total_len > kMaxSamples ||
+        job->frame0 + job->n_frames > kMaxSamples / kHop || job->batch > 0x7fffffffLL)
+        return TALFE_ERR_UNSUPPORTED;                         // ~37 h of 16 kHz audio per row: stream it in chunks instead
+    a.batch = (int)job->batch; a.row_stride = job->row_stride; a.buf_len = (int)job->buf_len; a.origin = (int)job->origin;
+    a.total_len = (int)job->total_len; a.lens = reinterpret_cast<const long long*>(job->lens);
+    a.frame0 = (int)job->frame0; a.n_frames = (int)job->n_frames; a.frame_end = a.frame0 + a.n_frames;
     a.out = job->out; a.out_row_stride = ors; a.out_layout = job->out_layout; a.eps = job->eps;
     if (w.n_tiles > 0x7fffffffLL) return TALFE_ERR_UNSUPPORTED;
     a.tiles_per_row = (int)w.tiles_per_row; a.n_tiles = (int)w.n_tiles;
