@@ -105,6 +105,8 @@ def cpu_reference_rate(steps: int, warmup: int, batch_np=None):
     if batch_np is None:
         batch_np = synth.batch(2020, BATCH, N_SAMPLES)
     x = torch.from_numpy(batch_np)
+    if os.environ.get("OMP_NUM_THREADS") in ("1", None) and "LOCAL_RANK" in os.environ:
+        torch.set_num_threads(os.cpu_count() or 1)      # torchrun pins OMP_NUM_THREADS=1; the baseline may use every core
     threads = torch.get_num_threads()
     for _ in range(warmup):
         O.logmel_port_f32(x)

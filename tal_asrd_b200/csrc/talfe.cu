@@ -96,9 +96,18 @@ __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned coun
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
-                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+// waveform samples are used once: fetch them with an L2 evict-first policy so that the features K1 writes
+// stay L2-resident for the normalisation sweep that follows
+__device__ __forceinline__ unsigned long long l2_evict_first_policy() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar,
+                                         unsigned long long policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
                  : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
@@ -150,10 +159,11 @@ __device__ __forceinline__ void load_tile(const KernelArgs& a, TileInfo& ti, flo
         if ((tid & 31) == 0) {
             const float* src = reinterpret_cast<const float*>(rowp) + b0;
             if (tid == 0) mbar_expect_tx(bar, kTileSamples * 4);
+            const unsigned long long pol = l2_evict_first_policy();
 #pragma unroll 1
             for (int blk = tid >> 5; blk * kXBlock < kTileSamples; blk += kWarps) {
                 const int n = min(kXBlock, kTileSamples - blk * kXBlock);
-                bulk_g2s(s_x + blk * kXGroup, src + blk * kXBlock, n * 4, bar);
+                bulk_g2s(s_x + blk * kXGroup, src + blk * kXBlock, n * 4, bar, pol);
             }
         }
     } else {
@@ -319,12 +329,20 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const KernelArgs a)
         __syncthreads();                                                // E(n+1) complete, s_x and P free
     }
     if (!a.partials_per_tile) {
+        // one slot per CTA: warp shuffle tree, then a fixed-order sum over the 10 warps (bit-reproducible)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             acc_s += __shfl_xor_sync(0xffffffffu, acc_s, o);
             acc_q += __shfl_xor_sync(0xffffffffu, acc_q, o);
         }
-        if (lane == 0) a.partials[(long long)blockIdx.x * kWarps + warp] = make_double2(acc_s, acc_q);
+        double2* s_red = reinterpret_cast<double2*>(s_e);              // exchange buffer is free after the last barrier
+        if (lane == 0) s_red[warp] = make_double2(acc_s, acc_q);
+        __syncthreads();
+        if (tid == 0) {
+            double ts = 0.0, tq2 = 0.0;
+            for (int w2 = 0; w2 < kWarps; ++w2) { ts += s_red[w2].x; tq2 += s_red[w2].y; }
+            a.partials[blockIdx.x] = make_double2(ts, tq2);
+        }
     }
 }
 
@@ -462,6 +480,44 @@ __global__ void __launch_bounds__(256) apply_stats_kernel(float* __restrict__ fe
             if (f < valid) base[i] = (base[i] - s_mean[m]) * s_rstd[m];
         }
     }
+}
+
+// Reference normalisation (one scalar for the whole contiguous tensor): flat float4 sweep, four
+// independent 128-bit loads in flight per thread, most recently written data first (the tail of the
+// tensor is what K1 left in L2 last).
+__global__ void __launch_bounds__(256) sub_scalar_flat_kernel(float4* __restrict__ p, long long n4, float* __restrict__ tail,
+                                                              int n_tail, const double2* __restrict__ partials, int n_partials,
+                                                              double count, double* __restrict__ stats_out) {
+    // every block re-derives the scalar from the few-hundred per-CTA partials K1 left in L2 (fixed order:
+    // identical in every block and every run), which removes a separate reduction launch from the path
+    __shared__ double s_a[256], s_b[256];
+    double ra = 0.0, rb = 0.0;
+    for (int i = threadIdx.x; i < n_partials; i += 256) { const double2 v = partials[i]; ra += v.x; rb += v.y; }
+    s_a[threadIdx.x] = ra; s_b[threadIdx.x] = rb;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) { s_a[threadIdx.x] += s_a[threadIdx.x + o]; s_b[threadIdx.x] += s_b[threadIdx.x + o]; }
+        __syncthreads();
+    }
+    const float mean = count > 0.0 ? (float)(s_a[0] / count) : 0.f;
+    if (stats_out && blockIdx.x == 0 && threadIdx.x == 0) { stats_out[0] = count; stats_out[1] = s_a[0]; stats_out[2] = s_b[0]; }
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long first = (long long)(gridDim.x - 1 - blockIdx.x) * blockDim.x + threadIdx.x;   // reversed block order
+    long long i = first;
+    for (; i + 3 * stride < n4; i += 4 * stride) {
+        float4 a = p[i], b = p[i + stride], c = p[i + 2 * stride], d = p[i + 3 * stride];
+        a.x -= mean; a.y -= mean; a.z -= mean; a.w -= mean;
+        b.x -= mean; b.y -= mean; b.z -= mean; b.w -= mean;
+        c.x -= mean; c.y -= mean; c.z -= mean; c.w -= mean;
+        d.x -= mean; d.y -= mean; d.z -= mean; d.w -= mean;
+        p[i] = a; p[i + stride] = b; p[i + 2 * stride] = c; p[i + 3 * stride] = d;
+    }
+    for (; i < n4; i += stride) {
+        float4 a = p[i];
+        a.x -= mean; a.y -= mean; a.z -= mean; a.w -= mean;
+        p[i] = a;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < n_tail) tail[threadIdx.x] -= mean;
 }
 
 // ------------------------------------------------------------------------------------------ synthetic audio
@@ -646,8 +702,8 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
     if (grid > w.n_tiles) grid = w.n_tiles;
     const bool want_stats = job->stats != nullptr || job->norm != TALFE_NORM_NONE;
     const bool per_row = job->norm >= TALFE_NORM_ROW_MEAN;
-    a.partials_per_tile = per_row ? 1 : 0;                // batch-wide sums: one slot per (CTA, warp) is enough
-    a.want_sumsq = want_stats ? 1 : 0;
+    a.partials_per_tile = per_row ? 1 : 0;                // batch-wide sums: one slot per CTA is enough
+    a.want_sumsq = job->stats != nullptr ? 1 : 0;         // the sum of squares is only ever reported, never needed by K3
     if (plan->ref_layout) logmel_kernel<true><<<(unsigned)grid, kThreads, plan->smem_bytes, stream>>>(a);
     else logmel_kernel<false><<<(unsigned)grid, kThreads, plan->smem_bytes, stream>>>(a);
     TALFE_CUDA(cudaGetLastError());
@@ -655,9 +711,20 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
     if (!want_stats) return TALFE_OK;
     double* stats = job->stats ? job->stats : reinterpret_cast<double*>(ws + w.scratch_stats);
     const int accumulate = (job->accumulate_stats && job->stats) ? 1 : 0;
+    if (job->norm == TALFE_NORM_BATCH_MEAN && !a.lens && !accumulate && !job->defer_normalise && ors == dense &&
+        (reinterpret_cast<uintptr_t>(job->out) & 15) == 0) {
+        // the reference case: one scalar over a contiguous [B, T, M] (or [B, M, T]) tensor; the sweep
+        // derives the mean from the per-CTA partials itself (no separate reduction launch)
+        const long long total = dense * job->batch, n4 = total / 4;
+        const unsigned blocks = (unsigned)std::max<long long>(1, std::min<long long>((n4 + 1023) / 1024, (long long)plan->sm_count * 8));
+        sub_scalar_flat_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<float4*>(job->out), n4, job->out + 4 * n4,
+                                                           (int)(total - 4 * n4), a.partials, (int)grid, (double)total, job->stats);
+        TALFE_CUDA(cudaGetLastError());
+        return TALFE_OK;
+    }
     const long long blocks = per_row ? job->batch : 1;
     const long long rows_per_block = per_row ? 1 : job->batch;
-    const long long slots_per_block = per_row ? w.tiles_per_row * kWarps : grid * kWarps;
+    const long long slots_per_block = per_row ? w.tiles_per_row * kWarps : grid;
     reduce_partials_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a.partials, slots_per_block, a.lens, a.total_len,
                                                                   a.frame0, a.n_frames, rows_per_block, M, accumulate, stats);
     TALFE_CUDA(cudaGetLastError());
