@@ -23,7 +23,7 @@ extern "C" int talfe_emul_logmel(const float* x, int64_t n_samples, int n_mels, 
     int rc = build_tables(n_mels, win.data(), fbv.data(), t);
     if (rc) return rc;
     const int64_t T = 1 + n_samples / kHop;
-    std::vector<float> xs(xskew(kNfft + kHop - 1) + 1);
+    std::vector<float> xs(xskew<float>(kNfft + kHop - 1) + 1);
     std::vector<cf> e(kEGroup), p2(t.pstride);
     const cf* tw = reinterpret_cast<const cf*>(t.tw_t.data());
     for (int64_t t0 = 0; t0 < T; t0 += 2) {
@@ -31,13 +31,13 @@ extern "C" int talfe_emul_logmel(const float* x, int64_t n_samples, int n_mels, 
             int64_t g = kHop * t0 - kHalf + i;
             if (g < 0) g = -g;
             if (g >= n_samples) g = 2 * (n_samples - 1) - g;
-            xs[xskew(i)] = (g >= 0 && g < n_samples) ? x[g] : 0.f;
+            xs[xskew<float>(i)] = (g >= 0 && g < n_samples) ? x[g] : 0.f;
         }
         for (auto& v : e) v = make_float2(0.f, 0.f);
         for (auto& v : p2) v = make_float2(0.f, 0.f);
         for (int j = 0; j < 20; ++j) {
             float win[20];
-            load_window(j, t.win_t.data(), win);
+            load_window(j, t.win_t.data(), 1.0f, win);
             stage1(j, xs.data(), win, tw, e.data());
         }
         for (int row = 0; row < 20; ++row) {

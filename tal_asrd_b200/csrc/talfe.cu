@@ -34,7 +34,7 @@ constexpr int kThreads = kGroupsPerCta * kGroup;            // 320
 constexpr int kWarps = kThreads / 32;                       // 10
 constexpr int kFramesPerTile = 2 * kGroupsPerCta;           // 32
 constexpr int kTileSamples = kHop * kFramesPerTile + (kNfft - kHop);   // 5360
-constexpr int kXFloats = (kTileSamples + kXSkew * ((kTileSamples - 1) / kXBlock) + 3) & ~3;   // skewed tile, 5680
+constexpr int kXFloats = (kTileSamples + 24 * ((kTileSamples - 1) / kXBlock) + 3) & ~3;   // skewed tile in elements (fp32 sizing)
 constexpr int kNormalThreads = 18 * kGroupsPerCta;          // 288 = 9 full warps; warp 9 = packed rows 0/10
 constexpr int kMaxSamples = 0x7fff0000;                     // sample / frame indices are 32-bit on the device
 constexpr int kColChunk = 2048;                             // frames per block in the per-mel statistics pass
@@ -78,12 +78,6 @@ struct KernelArgs {
     MelLayout layout;
     int pstride;
 };
-
-__device__ __forceinline__ float load_sample(const void* base, int dtype, long long idx) {
-    if (dtype == TALFE_F32) return __ldg(reinterpret_cast<const float*>(base) + idx);
-    if (dtype == TALFE_F16) return __half2float(__ldg(reinterpret_cast<const __half*>(base) + idx));
-    return (float)__ldg(reinterpret_cast<const short*>(base) + idx) * (1.0f / 32768.0f);
-}
 
 // ------------------------------------------------------------------------------------------ K1
 // mbarrier + bulk-copy (TMA, 1-D) helpers: the waveform tile of the NEXT iteration is fetched by the
@@ -145,25 +139,26 @@ __device__ __forceinline__ void tile_fill(const KernelArgs& a, TileInfo& ti) {
 // block so that the skew can be inserted; completion is signalled on `bar`).  Edge tiles (reflection),
 // narrow dtypes and unaligned rows take the synchronous element-wise path; the barrier that follows
 // in program order (B3, or the set-up barrier for the first tile) publishes them.
-__device__ __forceinline__ void load_tile(const KernelArgs& a, TileInfo& ti, float* s_x, unsigned long long* bar, int tid) {
+template <typename XT>
+__device__ __forceinline__ void load_tile(const KernelArgs& a, TileInfo& ti, XT* s_x, unsigned long long* bar, int tid) {
     if (!ti.active) return;
+    constexpr int kXG = XLayout<XT>::kGroup;
     const int s0 = kHop * ti.t0 - kHalf;                                // episode index of tile sample 0
     const int b0 = s0 - a.origin;                                       // buffer index of tile sample 0
-    const char* rowp = reinterpret_cast<const char*>(a.wave) + (long long)ti.row * a.row_stride * (a.dtype == TALFE_F32 ? 4 : 2);
+    const XT* rowp = reinterpret_cast<const XT*>(a.wave) + (long long)ti.row * a.row_stride;
     const bool interior = s0 >= 0 && s0 + kTileSamples <= ti.L && b0 >= 0 && b0 + kTileSamples <= a.buf_len;
-    if (interior && a.dtype == TALFE_F32 &&
-        ((reinterpret_cast<unsigned long long>(rowp) + 4ull * (unsigned long long)(unsigned)b0) & 15ull) == 0) {
+    if (interior && (reinterpret_cast<unsigned long long>(rowp + b0) & 15ull) == 0) {
         ti.bulk = true;
         // one elected lane per warp issues its share of the 17 pieces (a single thread issuing all of
         // them sat on the critical path of the following barrier); thread 0 posts the byte count
         if ((tid & 31) == 0) {
-            const float* src = reinterpret_cast<const float*>(rowp) + b0;
-            if (tid == 0) mbar_expect_tx(bar, kTileSamples * 4);
+            const XT* src = rowp + b0;
+            if (tid == 0) mbar_expect_tx(bar, kTileSamples * (int)sizeof(XT));
             const unsigned long long pol = l2_evict_first_policy();
 #pragma unroll 1
             for (int blk = tid >> 5; blk * kXBlock < kTileSamples; blk += kWarps) {
                 const int n = min(kXBlock, kTileSamples - blk * kXBlock);
-                bulk_g2s(s_x + blk * kXGroup, src + blk * kXBlock, n * 4, bar, pol);
+                bulk_g2s(s_x + blk * kXG, src + blk * kXBlock, n * (int)sizeof(XT), bar, pol);
             }
         }
     } else {
@@ -172,14 +167,14 @@ __device__ __forceinline__ void load_tile(const KernelArgs& a, TileInfo& ti, flo
             if (g < 0) g = -g;                                          // reflect, no edge repeat
             if (g >= ti.L) g = 2 * (ti.L - 1) - g;
             const int bi = g - a.origin;
-            float v = 0.f;
-            if (g >= 0 && g < ti.L && bi >= 0 && bi < a.buf_len) v = load_sample(rowp, a.dtype, bi);
-            s_x[xskew(i)] = v;
+            XT v = XT(0.f);
+            if (g >= 0 && g < ti.L && bi >= 0 && bi < a.buf_len) v = __ldg(rowp + bi);
+            s_x[xskew<XT>(i)] = v;
         }
     }
 }
 
-template <bool kRef>
+template <bool kRef, typename XT>
 __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const KernelArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     // shared-memory carve-up (all offsets multiples of 16 bytes)
@@ -188,8 +183,8 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const KernelArgs a)
     const float* s_w = reinterpret_cast<const float*>(smem + a.off_w);
     const int* s_lo = reinterpret_cast<const int*>(smem + a.off_lo);
     const int* s_id = reinterpret_cast<const int*>(smem + a.off_id);
-    float* s_x = reinterpret_cast<float*>(smem + a.blob_bytes);
-    cf* s_e = reinterpret_cast<cf*>(s_x + kXFloats);
+    XT* s_x = reinterpret_cast<XT*>(smem + a.blob_bytes);
+    cf* s_e = reinterpret_cast<cf*>(smem + a.blob_bytes + kXFloats * sizeof(float));
     cf* s_p = s_e + kGroupsPerCta * kEGroup;
     unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_p + kGroupsPerCta * a.pstride);
 
@@ -216,7 +211,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const KernelArgs a)
     else { const int s = tid - kNormalThreads; g2 = s >> 1; row = 18 + (s & 1); }
     const int warp = tid >> 5, lane = tid & 31;
     const int M = a.layout.n_mels;
-    const float* xg = s_x + kXGroup * g1;
+    const XT* xg = s_x + XLayout<XT>::kGroup * g1;
     cf* e1 = s_e + g1 * kEGroup;
     const cf* e2 = s_e + g2 * kEGroup + c_row_slot[row] * kERow;
     float* p2w = reinterpret_cast<float*>(s_p + g2 * a.pstride);
@@ -225,7 +220,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const KernelArgs a)
 #pragma unroll
     for (int i = 0; i < kMelSlots; ++i) { lo[i] = s_lo[i * 20 + j]; mid[i] = s_id[i * 20 + j]; }
     float win[20];                                                      // this lane's 20 window taps stay in registers
-    load_window(j, s_win, win);
+    load_window(j, s_win, XLayout<XT>::kScale, win);
     double acc_s = 0.0, acc_q = 0.0;                                    // per-thread sums when partials are per CTA
     __syncthreads();                                                    // publishes an element-wise first tile
 
@@ -553,6 +548,12 @@ __global__ void synth_kernel(void* wave, int dtype, long long rows, long long n,
     }
 }
 
+typedef void (*logmel_kernel_t)(const KernelArgs);
+logmel_kernel_t kernel_for(bool ref_layout, int dtype) {
+    if (ref_layout) return dtype == TALFE_F32 ? logmel_kernel<true, float> : dtype == TALFE_F16 ? logmel_kernel<true, __half> : logmel_kernel<true, short>;
+    return dtype == TALFE_F32 ? logmel_kernel<false, float> : dtype == TALFE_F16 ? logmel_kernel<false, __half> : logmel_kernel<false, short>;
+}
+
 int cuda_fail(cudaError_t e) { g_last_cuda_error = (int)e; return TALFE_ERR_CUDA; }
 #define TALFE_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return cuda_fail(e__); } while (0)
 
@@ -638,9 +639,10 @@ int talfe_plan_create(talfe_plan** plan_out, int device, int n_mels, const float
     cudaError_t e = cudaMalloc(&p->blob_dev, t.blob_bytes);
     if (e == cudaSuccess) e = cudaMemcpy(p->blob_dev, t.blob.data(), t.blob_bytes, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, device);
-    auto kern = p->ref_layout ? logmel_kernel<true> : logmel_kernel<false>;
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p->ctas_per_sm, kern, kThreads, p->smem_bytes);
+    for (int dt = TALFE_F32; dt <= TALFE_I16 && e == cudaSuccess; ++dt)
+        e = cudaFuncSetAttribute(kernel_for(p->ref_layout != 0, dt), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes);
+    if (e == cudaSuccess)
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p->ctas_per_sm, kernel_for(p->ref_layout != 0, TALFE_F32), kThreads, p->smem_bytes);
     cudaSetDevice(prev);
     if (e != cudaSuccess) { if (p->blob_dev) cudaFree(p->blob_dev); delete p; return cuda_fail(e); }
     if (p->ctas_per_sm < 1) { cudaFree(p->blob_dev); delete p; return TALFE_ERR_UNSUPPORTED; }
@@ -704,8 +706,7 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
     const bool per_row = job->norm >= TALFE_NORM_ROW_MEAN;
     a.partials_per_tile = per_row ? 1 : 0;                // batch-wide sums: one slot per CTA is enough
     a.want_sumsq = job->stats != nullptr ? 1 : 0;         // the sum of squares is only ever reported, never needed by K3
-    if (plan->ref_layout) logmel_kernel<true><<<(unsigned)grid, kThreads, plan->smem_bytes, stream>>>(a);
-    else logmel_kernel<false><<<(unsigned)grid, kThreads, plan->smem_bytes, stream>>>(a);
+    kernel_for(plan->ref_layout != 0, a.dtype)<<<(unsigned)grid, kThreads, plan->smem_bytes, stream>>>(a);
     TALFE_CUDA(cudaGetLastError());
 
     if (!want_stats) return TALFE_OK;

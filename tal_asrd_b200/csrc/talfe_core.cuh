@@ -29,12 +29,13 @@
 //
 // Shared-memory layouts (bank-conflict analysis in DESIGN.md §4):
 //   waveform tile : sample i of the tile lives at i + 20 * (i / 320)  -> thread (g, j) reads word
-//                   340 g + j + const, i.e. consecutive lanes hit consecutive banks;
+//                   340 g + j + const, i.e. consecutive lanes hit consecutive banks (16-bit tiles: skew 24);
 //   exchange      : row stride 22 complex, group stride 452 complex (904 words = 8 mod 32);
 //   power         : float2 (P_a[k], P_b[k]) at index k, group stride `pstride` = 9 (mod 16) so that
 //                   lane r of group g writes word 18 g + r + const.
 #pragma once
 
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #ifndef TALFE_HD
@@ -52,9 +53,23 @@ constexpr int kMaxMels = 80;
 constexpr int kMelSlots = 4;          // mel m is owned by thread m % 20, slot m / 20
 constexpr int kERow = 22;             // exchange row stride in float2 (20 + 2 pad -> conflict-free LDS.128)
 constexpr int kEGroup = 452;          // exchange group stride in float2 (= 904 words, 8 mod 32)
-constexpr int kXBlock = 320;          // waveform tile: a skew of kXSkew floats after every kXBlock samples
-constexpr int kXSkew = 20;
-constexpr int kXGroup = kXBlock + kXSkew;   // 340: distance between the first samples of consecutive pairs
+constexpr int kXBlock = 320;          // waveform tile: a skew after every kXBlock samples (one TMA piece each)
+// Element type of the staged waveform tile: fp32, or the narrow on-disk / decoding formats kept narrow in
+// shared memory and widened in stage 1 (int16 PCM: the 1/32768 of torchaudio.load is folded into the window).
+// The skew keeps every TMA piece 16-byte aligned and spreads consecutive pairs over distinct banks.
+template <typename XT> struct XLayout {
+    static constexpr int kSkew = sizeof(XT) == 4 ? 20 : 24;
+    static constexpr int kGroup = kXBlock + kSkew;           // distance between the first samples of consecutive pairs
+    static constexpr float kScale = 1.0f;
+};
+template <> struct XLayout<short> {
+    static constexpr int kSkew = 24;
+    static constexpr int kGroup = kXBlock + kSkew;
+    static constexpr float kScale = 1.0f / 32768.0f;
+};
+TALFE_HD float x_to_float(float v) { return v; }
+TALFE_HD float x_to_float(short v) { return (float)v; }
+TALFE_HD float x_to_float(__half v) { return __half2float(v); }
 
 // the reference configuration (80 HTK mels): common widths per slot, compile-time unrolled
 constexpr int kRefW0 = 2, kRefW1 = 4, kRefW2 = 7, kRefW3 = 13;
@@ -155,34 +170,36 @@ TALFE_HD constexpr int row_slot(int row) {
 }
 
 // position of tile sample i inside the skewed waveform buffer
-TALFE_HD int xskew(int i) { return i + kXSkew * (i / kXBlock); }
+template <typename XT> TALFE_HD int xskew(int i) { return i + XLayout<XT>::kSkew * (i / kXBlock); }
 
 // ---------------------------------------------------------------------------------------------
-// Stage 1.  xg points at this pair's first sample inside the skewed tile (s_x + kXGroup * g);
+// Stage 1.  xg points at this pair's first sample inside the skewed tile (s_x + XLayout<XT>::kGroup * g);
 // frame a = samples 0..399 of the pair, frame b = samples 160..559.
 // win_t[j*20 + m] = 0.5 * hann[j + 20 m]  (the 0.5 makes A_a = C[k] + conj C[20-k] exact scale);
 // tw_t[j*10 + (k1-1)] = W400^(j k1) for k1 = 1..10.  Rows 18 / 19 (the packed k1 = 0 / 10 rows) are left
 // at half scale, which the power computation of stage 2 absorbs ((X/2 + X/2)^2 = |X|^2).
 // Writes this thread's column j of the 20 exchange rows.
-TALFE_HD void load_window(int j, const float* __restrict__ win_t, float (&win)[20]) {
+TALFE_HD void load_window(int j, const float* __restrict__ win_t, float scale, float (&win)[20]) {
     const float4* w4 = reinterpret_cast<const float4*>(win_t + j * 20);
 #pragma unroll
     for (int q = 0; q < 5; ++q) {
         const float4 w = w4[q];
-        win[4 * q] = w.x; win[4 * q + 1] = w.y; win[4 * q + 2] = w.z; win[4 * q + 3] = w.w;
+        win[4 * q] = w.x * scale; win[4 * q + 1] = w.y * scale; win[4 * q + 2] = w.z * scale; win[4 * q + 3] = w.w * scale;
     }
 }
 
-TALFE_HD void stage1(int j, const float* __restrict__ xg, const float (&win)[20],
+template <typename XT>
+TALFE_HD void stage1(int j, const XT* __restrict__ xg, const float (&win)[20],
                      const cf* __restrict__ tw_t, cf* __restrict__ e_group) {
     cf z[20];
-    const float* p = xg + j;
+    const XT* p = xg + j;
+    constexpr int kSkew = XLayout<XT>::kSkew;
 #pragma unroll
     for (int m = 0; m < 20; ++m) {
         // sample j + 20 m of frame a, j + 20 m + 160 of the pair for frame b, with the block skew
-        const int ia = 20 * m + (20 * m >= kXBlock ? kXSkew : 0);
-        const int ib = 20 * m + kHop + (20 * m + kHop >= kXBlock ? kXSkew : 0);
-        z[m] = make_float2(win[m] * p[ia], win[m] * p[ib]);
+        const int ia = 20 * m + (20 * m >= kXBlock ? kSkew : 0);
+        const int ib = 20 * m + kHop + (20 * m + kHop >= kXBlock ? kSkew : 0);
+        z[m] = make_float2(win[m] * x_to_float(p[ia]), win[m] * x_to_float(p[ib]));
     }
     fft20(z);
     const float4* t4 = reinterpret_cast<const float4*>(tw_t + j * 10);

@@ -282,3 +282,45 @@ def test_full_size_training_chunk_properties(mod, dev):
     xs = x[:2, 160:]
     ys = mod.features(xs.contiguous(), norm="none")
     assert float((ys[:, 2:2000] - raw[:2, 3:2001]).abs().max()) < 2e-4
+
+
+def test_ragged_batch_config4(mod, dev):
+    """BASELINE config 4: variable-length utterances (1 s .. 10 min), both padding semantics."""
+    from tal_asrd_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(4)
+    lens = np.exp(rng.uniform(np.log(16000), np.log(9_600_000), size=12)).astype(np.int64)
+    lens[0], lens[-1] = 16000, 9_600_000
+    Lmax = int(lens.max())
+    x = torch.zeros(len(lens), Lmax, device=dev)
+    for r, n in enumerate(lens):                                         # collater layout: zero right-pad
+        _lib.check(lib.talfe_synth_fill(x[r].data_ptr(), _lib.F32, 1, int(n), int(n), 2020, 100 + r, 0, None))
+    lens_t = torch.from_numpy(lens)
+    # (i) padded semantics == the reference on the padded batch: every row gets 1 + Lmax//160 frames
+    padded = mod(x)
+    assert padded.shape == (len(lens), 1 + Lmax // 160, 80)
+    assert abs(float(padded.double().mean())) < 2e-6
+    # (ii) per-row semantics: each row equals the front end run on that row alone
+    per_row = mod.features(x, audio_lens=lens_t, norm="row")
+    for r in (0, 3, len(lens) - 1):
+        n = int(lens[r])
+        alone = mod(x[r:r + 1, :n].contiguous())
+        T = 1 + n // 160
+        assert float((per_row[r, :T] - alone[0]).abs().max()) < 2e-5
+        assert not per_row[r, T:].any()
+    # short row against the float64 oracle end to end
+    r = int(np.argmin(lens))
+    ref, frames = O.logmel_rows_f64([x[r, :int(lens[r])].cpu().numpy()], mode="row")
+    assert rel_err(per_row[r, :frames[0]].cpu().numpy(), ref[0]) < TOL
+
+
+def test_invalid_arguments_fail_cleanly(mod, dev):
+    x = torch.zeros(2, 16000, device=dev)
+    with pytest.raises(ValueError):
+        mod.features(x, audio_lens=torch.tensor([16000]))               # one length per row required
+    with pytest.raises(KeyError):
+        mod.features(x, norm="bogus")
+    with pytest.raises(ValueError):
+        mod.features(x, out=torch.empty(2, 100, 80, device=dev))          # wrong out shape
+    y = mod(torch.zeros(1, 201, device=dev))                              # shortest legal input
+    assert y.shape == (1, 2, 80)

@@ -161,3 +161,48 @@ def test_corpus_pass_single_rank_global_cmvn():
     got = np.concatenate([f[0].cpu().numpy() for f in feats])
     want = (raw - raw.mean(0)) / raw.std(0)
     assert rel_err(got, want) < 5e-4
+
+
+def _nccl_corpus_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from tal_asrd_b200 import LogMelSpec, synth
+    from tal_asrd_b200.corpus import corpus_pass, shard_episodes
+    lengths = [64000, 48000, 100000, 16001, 80000]
+    mine = shard_episodes(lengths, world, rank)
+    mod = LogMelSpec().to(torch.device("cuda", rank))
+    eps_ = [torch.from_numpy(synth.waveform(1, i, 0, lengths[i])) for i in mine]
+    feats, stats = corpus_pass(mod, eps_, norm="row_mel_var", chunk_seconds=2.0)
+    torch.cuda.synchronize()
+    q.put((rank, mine, stats.block.cpu().numpy(), [f[0].cpu().numpy() for f in feats]))
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_corpus_pass_two_ranks_nccl_allreduce():
+    """BASELINE config 5 in miniature: episodes sharded over 2 GPUs, ONE all-reduce of the statistics block."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from oracle import logmel_oracle as O
+    from tal_asrd_b200 import synth
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_nccl_corpus_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    lengths = [64000, 48000, 100000, 16001, 80000]
+    raw = {i: O.logmel_unnormalised_f64(synth.waveform(1, i, 0, n)[None])[0] for i, n in enumerate(lengths)}
+    allraw = np.concatenate([raw[i] for i in range(len(lengths))])
+    assert np.array_equal(res[0][2], res[1][2])                            # both ranks hold the global sums
+    assert res[0][2][0, 0] == allraw.size
+    mu, sd = allraw.mean(0), allraw.std(0)
+    for rank, mine, _, feats in res:
+        for i, f in zip(mine, feats):
+            assert rel_err(f, (raw[i] - mu) / sd) < 5e-4
