@@ -134,6 +134,21 @@ int talfe_apply_stats(const talfe_plan* plan, float* feats, int64_t batch, int64
                       int64_t out_row_stride, int out_layout, int norm, const double* stats,
                       const int64_t* valid_frames, void* stream);
 
+/* One long episode streamed from HOST memory (pinned for full copy speed) in chunks of `chunk_frames`
+ * frames: chunk k+1 is copied host->device on the plan's side stream while chunk k is transformed on
+ * `stream`; chunk boundaries sit on hop multiples with 200-sample halos, reflection happens only at the
+ * true ends of the episode, statistics accumulate across chunks and the normalisation is applied once at
+ * the end — the result equals the one-shot transform of the whole episode, which is what the reference
+ * does (tal/baseline/reconcile.py:76-85 feeds a whole episode to LogMelSpec.forward).
+ * out: DEVICE [T, M] with T = 1 + total_len/160.  stats: DEVICE, TALFE_STATS_DOUBLES(M) doubles.
+ * staging: DEVICE, talfe_stream_staging_bytes() bytes.  workspace: talfe_workspace_bytes(plan, 1, chunk_frames).
+ * defer_normalise != 0 leaves `out` un-normalised and `stats` holding the sums (dataset-level statistics).
+ * One episode at a time per plan (the side stream and its events belong to the plan). */
+size_t talfe_stream_staging_bytes(int wave_dtype, int64_t chunk_frames);
+int talfe_stream_episode(const talfe_plan* plan, const void* wave_host, int wave_dtype, int64_t total_len,
+                         int64_t chunk_frames, float* out, int norm, int defer_normalise, double* stats, float eps,
+                         void* staging, size_t staging_bytes, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Dataset-level statistics across ranks: in-place sum of `count` doubles over the communicator.
  * nccl_comm is an ncclComm_t created by the caller; NCCL is resolved at run time with dlopen
  * ("libnccl.so.2"), so the library itself has no link-time dependency on it. */

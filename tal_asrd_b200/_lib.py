@@ -16,7 +16,8 @@ ERR_TOO_SHORT = -2
 EXPORTED = [
     "talfe_version", "talfe_strerror", "talfe_last_cuda_error", "talfe_num_frames", "talfe_plan_create",
     "talfe_plan_destroy", "talfe_plan_n_mels", "talfe_workspace_bytes", "talfe_run", "talfe_logmel_forward",
-    "talfe_apply_stats", "talfe_allreduce_stats", "talfe_synth_fill",
+    "talfe_apply_stats", "talfe_allreduce_stats", "talfe_synth_fill", "talfe_stream_staging_bytes",
+    "talfe_stream_episode",
 ]
 
 
@@ -70,6 +71,11 @@ def load() -> ctypes.CDLL:
     lib.talfe_apply_stats.restype = c_int
     lib.talfe_apply_stats.argtypes = [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_void_p,
                                       c_void_p, c_void_p]
+    lib.talfe_stream_staging_bytes.restype = c_size_t
+    lib.talfe_stream_staging_bytes.argtypes = [c_int, c_int64]
+    lib.talfe_stream_episode.restype = c_int
+    lib.talfe_stream_episode.argtypes = [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_int, c_int, c_void_p,
+                                         c_float, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p]
     lib.talfe_allreduce_stats.restype = c_int
     lib.talfe_allreduce_stats.argtypes = [c_void_p, c_int64, c_void_p, c_void_p]
     lib.talfe_synth_fill.restype = c_int

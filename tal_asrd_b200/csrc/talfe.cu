@@ -56,6 +56,10 @@ struct talfe_plan_impl {
     size_t off_tw, off_w, off_lo, off_id, blob_bytes;
     unsigned char* blob_dev;
     size_t smem_bytes;
+    // streaming (talfe_stream_episode): a side stream for host->device chunk copies and the events that
+    // hand the two staging buffers back and forth; created with the plan, never on the hot path
+    cudaStream_t copy_stream;
+    cudaEvent_t ev_ready[2], ev_free[2];
 };
 
 struct KernelArgs {
@@ -643,6 +647,11 @@ int talfe_plan_create(talfe_plan** plan_out, int device, int n_mels, const float
         e = cudaFuncSetAttribute(kernel_for(p->ref_layout != 0, dt), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes);
     if (e == cudaSuccess)
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p->ctas_per_sm, kernel_for(p->ref_layout != 0, TALFE_F32), kThreads, p->smem_bytes);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = cudaEventCreateWithFlags(&p->ev_ready[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_free[i], cudaEventDisableTiming);
+    }
     cudaSetDevice(prev);
     if (e != cudaSuccess) { if (p->blob_dev) cudaFree(p->blob_dev); delete p; return cuda_fail(e); }
     if (p->ctas_per_sm < 1) { cudaFree(p->blob_dev); delete p; return TALFE_ERR_UNSUPPORTED; }
@@ -653,6 +662,11 @@ int talfe_plan_create(talfe_plan** plan_out, int device, int n_mels, const float
 void talfe_plan_destroy(talfe_plan* plan) {
     if (!plan) return;
     if (plan->blob_dev) cudaFree(plan->blob_dev);
+    if (plan->copy_stream) cudaStreamDestroy(plan->copy_stream);
+    for (int i = 0; i < 2; ++i) {
+        if (plan->ev_ready[i]) cudaEventDestroy(plan->ev_ready[i]);
+        if (plan->ev_free[i]) cudaEventDestroy(plan->ev_free[i]);
+    }
     delete plan;
 }
 
@@ -769,6 +783,62 @@ int talfe_apply_stats(const talfe_plan* plan, float* feats, int64_t batch, int64
         feats, batch, n_frames, ors, out_layout, M, norm, stats, reinterpret_cast<const long long*>(valid_frames), nullptr, 0);
     TALFE_CUDA(cudaGetLastError());
     return TALFE_OK;
+}
+
+// ---- streaming of one long episode from (pinned) host memory, native loop: no per-chunk interpreter cost
+size_t talfe_stream_staging_bytes(int wave_dtype, int64_t chunk_frames) {
+    if (chunk_frames < 1 || wave_dtype < TALFE_F32 || wave_dtype > TALFE_I16) return 0;
+    const size_t elt = wave_dtype == TALFE_F32 ? 4 : 2;
+    const size_t per = align_up((size_t)(kHop * chunk_frames + kNfft + kHalf) * elt, 256);
+    return 2 * per;
+}
+
+int talfe_stream_episode(const talfe_plan* plan, const void* wave_host, int wave_dtype, int64_t total_len,
+                         int64_t chunk_frames, float* out, int norm, int defer_normalise, double* stats, float eps,
+                         void* staging, size_t staging_bytes, void* workspace, size_t workspace_bytes, void* stream_v) {
+    if (!plan || !wave_host || !out || !stats || !staging || chunk_frames < 1) return TALFE_ERR_INVALID;
+    if (total_len <= kHalf) return TALFE_ERR_TOO_SHORT;
+    if (wave_dtype < TALFE_F32 || wave_dtype > TALFE_I16) return TALFE_ERR_INVALID;
+    if (norm < TALFE_NORM_NONE || norm > TALFE_NORM_ROW_MEL_MEANVAR) return TALFE_ERR_INVALID;
+    if (staging_bytes < talfe_stream_staging_bytes(wave_dtype, chunk_frames)) return TALFE_ERR_WORKSPACE;
+    const size_t elt = wave_dtype == TALFE_F32 ? 4 : 2;
+    const size_t per = staging_bytes / 2 / 256 * 256;
+    const int64_t T = 1 + total_len / kHop;
+    const int M = plan->n_mels;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+    talfe_plan* pl = const_cast<talfe_plan*>(plan);
+    int k = 0;
+    for (int64_t f0 = 0; f0 < T; f0 += chunk_frames, ++k) {
+        const int64_t f1 = std::min<int64_t>(T, f0 + chunk_frames);
+        // samples the frames span, widened where an edge reflects back into the episode
+        int64_t lo = kHop * f0 - kHalf, hi = kHop * (f1 - 1) + kHalf, need_lo = lo, need_hi = hi;
+        if (hi > total_len) need_lo = std::min(need_lo, 2 * (total_len - 1) - (hi - 1));
+        if (lo < 0) need_hi = std::max(need_hi, -lo + 1);
+        lo = std::max<int64_t>(0, need_lo);
+        hi = std::min<int64_t>(total_len, need_hi);
+        lo -= lo % 8;                                          // keep the chunk origin 16-byte aligned -> TMA fast path
+        const int b = k & 1;
+        unsigned char* buf = reinterpret_cast<unsigned char*>(staging) + b * per;
+        if ((size_t)(hi - lo) * elt > per) return TALFE_ERR_WORKSPACE;
+        // staging buffer b is free once the transform that last read it has run (also orders against a previous episode;
+        // waiting on a never-recorded event is a no-op)
+        TALFE_CUDA(cudaStreamWaitEvent(pl->copy_stream, pl->ev_free[b], 0));
+        TALFE_CUDA(cudaMemcpyAsync(buf, reinterpret_cast<const unsigned char*>(wave_host) + lo * elt, (size_t)(hi - lo) * elt,
+                                   cudaMemcpyHostToDevice, pl->copy_stream));
+        TALFE_CUDA(cudaEventRecord(pl->ev_ready[b], pl->copy_stream));
+        TALFE_CUDA(cudaStreamWaitEvent(stream, pl->ev_ready[b], 0));
+        talfe_job job{};
+        job.wave = buf; job.wave_dtype = wave_dtype; job.norm = norm; job.batch = 1; job.row_stride = hi - lo;
+        job.buf_len = hi - lo; job.origin = lo; job.total_len = total_len; job.lens = nullptr;
+        job.frame0 = f0; job.n_frames = f1 - f0; job.out = out + f0 * M; job.out_row_stride = 0;
+        job.out_layout = TALFE_LAYOUT_TM; job.accumulate_stats = k > 0; job.eps = eps; job.defer_normalise = 1;
+        job.stats = stats; job.workspace = workspace; job.workspace_bytes = workspace_bytes; job.stream = stream_v;
+        const int rc = talfe_run(plan, &job);
+        if (rc) return rc;
+        TALFE_CUDA(cudaEventRecord(pl->ev_free[b], stream));
+    }
+    if (norm == TALFE_NORM_NONE || defer_normalise) return TALFE_OK;
+    return talfe_apply_stats(plan, out, 1, T, 0, TALFE_LAYOUT_TM, norm, stats, nullptr, stream_v);
 }
 
 // ---- NCCL, resolved at run time so that the library has no link-time dependency on it

@@ -67,6 +67,20 @@ def stream_episode(frontend: LogMelSpec, episode: torch.Tensor, chunk_seconds: f
         chunks = chunk_plan(L, chunk_frames)
         compute = torch.cuda.current_stream(device)
         on_device = episode.is_cuda
+        if not on_device and episode.is_contiguous():
+            # native loop (talfe_stream_episode): copies and transforms are enqueued from C, chunk after chunk
+            lib = plan.lib
+            code = _DTYPES[episode.dtype]
+            staging = torch.empty(int(lib.talfe_stream_staging_bytes(code, chunk_frames)), dtype=torch.uint8, device=device)
+            ws_bytes = plan.workspace_bytes(1, min(chunk_frames, T))
+            workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+            _lib.check(lib.talfe_stream_episode(plan.handle, episode.data_ptr(), code, L, chunk_frames, out.data_ptr(),
+                                                _NORMS[norm], 0 if normalise else 1, stats.data_ptr(), frontend.eps,
+                                                staging.data_ptr(), staging.numel(), workspace.data_ptr(), ws_bytes,
+                                                compute.cuda_stream), "talfe_stream_episode")
+            # every side-stream copy into `staging` is followed (through an event) by a transform already queued on
+            # `compute`, so handing the blocks back to the caching allocator here is ordered correctly
+            return out
         if not on_device:
             copy_stream = torch.cuda.Stream(device)
             max_n = max(hi - lo for _, _, lo, hi in chunks)
