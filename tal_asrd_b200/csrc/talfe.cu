@@ -201,6 +201,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const KernelArgs a)
         for (int i = tid; i < kGroupsPerCta * a.pstride; i += kThreads) s_p[i] = make_float2(0.f, 0.f);
     }
     __syncthreads();                                                    // tables + mbarrier visible
+    cudaGridDependencySynchronize();       // launched programmatically: everything above overlapped the previous kernel's tail
     int tile = blockIdx.x;
     TileInfo ti;
     ti.row = tile / a.tiles_per_row;
@@ -490,6 +491,7 @@ __global__ void __launch_bounds__(256) sub_scalar_flat_kernel(float4* __restrict
     // every block re-derives the scalar from the few-hundred per-CTA partials K1 left in L2 (fixed order:
     // identical in every block and every run), which removes a separate reduction launch from the path
     __shared__ double s_a[256], s_b[256];
+    cudaGridDependencySynchronize();                  // K1 (the preceding kernel in the stream) has completed and flushed
     double ra = 0.0, rb = 0.0;
     for (int i = threadIdx.x; i < n_partials; i += 256) { const double2 v = partials[i]; ra += v.x; rb += v.y; }
     s_a[threadIdx.x] = ra; s_b[threadIdx.x] = rb;
@@ -720,8 +722,15 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
     const bool per_row = job->norm >= TALFE_NORM_ROW_MEAN;
     a.partials_per_tile = per_row ? 1 : 0;                // batch-wide sums: one slot per CTA is enough
     a.want_sumsq = job->stats != nullptr ? 1 : 0;         // the sum of squares is only ever reported, never needed by K3
-    kernel_for(plan->ref_layout != 0, a.dtype)<<<(unsigned)grid, kThreads, plan->smem_bytes, stream>>>(a);
-    TALFE_CUDA(cudaGetLastError());
+    {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = plan->smem_bytes; cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        TALFE_CUDA(cudaLaunchKernelEx(&cfg, kernel_for(plan->ref_layout != 0, a.dtype), (const KernelArgs)a));
+    }
 
     if (!want_stats) return TALFE_OK;
     double* stats = job->stats ? job->stats : reinterpret_cast<double*>(ws + w.scratch_stats);
@@ -732,9 +741,16 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
         // derives the mean from the per-CTA partials itself (no separate reduction launch)
         const long long total = dense * job->batch, n4 = total / 4;
         const unsigned blocks = (unsigned)std::max<long long>(1, std::min<long long>((n4 + 1023) / 1024, (long long)plan->sm_count * 8));
-        sub_scalar_flat_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<float4*>(job->out), n4, job->out + 4 * n4,
-                                                           (int)(total - 4 * n4), a.partials, (int)grid, (double)total, job->stats);
-        TALFE_CUDA(cudaGetLastError());
+        // programmatic dependent launch: the sweep's blocks are scheduled while K1 drains and wait at
+        // cudaGridDependencySynchronize() for its memory to be visible, which hides the launch gap
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        TALFE_CUDA(cudaLaunchKernelEx(&cfg, sub_scalar_flat_kernel, reinterpret_cast<float4*>(job->out), n4, job->out + 4 * n4,
+                                      (int)(total - 4 * n4), (const double2*)a.partials, (int)grid, (double)total, job->stats));
         return TALFE_OK;
     }
     const long long blocks = per_row ? job->batch : 1;
