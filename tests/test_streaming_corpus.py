@@ -193,7 +193,7 @@ def test_corpus_pass_two_ranks_nccl_allreduce():
     procs = [ctx.Process(target=_nccl_corpus_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = sorted([q.get(timeout=300) for _ in procs], key=lambda t: t[0])
+    res = sorted([q.get(timeout=90) for _ in procs], key=lambda t: t[0])
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -206,3 +206,58 @@ def test_corpus_pass_two_ranks_nccl_allreduce():
     for rank, mine, _, feats in res:
         for i, f in zip(mine, feats):
             assert rel_err(f, (raw[i] - mu) / sd) < 5e-4
+
+
+def _nccl_c_abi_worker(rank, world, port, q):
+    """talfe_allreduce_stats with an ncclComm_t created through NCCL's own C API (no torch.distributed collectives)."""
+    import ctypes
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)            # only to ship the 128-byte unique id
+    import glob
+    import nvidia.nccl  # noqa: F401  (torch's bundled NCCL; a namespace package: use __path__)
+    cands = sorted(glob.glob(os.path.join(list(nvidia.nccl.__path__)[0], "lib", "libnccl.so*")))
+    nccl = ctypes.CDLL(cands[0], mode=ctypes.RTLD_GLOBAL)
+    uid = (ctypes.c_byte * 128)()
+    if rank == 0:
+        assert nccl.ncclGetUniqueId(ctypes.byref(uid)) == 0
+    t = torch.tensor(list(bytes(uid)), dtype=torch.uint8)
+    dist.broadcast(t, 0)
+    uid = (ctypes.c_byte * 128).from_buffer_copy(bytes(t.tolist()))
+    comm = ctypes.c_void_p()
+
+    class UID(ctypes.Structure):
+        _fields_ = [("internal", ctypes.c_byte * 128)]
+    nccl.ncclCommInitRank.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, UID, ctypes.c_int]
+    u = UID()
+    ctypes.memmove(ctypes.byref(u), uid, 128)
+    assert nccl.ncclCommInitRank(ctypes.byref(comm), world, u, rank) == 0
+    from tal_asrd_b200 import _lib
+    lib = _lib.load()
+    stats = torch.arange(163, dtype=torch.float64, device=f"cuda:{rank}") * (rank + 1)
+    rc = lib.talfe_allreduce_stats(stats.data_ptr(), 163, comm, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    q.put((rank, rc, stats.cpu().numpy()))
+    nccl.ncclCommDestroy.argtypes = [ctypes.c_void_p]
+    nccl.ncclCommDestroy(comm)
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_c_abi_allreduce_stats_two_ranks():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_nccl_c_abi_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=90) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = np.arange(163, dtype=np.float64) * 3
+    for rank, rc, got in res:
+        assert rc == 0 and np.array_equal(got, want)
