@@ -69,6 +69,8 @@ struct KernelArgs {
     int batch, buf_len, origin, total_len;     // sample indices fit 31 bits (checked on the host; lens[] is clamped)
     const long long* lens;
     int frame0, n_frames, frame_end;           // frame_end = frame0 + n_frames
+    int t_end_const;                           // min(frame_end, 1 + total_len / 160) when lens == nullptr
+    int align_ok;                              // every interior tile of every row starts 16-byte aligned
     float* out;
     long long out_row_stride;
     int out_layout;
@@ -101,10 +103,10 @@ __device__ __forceinline__ unsigned long long l2_evict_first_policy() {
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
     return pol;
 }
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar,
-                                         unsigned long long policy) {
+__device__ __forceinline__ void bulk_g2s_u32(unsigned smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar,
+                                             unsigned long long policy) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
-                     smem_u32(smem_dst)),
+                     smem_dst),
                  "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
                  : "memory");
 }
@@ -128,42 +130,50 @@ struct TileInfo {
     bool bulk;                     // staged by the copy engine (completion on the mbarrier)
 };
 
+// Per-tile bookkeeping is executed by every warp (uniform datapath); it is kept to a handful of 32-bit
+// operations: everything that does not depend on the tile is folded into KernelArgs on the host.
 __device__ __forceinline__ void tile_fill(const KernelArgs& a, TileInfo& ti) {
     ti.t0 = a.frame0 + ti.tq * kFramesPerTile;
-    ti.L = a.lens ? (int)min(a.lens[ti.row], (long long)kMaxSamples) : a.total_len;
-    const int T_row = ti.L > kHalf ? 1 + ti.L / kHop : 0;               // frames this row really has
-    ti.t_end = min(a.frame_end, T_row);                                 // valid frames are t < t_end
+    if (a.lens) {
+        ti.L = (int)min(a.lens[ti.row], (long long)kMaxSamples);
+        ti.t_end = min(a.frame_end, ti.L > kHalf ? 1 + ti.L / kHop : 0);
+    } else {
+        ti.L = a.total_len;
+        ti.t_end = a.t_end_const;                                       // min(frame_end, 1 + total_len / 160)
+    }
     ti.active = ti.t0 < ti.t_end;
     ti.full = ti.t0 + kFramesPerTile <= ti.t_end;
     ti.bulk = false;
 }
 
+// what one warp contributes to a tile fetch: pieces `warp` and `warp + 10` of the 17 (constant per kernel)
+struct WarpCopy {
+    unsigned dst0, dst1;           // shared-memory addresses of the two pieces
+    int off0, off1;                // source offsets in elements
+    unsigned bytes0, bytes1;       // bytes1 == 0: this warp has a single piece
+    unsigned long long policy;     // L2 evict-first
+};
+
 // Stage 0: waveform tile -> shared memory, skewed layout (talfe_core.cuh).  Interior tiles of an
-// aligned fp32 row are fetched by the copy engine (cp.async.bulk, one 1280-byte piece per 320-sample
-// block so that the skew can be inserted; completion is signalled on `bar`).  Edge tiles (reflection),
-// narrow dtypes and unaligned rows take the synchronous element-wise path; the barrier that follows
-// in program order (B3, or the set-up barrier for the first tile) publishes them.
+// aligned row are fetched by the copy engine (cp.async.bulk, one piece per 320-sample block so that the
+// skew can be inserted; completion is signalled on `bar`); one elected lane per warp issues that warp's
+// one or two pieces, thread 0 posts the byte count.  Edge tiles (reflection) and unaligned rows take the
+// synchronous element-wise path; the barrier that follows in program order publishes them.
 template <typename XT>
-__device__ __forceinline__ void load_tile(const KernelArgs& a, TileInfo& ti, XT* s_x, unsigned long long* bar, int tid) {
+__device__ __forceinline__ void load_tile(const KernelArgs& a, TileInfo& ti, XT* s_x, unsigned long long* bar,
+                                          const WarpCopy& wc, int tid) {
     if (!ti.active) return;
-    constexpr int kXG = XLayout<XT>::kGroup;
     const int s0 = kHop * ti.t0 - kHalf;                                // episode index of tile sample 0
     const int b0 = s0 - a.origin;                                       // buffer index of tile sample 0
     const XT* rowp = reinterpret_cast<const XT*>(a.wave) + (long long)ti.row * a.row_stride;
     const bool interior = s0 >= 0 && s0 + kTileSamples <= ti.L && b0 >= 0 && b0 + kTileSamples <= a.buf_len;
-    if (interior && (reinterpret_cast<unsigned long long>(rowp + b0) & 15ull) == 0) {
+    if (interior && a.align_ok) {
         ti.bulk = true;
-        // one elected lane per warp issues its share of the 17 pieces (a single thread issuing all of
-        // them sat on the critical path of the following barrier); thread 0 posts the byte count
         if ((tid & 31) == 0) {
             const XT* src = rowp + b0;
             if (tid == 0) mbar_expect_tx(bar, kTileSamples * (int)sizeof(XT));
-            const unsigned long long pol = l2_evict_first_policy();
-#pragma unroll 1
-            for (int blk = tid >> 5; blk * kXBlock < kTileSamples; blk += kWarps) {
-                const int n = min(kXBlock, kTileSamples - blk * kXBlock);
-                bulk_g2s(s_x + blk * kXG, src + blk * kXBlock, n * (int)sizeof(XT), bar, pol);
-            }
+            bulk_g2s_u32(wc.dst0, src + wc.off0, wc.bytes0, bar, wc.policy);
+            if (wc.bytes1) bulk_g2s_u32(wc.dst1, src + wc.off1, wc.bytes1, bar, wc.policy);
         }
     } else {
         for (int i = tid; i < kTileSamples; i += kThreads) {
@@ -203,11 +213,21 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const KernelArgs a)
     __syncthreads();                                                    // tables + mbarrier visible
     cudaGridDependencySynchronize();       // launched programmatically: everything above overlapped the previous kernel's tail
     int tile = blockIdx.x;
+    WarpCopy wc;
+    {
+        constexpr int kXG = XLayout<XT>::kGroup;
+        const int b0 = tid >> 5, b1 = b0 + kWarps;
+        wc.dst0 = smem_u32(s_x + b0 * kXG); wc.off0 = b0 * kXBlock;
+        wc.bytes0 = (unsigned)(min(kXBlock, kTileSamples - b0 * kXBlock) * (int)sizeof(XT));
+        wc.dst1 = smem_u32(s_x + b1 * kXG); wc.off1 = b1 * kXBlock;
+        wc.bytes1 = b1 * kXBlock < kTileSamples ? (unsigned)(min(kXBlock, kTileSamples - b1 * kXBlock) * (int)sizeof(XT)) : 0u;
+        wc.policy = l2_evict_first_policy();
+    }
     TileInfo ti;
     ti.row = tile / a.tiles_per_row;
     ti.tq = tile - ti.row * a.tiles_per_row;
     tile_fill(a, ti);
-    if (tile < a.n_tiles) load_tile(a, ti, s_x, s_bar, tid);
+    if (tile < a.n_tiles) load_tile(a, ti, s_x, s_bar, wc, tid);
     unsigned parity = 0;
     // roles: stage 1 and the mel stage use (pair g1, lane j); stage 2 uses (pair g2, exchange row)
     const int g1 = tid / kGroup, j = tid - g1 * kGroup;
@@ -310,7 +330,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const KernelArgs a)
             ti.tq += gridDim.x;
             while (ti.tq >= a.tiles_per_row) { ti.tq -= a.tiles_per_row; ++ti.row; }
             tile_fill(a, ti);
-            load_tile(a, ti, s_x, s_bar, tid);
+            load_tile(a, ti, s_x, s_bar, wc, tid);
         }
         if (cur.active) {                                               // phase A: stage 2
             cf v[20];
@@ -708,6 +728,14 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
     a.batch = (int)job->batch; a.row_stride = job->row_stride; a.buf_len = (int)job->buf_len; a.origin = (int)job->origin;
     a.total_len = (int)job->total_len; a.lens = reinterpret_cast<const long long*>(job->lens);
     a.frame0 = (int)job->frame0; a.n_frames = (int)job->n_frames; a.frame_end = a.frame0 + a.n_frames;
+    a.t_end_const = (int)std::min<long long>(a.frame_end, job->total_len > kHalf ? 1 + job->total_len / kHop : 0);
+    {
+        // 160 samples (one hop) are a multiple of 16 bytes for every element type, so whether an interior tile of
+        // any row starts 16-byte aligned depends only on the base pointer, the row pitch and the chunk origin
+        const long long elt = job->wave_dtype == TALFE_F32 ? 4 : 2;
+        a.align_ok = ((reinterpret_cast<uintptr_t>(job->wave) & 15) == 0 && ((job->row_stride * elt) & 15) == 0 &&
+                      (((kHalf + job->origin) * elt) & 15) == 0) ? 1 : 0;
+    }
     a.out = job->out; a.out_row_stride = ors; a.out_layout = job->out_layout; a.eps = job->eps;
     if (w.n_tiles > 0x7fffffffLL) return TALFE_ERR_UNSUPPORTED;
     a.tiles_per_row = (int)w.tiles_per_row; a.n_tiles = (int)w.n_tiles;
