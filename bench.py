@@ -271,7 +271,7 @@ def run_ours(args):
                        "l2_policy": "3 rotating input batches (369 MB) + 2 output buffers (123 MB) > 126 MB L2",
                        "parallelism": f"episode-sharded x{world}, no data-path collective"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": 2 * args.steps,        # logmel_kernel + sub_scalar_flat_kernel per step "clocks": clocks.summary(),
+            "gpu_launches": 2 * args.steps, "clocks": clocks.summary(),   # logmel_kernel + sub_scalar_flat_kernel per step "clocks": clocks.summary(),
         }
         print(json.dumps(line), flush=True)
     if world > 1:
