@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TALFE_VERSION 100 /* major * 100 + minor */
+#define TALFE_VERSION 101 /* major * 100 + minor */
 
 typedef enum talfe_status {
     TALFE_OK = 0,
@@ -95,6 +95,13 @@ typedef struct talfe_job {
     void* workspace;         /* DEVICE: at least talfe_workspace_bytes() bytes                                */
     size_t workspace_bytes;
     void* stream;            /* cudaStream_t                                                                  */
+    /* --- extensions beyond LogMelSpec.forward (all NULL / 0 for the reference behaviour) ---                */
+    const int64_t* out_offsets; /* DEVICE or NULL: packed ragged output [sum T_i, M]: row r starts at frame    */
+                             /*   out_offsets[r]; requires lens and TM layout; no padding frames are written   */
+    const int32_t* freq_bands;  /* DEVICE [B, n_bands, 2] (first mel, end mel): SpecAugment frequency masks, set */
+                             /*   to 0 after normalisation like freq_mask(), tal/asr/models.py:531-548          */
+    const int32_t* time_bands;  /* DEVICE [B, n_bands, 2] (first frame, end frame): time_mask(), models.py:550-566 */
+    int32_t n_bands;         /* bands per row and axis, 0..16 (empty bands: first == end)                       */
 } talfe_job;
 
 int talfe_version(void);

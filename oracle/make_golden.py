@@ -98,6 +98,16 @@ def main():
     np.savez_compressed(os.path.join(GOLDEN, "frame_counts.npz"),
                         lengths=np.array(list(counts.keys())), frames=np.array(list(counts.values())),
                         raises_runtime_error=np.array(errors))
+    # SpecAugment (tal/asr/models.py:531-566): what time_mask(freq_mask(x)) zeroes for a given `random` seed
+    import random
+    ref_models = ref_import.load_reference_models()
+    sa = {}
+    for seed in (0, 1, 2, 3, 7, 11, 2020):
+        random.seed(seed)
+        ones = torch.ones(4, 300, 80)
+        masked = ref_models.time_mask(ref_models.freq_mask(ones))
+        sa[f"seed_{seed}"] = np.packbits((masked == 0).numpy())
+    np.savez_compressed(os.path.join(GOLDEN, "specaug_masks.npz"), shape=np.array([4, 300, 80]), **sa)
     with open(os.path.join(GOLDEN, "CASES.txt"), "w") as fh:
         fh.write("\n".join(names) + "\n")
     print("frame counts", counts, "errors", errors)

@@ -6,7 +6,7 @@ Public surface:
     reference_tables      fp32 window / mel filterbank, bit-identical to the reference's buffers
     synth                 deterministic synthetic audio (numpy; CUDA twin: talfe_synth_fill)
 """
-from . import synth  # noqa: F401
+from . import specaug, synth  # noqa: F401
 from .frontend import DEFAULT_SR, LogMelSpec, num_frames, reference_tables  # noqa: F401
 
 __all__ = ["LogMelSpec", "num_frames", "reference_tables", "synth", "DEFAULT_SR"]

@@ -30,6 +30,7 @@ class Job(ctypes.Structure):
         ("out", c_void_p), ("out_row_stride", c_int64), ("out_layout", c_int32), ("accumulate_stats", c_int32),
         ("eps", c_float), ("defer_normalise", c_int32), ("stats", c_void_p),
         ("workspace", c_void_p), ("workspace_bytes", c_size_t), ("stream", c_void_p),
+        ("out_offsets", c_void_p), ("freq_bands", c_void_p), ("time_bands", c_void_p), ("n_bands", c_int32),
     ]
 
 

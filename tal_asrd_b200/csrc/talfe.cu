@@ -37,6 +37,7 @@ constexpr int kTileSamples = kHop * kFramesPerTile + (kNfft - kHop);   // 5360
 constexpr int kXFloats = (kTileSamples + 24 * ((kTileSamples - 1) / kXBlock) + 3) & ~3;   // skewed tile in elements (fp32 sizing)
 constexpr int kNormalThreads = 18 * kGroupsPerCta;          // 288 = 9 full warps; warp 9 = packed rows 0/10
 constexpr int kMaxSamples = 0x7fff0000;                     // sample / frame indices are 32-bit on the device
+constexpr int kMaxBands = 16;                               // SpecAugment bands per row and axis
 constexpr int kColChunk = 2048;                             // frames per block in the per-mel statistics pass
 static_assert(kNormalThreads % 32 == 0, "special rows must fill whole warps");
 
@@ -73,6 +74,7 @@ struct KernelArgs {
     int align_ok;                              // every interior tile of every row starts 16-byte aligned
     float* out;
     long long out_row_stride;
+    const long long* out_offsets;   // packed ragged output: row r starts at frame out_offsets[r] (nullptr = padded rows)
     int out_layout;
     float eps;
     int tiles_per_row, n_tiles;
@@ -259,7 +261,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const KernelArgs a)
         if (t.active) stage1(j, xg, win, s_tw, e1);
     };
     auto run_mel = [&](const TileInfo& cur, int cur_tile) {
-        float* out_row = a.out + (long long)cur.row * a.out_row_stride;
+        float* out_row = a.out + (a.out_offsets ? a.out_offsets[cur.row] * M : (long long)cur.row * a.out_row_stride);
         float sum = 0.f, sumsq = 0.f;
         if (cur.active) {
             float y[2 * kMelSlots];
@@ -286,7 +288,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const KernelArgs a)
 #pragma unroll
                         for (int i = 0; i < kMelSlots; ++i) {
                             const int m = mid[i];
-                            if (m >= 0) {
+                            if (m >= 0 && (valid || !a.out_offsets)) {
                                 const float v = valid ? y[2 * i + f] : 0.f;
                                 sum += v;
                                 if (a.want_sumsq) sumsq = fmaf(v, v, sumsq);
@@ -297,7 +299,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const KernelArgs a)
                     }
                 }
             }
-        } else {
+        } else if (!a.out_offsets) {
             // tile lies entirely beyond this row's own frames ("each row as if alone"): zero fill
             const int nfr = min(kFramesPerTile, a.frame_end - cur.t0);
             for (int i = tid; i < nfr * M; i += kThreads) {
@@ -402,7 +404,8 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const double2* __r
 // Per-mel column sums of un-normalised features (extension modes 3/4).  grid (chunks, B).
 __global__ void __launch_bounds__(320) colstats_kernel(const float* __restrict__ feats, long long out_row_stride, int out_layout,
                                                        long long n_frames, int n_mels, const long long* __restrict__ lens,
-                                                       long long total_len, long long frame0, double* __restrict__ colpart) {
+                                                       long long total_len, long long frame0, double* __restrict__ colpart,
+                                                       const long long* __restrict__ out_offsets) {
     __shared__ double s_sum[4][kMaxMels], s_sq[4][kMaxMels];
     const long long row = blockIdx.y, chunk = blockIdx.x;
     const long long L = lens ? lens[row] : total_len;
@@ -411,7 +414,7 @@ __global__ void __launch_bounds__(320) colstats_kernel(const float* __restrict__
     if (valid < 0) valid = 0;
     const int m = threadIdx.x % kMaxMels, lane_f = threadIdx.x / kMaxMels;       // 80 mels x 4 frame lanes
     const long long f_lo = chunk * kColChunk, f_hi = min(f_lo + kColChunk, valid);
-    const float* base = feats + row * out_row_stride;
+    const float* base = feats + (out_offsets ? out_offsets[row] * n_mels : row * out_row_stride);
     double a = 0.0, b = 0.0;
     if (m < n_mels)
         for (long long f = f_lo + lane_f; f < f_hi; f += 4) {
@@ -446,8 +449,12 @@ __global__ void colstats_finish_kernel(const double* __restrict__ colpart, int c
 __global__ void __launch_bounds__(256) apply_stats_kernel(float* __restrict__ feats, long long batch, long long n_frames,
                                                           long long out_row_stride, int out_layout, int n_mels, int norm,
                                                           const double* __restrict__ stats, const long long* __restrict__ valid_frames,
-                                                          const long long* __restrict__ lens, long long frame0) {
+                                                          const long long* __restrict__ lens, long long frame0,
+                                                          const long long* __restrict__ out_offsets,
+                                                          const int* __restrict__ freq_bands, const int* __restrict__ time_bands,
+                                                          int n_bands) {
     __shared__ float s_mean[kMaxMels], s_rstd[kMaxMels];
+    __shared__ int s_tb[2 * kMaxBands];
     const long long row = blockIdx.y;
     const double* s = stats + (norm == TALFE_NORM_BATCH_MEAN ? 0 : row * TALFE_STATS_DOUBLES(n_mels));
     long long valid = n_frames;
@@ -470,34 +477,49 @@ __global__ void __launch_bounds__(256) apply_stats_kernel(float* __restrict__ fe
                 rstd = (float)rsqrt(var);
             }
         }
+        // SpecAugment frequency bands (tal/asr/models.py:531-548 sets them to 0 AFTER the mean subtraction):
+        // a masked mel keeps its mean but gets a zero scale, so (x - mean) * 0 = 0
+        for (int k = 0; k < n_bands; ++k) {
+            const int lo_m = freq_bands[(row * n_bands + k) * 2], hi_m = freq_bands[(row * n_bands + k) * 2 + 1];
+            if ((int)threadIdx.x >= lo_m && (int)threadIdx.x < hi_m) rstd = 0.f;
+        }
         s_mean[threadIdx.x] = mean; s_rstd[threadIdx.x] = rstd;
     }
+    if ((int)threadIdx.x < 2 * n_bands) s_tb[threadIdx.x] = time_bands[row * n_bands * 2 + threadIdx.x];
     __syncthreads();
-    float* base = feats + row * out_row_stride;
+    float* base = feats + (out_offsets ? out_offsets[row] * n_mels : row * out_row_stride);
     const long long total = valid * n_mels;
+    auto time_masked = [&](int f) {                   // frame f inside a SpecAugment time band (models.py:550-566)
+        bool hit = false;
+        for (int k = 0; k < n_bands; ++k) hit |= (f >= s_tb[2 * k] && f < s_tb[2 * k + 1]);
+        return hit;
+    };
     if (out_layout == TALFE_LAYOUT_TM && (n_mels & 3) == 0 && ((reinterpret_cast<unsigned long long>(base) & 15ull) == 0)) {
         float4* b4 = reinterpret_cast<float4*>(base);
         const int m4 = n_mels >> 2;
         for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total / 4; i += (long long)gridDim.x * blockDim.x) {
-            const int m = (int)(i % m4) * 4;
+            const int f = (int)(i / m4);
+            const int m = (int)(i - (long long)f * m4) * 4;
             float4 v = b4[i];
             v.x = (v.x - s_mean[m]) * s_rstd[m];
             v.y = (v.y - s_mean[m + 1]) * s_rstd[m + 1];
             v.z = (v.z - s_mean[m + 2]) * s_rstd[m + 2];
             v.w = (v.w - s_mean[m + 3]) * s_rstd[m + 3];
+            if (n_bands && time_masked(f)) v = make_float4(0.f, 0.f, 0.f, 0.f);
             b4[i] = v;
         }
     } else if (out_layout == TALFE_LAYOUT_TM) {
         for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-            const int m = (int)(i % n_mels);
-            base[i] = (base[i] - s_mean[m]) * s_rstd[m];
+            const int f = (int)(i / n_mels);
+            const int m = (int)(i - (long long)f * n_mels);
+            base[i] = (n_bands && time_masked(f)) ? 0.f : (base[i] - s_mean[m]) * s_rstd[m];
         }
     } else {
         for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)n_mels * n_frames;
              i += (long long)gridDim.x * blockDim.x) {
             const int m = (int)(i / n_frames);
             const long long f = i - (long long)m * n_frames;
-            if (f < valid) base[i] = (base[i] - s_mean[m]) * s_rstd[m];
+            if (f < valid) base[i] = (n_bands && time_masked((int)f)) ? 0.f : (base[i] - s_mean[m]) * s_rstd[m];
         }
     }
 }
@@ -714,6 +736,10 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
     const long long dense = job->n_frames * M;
     const long long ors = job->out_row_stride ? job->out_row_stride : dense;
     if (ors < dense) return TALFE_ERR_INVALID;
+    if (job->out_offsets && (!job->lens || job->out_layout != TALFE_LAYOUT_TM)) return TALFE_ERR_INVALID;   // packed = ragged [sum T_i, M]
+    if (job->n_bands < 0 || job->n_bands > kMaxBands) return TALFE_ERR_INVALID;
+    if (job->n_bands > 0 && (!job->freq_bands || !job->time_bands || job->norm == TALFE_NORM_NONE || job->defer_normalise))
+        return TALFE_ERR_INVALID;                          // the masks ride on the normalisation sweep
     const WorkspaceLayout w = workspace_layout(M, job->batch, job->n_frames);
     if (!job->workspace || job->workspace_bytes < w.total) return TALFE_ERR_WORKSPACE;
     if ((reinterpret_cast<uintptr_t>(job->workspace) & 15) != 0) return TALFE_ERR_WORKSPACE;
@@ -737,6 +763,7 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
                       (((kHalf + job->origin) * elt) & 15) == 0) ? 1 : 0;
     }
     a.out = job->out; a.out_row_stride = ors; a.out_layout = job->out_layout; a.eps = job->eps;
+    a.out_offsets = reinterpret_cast<const long long*>(job->out_offsets);
     if (w.n_tiles > 0x7fffffffLL) return TALFE_ERR_UNSUPPORTED;
     a.tiles_per_row = (int)w.tiles_per_row; a.n_tiles = (int)w.n_tiles;
     a.partials = reinterpret_cast<double2*>(ws + w.partials);
@@ -764,7 +791,7 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
     double* stats = job->stats ? job->stats : reinterpret_cast<double*>(ws + w.scratch_stats);
     const int accumulate = (job->accumulate_stats && job->stats) ? 1 : 0;
     if (job->norm == TALFE_NORM_BATCH_MEAN && !a.lens && !accumulate && !job->defer_normalise && ors == dense &&
-        (reinterpret_cast<uintptr_t>(job->out) & 15) == 0) {
+        job->n_bands == 0 && (reinterpret_cast<uintptr_t>(job->out) & 15) == 0) {
         // the reference case: one scalar over a contiguous [B, T, M] (or [B, M, T]) tensor; the sweep
         // derives the mean from the per-CTA partials itself (no separate reduction launch)
         const long long total = dense * job->batch, n4 = total / 4;
@@ -790,7 +817,7 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
     if (job->norm == TALFE_NORM_ROW_MEL_MEAN || job->norm == TALFE_NORM_ROW_MEL_MEANVAR) {
         double* colpart = reinterpret_cast<double*>(ws + w.colpart);
         colstats_kernel<<<dim3((unsigned)w.chunks, (unsigned)job->batch), 320, 0, stream>>>(job->out, ors, job->out_layout, job->n_frames, M,
-                                                                                           a.lens, a.total_len, a.frame0, colpart);
+                                                                                           a.lens, a.total_len, a.frame0, colpart, a.out_offsets);
         TALFE_CUDA(cudaGetLastError());
         colstats_finish_kernel<<<(unsigned)job->batch, 96, 0, stream>>>(colpart, w.chunks, M, accumulate, stats);
         TALFE_CUDA(cudaGetLastError());
@@ -798,7 +825,8 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
     if (job->norm == TALFE_NORM_NONE || job->defer_normalise) return TALFE_OK;
     // rows keep their zero fill beyond their own length: the sweep derives valid frames from lens
     apply_stats_kernel<<<dim3(sweep_blocks(plan->sm_count, job->batch, dense), (unsigned)job->batch), 256, 0, stream>>>(
-        job->out, job->batch, job->n_frames, ors, job->out_layout, M, job->norm, stats, nullptr, a.lens, a.frame0);
+        job->out, job->batch, job->n_frames, ors, job->out_layout, M, job->norm, stats, nullptr, a.lens, a.frame0, a.out_offsets,
+        job->freq_bands, job->time_bands, job->n_bands);
     TALFE_CUDA(cudaGetLastError());
     return TALFE_OK;
 }
@@ -824,7 +852,8 @@ int talfe_apply_stats(const talfe_plan* plan, float* feats, int64_t batch, int64
     const long long dense = n_frames * M;
     const long long ors = out_row_stride ? out_row_stride : dense;
     apply_stats_kernel<<<dim3(sweep_blocks(plan->sm_count, batch, dense), (unsigned)batch), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        feats, batch, n_frames, ors, out_layout, M, norm, stats, reinterpret_cast<const long long*>(valid_frames), nullptr, 0);
+        feats, batch, n_frames, ors, out_layout, M, norm, stats, reinterpret_cast<const long long*>(valid_frames), nullptr, 0,
+        nullptr, nullptr, nullptr, 0);
     TALFE_CUDA(cudaGetLastError());
     return TALFE_OK;
 }

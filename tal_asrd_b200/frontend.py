@@ -54,6 +54,14 @@ def reference_tables(n_mels: int = 80, sr: int = DEFAULT_SR):
     return window, fb.contiguous()
 
 
+def encoder_padding_mask(audio_lens: torch.Tensor, enc_frames: int) -> torch.Tensor:
+    """Vectorised form of the mask loop in ``ASRModel.encode_features`` (tal/asr/models.py:178-187):
+    True (= ignore) where the encoder frame index is >= audio_len // (audio_lens.max() // enc_frames).
+    Stays on the device of ``audio_lens``; no per-row host loop."""
+    scaled = audio_lens // (audio_lens.max() // enc_frames)
+    return torch.arange(enc_frames, device=audio_lens.device)[None, :] >= scaled[:, None]
+
+
 class _Plan:
     """Owns one talfe_plan (device tables) and frees it with the object."""
 
@@ -92,7 +100,8 @@ def _require_cuda(t: torch.Tensor) -> torch.device:
 def _run(plan: _Plan, audio: torch.Tensor, *, norm: int, layout: int, eps: float, lens: Optional[torch.Tensor],
          origin: int = 0, total_len: Optional[int] = None, frame0: int = 0, n_frames: Optional[int] = None,
          out: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None, accumulate: bool = False,
-         defer: bool = False) -> torch.Tensor:
+         defer: bool = False, out_offsets: Optional[torch.Tensor] = None, packed_frames: int = 0,
+         bands=None) -> torch.Tensor:
     device = audio.device
     B, buf_len = audio.shape
     if total_len is None:
@@ -101,6 +110,8 @@ def _run(plan: _Plan, audio: torch.Tensor, *, norm: int, layout: int, eps: float
         n_frames = num_frames(total_len) - frame0
     M = plan.n_mels
     shape = (B, n_frames, M) if layout == _lib.LAYOUT_TM else (B, M, n_frames)
+    if out_offsets is not None:
+        shape = (packed_frames, M)
     if out is None:
         out = torch.empty(shape, dtype=torch.float32, device=device)
     elif tuple(out.shape) != shape or out.dtype != torch.float32 or not out.is_contiguous() or out.device != device:
@@ -128,6 +139,10 @@ def _run(plan: _Plan, audio: torch.Tensor, *, norm: int, layout: int, eps: float
     job.stats = stats.data_ptr() if stats is not None else None
     job.workspace = workspace.data_ptr()
     job.workspace_bytes = ws_bytes
+    job.out_offsets = out_offsets.data_ptr() if out_offsets is not None else None
+    if bands is not None:
+        fb, tb = bands
+        job.freq_bands, job.time_bands, job.n_bands = fb.data_ptr(), tb.data_ptr(), fb.shape[1]
     with torch.cuda.device(device):
         job.stream = torch.cuda.current_stream(device).cuda_stream
         _lib.check(plan.lib.talfe_run(plan.handle, job), "talfe_run")
@@ -207,7 +222,7 @@ class LogMelSpec(nn.Module):
     @torch.jit.ignore
     def features(self, audio: torch.Tensor, audio_lens: Optional[torch.Tensor] = None, norm: str = "batch",
                  layout: str = "tm", out: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None,
-                 defer_normalise: bool = False) -> torch.Tensor:
+                 defer_normalise: bool = False, spec_augment=None) -> torch.Tensor:
         """Extension surface on the same kernels.
 
         audio_lens  int64 [B] true lengths (what the collaters emit next to the padded batch,
@@ -218,6 +233,8 @@ class LogMelSpec(nn.Module):
         norm        'batch' (reference) | 'none' | 'row' | 'row_mel' | 'row_mel_var'
         layout      'tm' -> [B, T, M] (reference) | 'mt' -> [B, M, T] (what encode_features wants, models.py:167)
         stats       optional float64 tensor receiving the statistics block(s) (see include/talfe.h)
+        spec_augment (freq_bands, time_bands) from ``specaug.sample_masks``: zeroed in the normalisation sweep,
+                    replacing ``time_mask(freq_mask(x))`` of tal/asr/models.py:159-161
         """
         with torch.no_grad():
             audio = _prepare_audio(audio)
@@ -228,8 +245,38 @@ class LogMelSpec(nn.Module):
                 lens = audio_lens.to(device=device, dtype=torch.int64).contiguous()
                 if lens.numel() != audio.shape[0]:
                     raise ValueError("audio_lens must have one entry per row")
+            bands = None
+            if spec_augment is not None:
+                if norm == "none" or defer_normalise:
+                    raise ValueError("spec_augment rides on the normalisation sweep: needs norm != 'none' and no deferral")
+                fb, tb = spec_augment
+                fb = fb.to(device=device, dtype=torch.int32).contiguous()
+                tb = tb.to(device=device, dtype=torch.int32).contiguous()
+                if fb.shape != tb.shape or fb.dim() != 3 or fb.shape[0] != audio.shape[0] or fb.shape[2] != 2 or fb.shape[1] > 16:
+                    raise ValueError("spec_augment bands must be two int tensors [B, n_bands <= 16, 2]")
+                bands = (fb, tb)
             return _run(self.plan(device), audio, norm=_NORMS[norm], layout=_LAYOUTS[layout], eps=self.eps,
-                        lens=lens, out=out, stats=stats, defer=defer_normalise)
+                        lens=lens, out=out, stats=stats, defer=defer_normalise, bands=bands)
+
+    @torch.jit.ignore
+    def features_packed(self, audio: torch.Tensor, audio_lens: torch.Tensor, norm: str = "row"):
+        """Ragged batch without padding frames: returns (feats [sum T_i, n_mels], frame_offsets
+        int64 [B + 1]); row i owns feats[frame_offsets[i]:frame_offsets[i+1]] = the front end run on that row
+        alone (T_i = 1 + len_i // 160).  The reference instead pads every row to the longest
+        (tal/asr/data/aligned.py:250-257), which makes a 1 s row as expensive as a 10 min one."""
+        with torch.no_grad():
+            audio = _prepare_audio(audio)
+            device = _require_cuda(audio)
+            lens_host = audio_lens.detach().to("cpu", torch.int64)
+            if lens_host.numel() != audio.shape[0] or int(lens_host.min()) <= N_FFT // 2 or int(lens_host.max()) > audio.shape[1]:
+                raise RuntimeError("audio_lens must give every row a length in (200, L]")
+            frames = 1 + lens_host // HOP
+            offsets_host = torch.zeros(audio.shape[0] + 1, dtype=torch.int64)
+            offsets_host[1:] = torch.cumsum(frames, 0)
+            offsets = offsets_host.to(device)
+            out = _run(self.plan(device), audio, norm=_NORMS[norm], layout=_lib.LAYOUT_TM, eps=self.eps,
+                       lens=lens_host.to(device), out_offsets=offsets, packed_frames=int(offsets_host[-1]))
+            return out, offsets
 
     @torch.jit.ignore
     def forward_host(self, audio_host: torch.Tensor, out_host: Optional[torch.Tensor] = None,
