@@ -137,7 +137,7 @@ def run_reference(args):
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_ours(args):
@@ -273,12 +273,44 @@ def run_ours(args):
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": 2 * args.steps, "clocks": clocks.summary(),   # logmel_kernel + sub_scalar_flat_kernel per step "clocks": clocks.summary(),
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+class _QuietStdout:
+    """The contract is ONE JSON line on stdout.  Libraries (NCCL's version banner, torchrun notices) write to the
+    process-level stdout from C, so file descriptor 1 is pointed at stderr for the duration of the run and the
+    JSON line goes to the saved descriptor."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, line: str):
+        os.write(self.saved, (line + "\n").encode())
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
+_OUT = None
+
+
+def emit(obj):
+    line = json.dumps(obj)
+    if _OUT is not None:
+        _OUT.emit(line)
+    else:
+        print(line, flush=True)
+
+
 def main():
+    global _OUT
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -287,10 +319,13 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    with _QuietStdout() as out:
+        _OUT = out
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_ours(args)
+        _OUT = None
 
 
 if __name__ == "__main__":
