@@ -16,6 +16,8 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <algorithm>
 #include <mutex>
 #include <new>
@@ -52,6 +54,10 @@ struct talfe_plan_impl {
     int sm_count;
     int ctas_per_sm;
     int ref_layout;                // 80-mel reference filterbank shape -> fully unrolled mel stage
+    int variant;                   // 0 = legacy kernel (2 CTAs/SM, every thread runs every stage), 1 = warp-specialised
+    int tw_reg;                    // ws: twiddles in producer registers (else re-read from shared memory per tile)
+    int l2_prefetch;
+    size_t off_w_ws, off_lo_ws, ws_smem;
     MelLayout layout;
     int pstride;
     size_t off_tw, off_w, off_lo, off_id, blob_bytes;
@@ -85,6 +91,10 @@ struct KernelArgs {
     int blob_bytes, off_tw, off_w, off_lo, off_id;
     MelLayout layout;
     int pstride;
+    // warp-specialised kernel only
+    int off_w_ws, off_lo_ws;       // its mel tables inside the blob
+    int out_align_ok;              // every frame row of `out` starts 16-byte aligned (bulk stores allowed)
+    int l2_prefetch;               // prefetch tile k+2 into L2 while tile k+1 travels to shared memory
 };
 
 // ------------------------------------------------------------------------------------------ K1
@@ -189,6 +199,10 @@ __device__ __forceinline__ void load_tile(const KernelArgs& a, TileInfo& ti, XT*
         }
     }
 }
+
+}  // namespace
+#include "talfe_ws.cuh"
+namespace {
 
 template <bool kRef, typename XT>
 __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const KernelArgs a) {
@@ -602,6 +616,17 @@ logmel_kernel_t kernel_for(bool ref_layout, int dtype) {
     return dtype == TALFE_F32 ? logmel_kernel<false, float> : dtype == TALFE_F16 ? logmel_kernel<false, __half> : logmel_kernel<false, short>;
 }
 
+logmel_kernel_t ws_kernel_for(int dtype, bool tw_reg) {
+    if (tw_reg) return dtype == TALFE_F32 ? logmel_ws_kernel<float, true> : dtype == TALFE_F16 ? logmel_ws_kernel<__half, true> : logmel_ws_kernel<short, true>;
+    return dtype == TALFE_F32 ? logmel_ws_kernel<float, false> : dtype == TALFE_F16 ? logmel_ws_kernel<__half, false> : logmel_ws_kernel<short, false>;
+}
+
+// Development / profiling knobs (read once per plan): TALFE_KERNEL=legacy|ws, TALFE_TW_REG=0|1, TALFE_L2_PREFETCH=0|1.
+int env_int(const char* name, int dflt) {
+    const char* v = std::getenv(name);
+    return (v && *v) ? std::atoi(v) : dflt;
+}
+
 int cuda_fail(cudaError_t e) { g_last_cuda_error = (int)e; return TALFE_ERR_CUDA; }
 #define TALFE_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return cuda_fail(e__); } while (0)
 
@@ -682,6 +707,15 @@ int talfe_plan_create(talfe_plan** plan_out, int device, int n_mels, const float
     p->pstride = t.pstride;
     p->off_tw = t.off_tw; p->off_w = t.off_w; p->off_lo = t.off_lo; p->off_id = t.off_id; p->blob_bytes = t.blob_bytes;
     p->ref_layout = is_reference_layout(t.layout) ? 1 : 0;
+    p->off_w_ws = t.off_w_ws; p->off_lo_ws = t.off_lo_ws;
+    p->ws_smem = ws_smem_bytes(t.blob_bytes);
+    {
+        const char* kv = std::getenv("TALFE_KERNEL");
+        p->variant = p->ref_layout ? 1 : 0;                               // the warp-specialised kernel is unrolled for the reference filterbank shape
+        if (kv && std::strcmp(kv, "legacy") == 0) p->variant = 0;
+        p->tw_reg = env_int("TALFE_TW_REG", 1);
+        p->l2_prefetch = env_int("TALFE_L2_PREFETCH", 1);
+    }
     p->smem_bytes = t.blob_bytes + (size_t)kXFloats * sizeof(float) +
                     (size_t)kGroupsPerCta * kEGroup * sizeof(cf) + (size_t)kGroupsPerCta * t.pstride * sizeof(cf) + 16;
     cudaError_t e = cudaMalloc(&p->blob_dev, t.blob_bytes);
@@ -691,6 +725,10 @@ int talfe_plan_create(talfe_plan** plan_out, int device, int n_mels, const float
         e = cudaFuncSetAttribute(kernel_for(p->ref_layout != 0, dt), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes);
     if (e == cudaSuccess)
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p->ctas_per_sm, kernel_for(p->ref_layout != 0, TALFE_F32), kThreads, p->smem_bytes);
+    if (p->variant == 1) {
+        for (int dt = TALFE_F32; dt <= TALFE_I16 && e == cudaSuccess; ++dt)
+            e = cudaFuncSetAttribute(ws_kernel_for(dt, p->tw_reg != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->ws_smem);
+    }
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
         e = cudaEventCreateWithFlags(&p->ev_ready[i], cudaEventDisableTiming);
@@ -771,7 +809,11 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
     a.off_tw = (int)plan->off_tw; a.off_w = (int)plan->off_w; a.off_lo = (int)plan->off_lo; a.off_id = (int)plan->off_id;
     a.layout = plan->layout; a.pstride = plan->pstride;
 
-    long long grid = (long long)plan->sm_count * plan->ctas_per_sm;
+    const bool use_ws = plan->variant == 1;
+    a.off_w_ws = (int)plan->off_w_ws; a.off_lo_ws = (int)plan->off_lo_ws;
+    a.l2_prefetch = plan->l2_prefetch;
+    a.out_align_ok = ((reinterpret_cast<uintptr_t>(job->out) & 15) == 0 && (ors & 3) == 0) ? 1 : 0;
+    long long grid = use_ws ? (long long)plan->sm_count : (long long)plan->sm_count * plan->ctas_per_sm;
     if (grid > w.n_tiles) grid = w.n_tiles;
     const bool want_stats = job->stats != nullptr || job->norm != TALFE_NORM_NONE;
     const bool per_row = job->norm >= TALFE_NORM_ROW_MEAN;
@@ -779,12 +821,14 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
     a.want_sumsq = job->stats != nullptr ? 1 : 0;         // the sum of squares is only ever reported, never needed by K3
     {
         cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = plan->smem_bytes; cfg.stream = stream;
+        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(use_ws ? kWsThreads : kThreads);
+        cfg.dynamicSmemBytes = use_ws ? plan->ws_smem : plan->smem_bytes; cfg.stream = stream;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        TALFE_CUDA(cudaLaunchKernelEx(&cfg, kernel_for(plan->ref_layout != 0, a.dtype), (const KernelArgs)a));
+        TALFE_CUDA(cudaLaunchKernelEx(&cfg, use_ws ? ws_kernel_for(a.dtype, plan->tw_reg != 0) : kernel_for(plan->ref_layout != 0, a.dtype),
+                                      (const KernelArgs)a));
     }
 
     if (!want_stats) return TALFE_OK;

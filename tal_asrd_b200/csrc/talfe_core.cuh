@@ -346,4 +346,119 @@ TALFE_HD void mel_log_ref(int c, const cf* __restrict__ p2, const float* __restr
     mel_slot_ref<kRefW3, kRefW0 + kRefW1 + kRefW2>(p2 + lo[3], w, eps, y[6], y[7]);
 }
 
+
+// =============================================================================================
+// Warp-specialised path (csrc/talfe_ws.cuh): producer warps run stage 1, consumer warps stage 2 +
+// mel.  Same arithmetic as above; what changes is who holds which constants (per-role registers) and
+// the shared-memory layouts, all chosen so that EVERY shared access of the steady state is
+// conflict-free by construction (checked on the CPU by tests/test_ws_layout.py):
+//
+//   producers  thread (g1 = t / 20, j = t % 20)   — group-major, as in the legacy kernel;
+//   consumers  thread (g  = t % 16, r = t / 16)   — pair-minor: the 16 lanes of a half-warp are the 16
+//              frame pairs of the tile, r (exchange row in stage 2, mel lane in the mel stage) is uniform.
+//
+//   exchange   E[g][row][j] at complex index ws_e_base(g) + 20 row + j, ws_e_base(g) = 404 g + 2 ((g>>2)&1):
+//              404 = 4 (mod 16) keeps the group-major STS.64 of stage 1 on 16 distinct 8-byte banks wherever a
+//              half-warp straddles two groups (straddles only happen inside blocks of four groups), and the
+//              extra 16 bytes of every other block make 8 consecutive pairs hit 8 distinct 16-byte bank
+//              groups for the pair-minor LDS.128 of stage 2;
+//   power      P[bin][g] (float2: frame a, frame b): stage 2 writes words 32 bin + 2 g + f (one wavefront per
+//              warp store), the mel stage reads 16 consecutive float2 per half-warp (one wavefront);
+//   features   Y[frame][80] staged per tile, row fr at float offset 80 fr + 4 (fr >> 1) (16-byte aligned rows
+//              for the bulk store to global memory; the pad leaves the scalar stores 2-way conflicted).
+constexpr int kWsGroups = 16;
+constexpr int kWsFrames = 2 * kWsGroups;
+constexpr int kWsERow = 20;
+constexpr int kWsEGroup = 404;
+constexpr int kWsECf = kWsGroups * kWsEGroup + 4;                       // complex entries per exchange buffer
+constexpr int kWsPBins = 216;                                           // 200 bins + read padding of the widest slot
+constexpr int kWsPCf = kWsPBins * kWsGroups;
+constexpr int kWsYFloats = kWsFrames * kMaxMels + 4 * kWsGroups;
+TALFE_HD constexpr int ws_e_base(int g) { return g * kWsEGroup + 2 * ((g >> 2) & 1); }
+TALFE_HD constexpr int ws_y_off(int fr) { return fr * kMaxMels + 4 * (fr >> 1); }
+
+// Stage 1, first half: 28 waveform samples -> window -> complex FFT-20 of (frame a + i frame b), in registers.
+template <typename XT>
+TALFE_HD void stage1_ws_fft(const XT* __restrict__ p /* xg + j */, const float (&win)[20], cf (&z)[20]) {
+    constexpr int kSkew = XLayout<XT>::kSkew;
+#pragma unroll
+    for (int m = 0; m < 20; ++m) {
+        const int ia = 20 * m + (20 * m >= kXBlock ? kSkew : 0);
+        const int ib = 20 * m + kHop + (20 * m + kHop >= kXBlock ? kSkew : 0);
+        z[m] = make_float2(win[m] * x_to_float(p[ia]), win[m] * x_to_float(p[ib]));
+    }
+    fft20(z);
+}
+
+// Stage 1, second half: untangle the two real-input transforms, twiddle by tw[k1-1] = W400^(j k1), write
+// column j of the pair's 20 exchange rows (same row meaning as the legacy stage1; rows in natural order).
+TALFE_HD void stage1_ws_store(const cf (&z)[20], const cf (&tw)[10], cf* __restrict__ col /* E + ws_e_base(g1) + j */) {
+    col[18 * kWsERow] = z[0];
+#pragma unroll
+    for (int k1 = 1; k1 < 10; ++k1) {
+        const cf sm = cadd(z[k1], z[20 - k1]), df = csub(z[k1], z[20 - k1]);
+        const cf aa = make_float2(sm.x, df.y);
+        const cf ab = make_float2(sm.y, -df.x);
+        col[(2 * (k1 - 1)) * kWsERow] = cmul(aa, tw[k1 - 1]);
+        col[(2 * (k1 - 1) + 1) * kWsERow] = cmul(ab, tw[k1 - 1]);
+    }
+    col[19 * kWsERow] = cmul(z[10], tw[9]);
+}
+
+// Stage 2 (consumer thread (g, r)): |FFT-20(row r)|^2 kept in registers until the power array is free.
+// Normal rows r < 18: pw[q] = (bin k1 + 20 q, bin (20 - k1) + 20 q) of frame r & 1, k1 = 1 + r / 2.
+TALFE_HD void stage2_ws_power_normal(cf (&v)[20], cf (&pw)[10]) {
+    fft20(v);
+#pragma unroll
+    for (int q = 0; q < 10; ++q)
+        pw[q] = make_float2(fmaf(v[q].x, v[q].x, v[q].y * v[q].y), fmaf(v[19 - q].x, v[19 - q].x, v[19 - q].y * v[19 - q].y));
+}
+TALFE_HD void stage2_ws_store_normal(int k1, const cf (&pw)[10], float* __restrict__ pgf /* (float*)P + 2 g + f */) {
+    float* lo = pgf + 2 * kWsGroups * k1;
+    float* hi = pgf + 2 * kWsGroups * (20 - k1);
+#pragma unroll
+    for (int q = 0; q < 10; ++q) {
+        lo[2 * kWsGroups * 20 * q] = pw[q].x;
+        hi[2 * kWsGroups * 20 * q] = pw[q].y;
+    }
+}
+// Packed rows: r == 18 (zero = true) -> bins 20 (q + 1); r == 19 -> bins 10 + 20 q; both frames per entry.
+TALFE_HD void stage2_ws_power_special(bool zero, cf (&v)[20], cf (&pw)[10]) {
+    fft20(v);
+#pragma unroll
+    for (int q = 0; q < 10; ++q) {
+        const cf p = zero ? v[q + 1] : v[q];
+        const cf r = v[19 - q];
+        const cf sm = cadd(p, r), df = csub(p, r);
+        pw[q] = make_float2(fmaf(sm.x, sm.x, df.y * df.y), fmaf(df.x, df.x, sm.y * sm.y));
+    }
+}
+TALFE_HD void stage2_ws_store_special(bool zero, const cf (&pw)[10], cf* __restrict__ pg /* P + g */) {
+    cf* out = pg + kWsGroups * (zero ? 20 : 10);
+#pragma unroll
+    for (int q = 0; q < 10; ++q)
+        if (!(zero && q == 9)) out[kWsGroups * 20 * q] = pw[q];         // bin 200 carries no mel weight
+}
+
+// Mel stage (consumer thread (g, c)): mels c, 20 + c, 40 + c, 60 + c; weights in registers.
+template <int W, int OFF>
+TALFE_HD void mel_slot_ws(const cf* __restrict__ p /* P + g + 16 lo */, const float (&w)[kRefWStride], float eps, float& ya, float& yb) {
+    float acc_a = 0.f, acc_b = 0.f;
+#pragma unroll
+    for (int r = 0; r < W; ++r) {
+        const cf pw = p[kWsGroups * r];
+        acc_a = fmaf(w[OFF + r], pw.x, acc_a);
+        acc_b = fmaf(w[OFF + r], pw.y, acc_b);
+    }
+    ya = fast_log(acc_a + eps);
+    yb = fast_log(acc_b + eps);
+}
+TALFE_HD void mel_log_ws(const cf* __restrict__ pg /* P + g */, const float (&w)[kRefWStride], const int (&lo)[kMelSlots], float eps,
+                         float (&y)[2 * kMelSlots]) {
+    mel_slot_ws<kRefW0, 0>(pg + kWsGroups * lo[0], w, eps, y[0], y[1]);
+    mel_slot_ws<kRefW1, kRefW0>(pg + kWsGroups * lo[1], w, eps, y[2], y[3]);
+    mel_slot_ws<kRefW2, kRefW0 + kRefW1>(pg + kWsGroups * lo[2], w, eps, y[4], y[5]);
+    mel_slot_ws<kRefW3, kRefW0 + kRefW1 + kRefW2>(pg + kWsGroups * lo[3], w, eps, y[6], y[7]);
+}
+
 }  // namespace talfe

@@ -45,6 +45,11 @@ struct HostTables {
     std::vector<float> w_t;         // [20][wstride]
     std::vector<int> mel_lo;        // [4][20] slot-major: first bin of the mel owned by (slot i, lane c)
     std::vector<int> mel_id;        // [4][20] slot-major: which mel (slot i, lane c) owns, -1 = none
+    // warp-specialised kernel (talfe_ws.cuh): lane c owns mels c, 20 + c, 40 + c, 60 + c (no permutation: its
+    // power reads are conflict-free for any ownership), weights live in the consumer threads' registers
+    std::vector<float> w_ws;        // [20][wstride]
+    std::vector<int> lo_ws;         // [4][20] slot-major first bins
+    size_t off_w_ws, off_lo_ws;
     // byte offsets inside the blob that is copied to shared memory
     size_t off_win, off_tw, off_w, off_lo, off_id, blob_bytes;
     std::vector<unsigned char> blob;
@@ -150,19 +155,32 @@ inline int build_tables(int n_mels, const float* window, const float* fb, HostTa
             t.mel_lo[i * 20 + c] = lo[m];
             for (int f = lo[m]; f <= hi[m]; ++f) t.w_t[c * L.wstride + L.offset[i] + (f - lo[m])] = fb[f * n_mels + m];
         }
+    t.w_ws.assign(20 * L.wstride, 0.f);
+    t.lo_ws.assign(kMaxMels, 1);
+    for (int i = 0; i < L.n_slots; ++i)
+        for (int c = 0; c < 20; ++c) {
+            const int m = 20 * i + c;
+            if (m >= n_mels) continue;
+            t.lo_ws[i * 20 + c] = lo[m];
+            for (int f = lo[m]; f <= hi[m]; ++f) t.w_ws[c * L.wstride + L.offset[i] + (f - lo[m])] = fb[f * n_mels + m];
+        }
     auto align16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
     t.off_win = 0;
     t.off_tw = align16(t.off_win + 400 * sizeof(float));
     t.off_w = align16(t.off_tw + 400 * sizeof(float));
     t.off_lo = align16(t.off_w + t.w_t.size() * sizeof(float));
     t.off_id = align16(t.off_lo + kMaxMels * sizeof(int));
-    t.blob_bytes = align16(t.off_id + kMaxMels * sizeof(int));
+    t.off_w_ws = align16(t.off_id + kMaxMels * sizeof(int));
+    t.off_lo_ws = align16(t.off_w_ws + t.w_ws.size() * sizeof(float));
+    t.blob_bytes = align16(t.off_lo_ws + kMaxMels * sizeof(int));
     t.blob.assign(t.blob_bytes, 0);
     std::memcpy(t.blob.data() + t.off_win, t.win_t.data(), 400 * sizeof(float));
     std::memcpy(t.blob.data() + t.off_tw, t.tw_t.data(), 400 * sizeof(float));
     std::memcpy(t.blob.data() + t.off_w, t.w_t.data(), t.w_t.size() * sizeof(float));
     std::memcpy(t.blob.data() + t.off_lo, t.mel_lo.data(), kMaxMels * sizeof(int));
     std::memcpy(t.blob.data() + t.off_id, t.mel_id.data(), kMaxMels * sizeof(int));
+    std::memcpy(t.blob.data() + t.off_w_ws, t.w_ws.data(), t.w_ws.size() * sizeof(float));
+    std::memcpy(t.blob.data() + t.off_lo_ws, t.lo_ws.data(), kMaxMels * sizeof(int));
     return 0;
 }
 

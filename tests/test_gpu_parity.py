@@ -26,10 +26,26 @@ def dev():
     return torch.device("cuda:0")
 
 
-@pytest.fixture(scope="module")
-def mod(dev):
+def make_module(dev, kernel):
+    """kernel: 'ws' (warp-specialised, the default for the reference filterbank) or 'legacy'; the library reads
+    TALFE_KERNEL when the plan (device tables) is created, so create it here."""
     from tal_asrd_b200 import LogMelSpec
-    return LogMelSpec().to(dev)
+    old = os.environ.get("TALFE_KERNEL")
+    os.environ["TALFE_KERNEL"] = kernel
+    try:
+        m = LogMelSpec().to(dev)
+        m.plan(dev)
+    finally:
+        if old is None:
+            os.environ.pop("TALFE_KERNEL", None)
+        else:
+            os.environ["TALFE_KERNEL"] = old
+    return m
+
+
+@pytest.fixture(scope="module", params=["ws", "legacy"])
+def mod(dev, request):
+    return make_module(dev, request.param)
 
 
 def run(mod, x, **kw):
@@ -324,3 +340,42 @@ def test_invalid_arguments_fail_cleanly(mod, dev):
         mod.features(x, out=torch.empty(2, 100, 80, device=dev))          # wrong out shape
     y = mod(torch.zeros(1, 201, device=dev))                              # shortest legal input
     assert y.shape == (1, 2, 80)
+
+
+def test_ws_and_legacy_kernels_agree_bitwise(dev):
+    """Same arithmetic in the same order, different work decomposition and shared-memory layouts: un-normalised
+    features must be identical bit for bit, run after run (also a cheap race detector for the mbarrier pipeline)."""
+    from tal_asrd_b200 import synth
+    ws, legacy = make_module(dev, "ws"), make_module(dev, "legacy")
+    x = torch.from_numpy(synth.batch(7, 5, 16000 * 21 + 123)).to(dev)          # 66 tiles per row, ragged last tile
+    want = legacy.features(x, norm="none")
+    for _ in range(5):
+        got = ws.features(x, norm="none")
+        assert torch.equal(got, want)
+    lens = torch.tensor([x.shape[1], 200000, 7777, 201, 150001])
+    for norm in ("none", "row"):
+        a = legacy.features(x, audio_lens=lens, norm=norm)
+        b = ws.features(x, audio_lens=lens, norm=norm)
+        assert torch.equal(a, b), norm
+    a, b = legacy.features(x, norm="none", layout="mt"), ws.features(x, norm="none", layout="mt")
+    assert torch.equal(a, b)
+    for dt in (torch.float16, torch.int16):
+        xx = x.half() if dt == torch.float16 else (x * 32767).round().to(torch.int16)
+        assert torch.equal(legacy.features(xx, norm="none"), ws.features(xx, norm="none"))
+    # batch statistics: per-CTA partial sums differ in grouping, so the mean agrees to rounding, not bitwise
+    sa, sb = legacy.stats_block(dev), ws.stats_block(dev)
+    legacy.features(x, stats=sa); ws.features(x, stats=sb)
+    torch.cuda.synchronize()
+    assert torch.allclose(sa[:, :3], sb[:, :3], rtol=1e-12, atol=0)
+
+
+def test_ws_kernel_many_tiles_per_cta(dev):
+    """Config-2-sized batch (64 x 30 s): every persistent CTA runs ~41 tiles through both buffers of every queue."""
+    from tal_asrd_b200 import synth
+    ws, legacy = make_module(dev, "ws"), make_module(dev, "legacy")
+    x = torch.from_numpy(synth.batch(3, 64, 480000)).to(dev)
+    a = legacy.features(x, norm="none")
+    for _ in range(3):
+        assert torch.equal(ws.features(x, norm="none"), a)
+    ya, yb = legacy(x), ws(x)
+    assert float((ya - yb).abs().max()) < 1e-5

@@ -84,3 +84,37 @@ def test_emulated_other_mel_counts_and_builtin_tables(emul):
     assert np.array_equal(emul_logmel(emul, x, 80, generic=1), emul_logmel(emul, x, 80))
     # tables computed inside the C library (no torch): within tolerance of the reference's fp32 tables
     assert rel_err(emul_logmel(emul, x, 80, tables=False), O.logmel_unnormalised_f64(x[None])[0]) < 1e-4
+
+
+# ---- warp-specialised kernel (csrc/talfe_ws.cuh): same stage functions and E / P / Y layouts, a tile at a time
+def emul_logmel_ws(lib, x):
+    lib.talfe_emul_logmel_ws.restype = ctypes.c_int
+    lib.talfe_emul_logmel_ws.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float,
+                                         ctypes.c_void_p]
+    x = np.ascontiguousarray(x, np.float32)
+    T = 1 + x.shape[0] // 160
+    out = np.zeros((T, 80), np.float32)
+    win, fb = O.reference_tables(80)
+    rc = lib.talfe_emul_logmel_ws(x.ctypes.data, x.shape[0], win.ctypes.data, fb.ctypes.data, 1e-6, out.ctypes.data)
+    assert rc == 0
+    return out
+
+
+@pytest.mark.parametrize("name", ["lcg_noise", "tone_1k", "dc_half", "len_201", "len_15999", "loud_fullscale", "tiny_amplitude",
+                                  "zeros"])
+def test_emulated_ws_tile_matches_reference_double(emul, name):
+    c = load_case(name)
+    got = emul_logmel_ws(emul, c["audio"][0])
+    ref = c["ref_f64_unnormalised"][0]
+    gap = rel_err(c["ref_f32"], c["ref_f64"])
+    assert np.isfinite(got).all()
+    assert rel_err(got, ref) <= max(1e-4, 2 * gap)
+
+
+def test_emulated_ws_equals_legacy_layout_bitwise(emul):
+    """Both kernels run the same arithmetic in the same order; only the shared-memory layouts differ."""
+    rng = np.random.default_rng(11)
+    x = (rng.standard_normal(16000 * 3 + 77) * 0.1).astype(np.float32)
+    a = emul_logmel(emul, x)
+    b = emul_logmel_ws(emul, x)
+    assert np.array_equal(a, b)
