@@ -55,7 +55,7 @@ struct talfe_plan_impl {
     int ctas_per_sm;
     int ref_layout;                // 80-mel reference filterbank shape -> fully unrolled mel stage
     int variant;                   // 0 = legacy kernel (2 CTAs/SM, every thread runs every stage), 1 = warp-specialised
-    int tw_reg;                    // ws: twiddles in producer registers (else re-read from shared memory per tile)
+    int ws_cfg;                    // ws: which constant tables live in registers (talfe_ws.cuh, kCfg)
     int l2_prefetch;
     size_t off_w_ws, off_lo_ws, ws_smem;
     MelLayout layout;
@@ -616,12 +616,23 @@ logmel_kernel_t kernel_for(bool ref_layout, int dtype) {
     return dtype == TALFE_F32 ? logmel_kernel<false, float> : dtype == TALFE_F16 ? logmel_kernel<false, __half> : logmel_kernel<false, short>;
 }
 
-logmel_kernel_t ws_kernel_for(int dtype, bool tw_reg) {
-    if (tw_reg) return dtype == TALFE_F32 ? logmel_ws_kernel<float, true> : dtype == TALFE_F16 ? logmel_ws_kernel<__half, true> : logmel_ws_kernel<short, true>;
-    return dtype == TALFE_F32 ? logmel_ws_kernel<float, false> : dtype == TALFE_F16 ? logmel_ws_kernel<__half, false> : logmel_ws_kernel<short, false>;
+template <int kCfg> logmel_kernel_t ws_kernel_dt(int dtype) {
+    return dtype == TALFE_F32 ? logmel_ws_kernel<float, kCfg> : dtype == TALFE_F16 ? logmel_ws_kernel<__half, kCfg> : logmel_ws_kernel<short, kCfg>;
+}
+logmel_kernel_t ws_kernel_for(int dtype, int cfg) {
+    switch (cfg & 7) {
+        case 0: return ws_kernel_dt<0>(dtype);
+        case 1: return ws_kernel_dt<1>(dtype);
+        case 2: return ws_kernel_dt<2>(dtype);
+        case 3: return ws_kernel_dt<3>(dtype);
+        case 4: return ws_kernel_dt<4>(dtype);
+        case 5: return ws_kernel_dt<5>(dtype);
+        case 6: return ws_kernel_dt<6>(dtype);
+        default: return ws_kernel_dt<7>(dtype);
+    }
 }
 
-// Development / profiling knobs (read once per plan): TALFE_KERNEL=legacy|ws, TALFE_TW_REG=0|1, TALFE_L2_PREFETCH=0|1.
+// Development / profiling knobs (read once per plan): TALFE_KERNEL=legacy|ws, TALFE_WS_CFG=0..7 (bit 0 twiddles, bit 1 window, bit 2 mel weights in registers), TALFE_L2_PREFETCH=0|1.
 int env_int(const char* name, int dflt) {
     const char* v = std::getenv(name);
     return (v && *v) ? std::atoi(v) : dflt;
@@ -713,7 +724,7 @@ int talfe_plan_create(talfe_plan** plan_out, int device, int n_mels, const float
         const char* kv = std::getenv("TALFE_KERNEL");
         p->variant = p->ref_layout ? 1 : 0;                               // the warp-specialised kernel is unrolled for the reference filterbank shape
         if (kv && std::strcmp(kv, "legacy") == 0) p->variant = 0;
-        p->tw_reg = env_int("TALFE_TW_REG", 1);
+        p->ws_cfg = env_int("TALFE_WS_CFG", 1) & 7;
         p->l2_prefetch = env_int("TALFE_L2_PREFETCH", 1);
     }
     p->smem_bytes = t.blob_bytes + (size_t)kXFloats * sizeof(float) +
@@ -727,7 +738,7 @@ int talfe_plan_create(talfe_plan** plan_out, int device, int n_mels, const float
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p->ctas_per_sm, kernel_for(p->ref_layout != 0, TALFE_F32), kThreads, p->smem_bytes);
     if (p->variant == 1) {
         for (int dt = TALFE_F32; dt <= TALFE_I16 && e == cudaSuccess; ++dt)
-            e = cudaFuncSetAttribute(ws_kernel_for(dt, p->tw_reg != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->ws_smem);
+            e = cudaFuncSetAttribute(ws_kernel_for(dt, p->ws_cfg), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->ws_smem);
     }
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
@@ -827,7 +838,7 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        TALFE_CUDA(cudaLaunchKernelEx(&cfg, use_ws ? ws_kernel_for(a.dtype, plan->tw_reg != 0) : kernel_for(plan->ref_layout != 0, a.dtype),
+        TALFE_CUDA(cudaLaunchKernelEx(&cfg, use_ws ? ws_kernel_for(a.dtype, plan->ws_cfg) : kernel_for(plan->ref_layout != 0, a.dtype),
                                       (const KernelArgs)a));
     }
 

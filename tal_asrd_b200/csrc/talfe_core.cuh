@@ -113,7 +113,9 @@ TALFE_HD cf csub(cf a, cf b) { return make_float2(a.x - b.x, a.y - b.y); }
 TALFE_HD cf cfma_s(float s, cf t, cf a) { return make_float2(fmaf(s, t.x, a.x), fmaf(s, t.y, a.y)); }
 TALFE_HD cf cmul_s(float s, cf t) { return make_float2(s * t.x, s * t.y); }
 #endif
-TALFE_HD cf cmul(cf a, cf b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+// explicit fused forms: the contraction the compiler would pick for a.x*b.x - a.y*b.y may differ from one kernel
+// to the next; fixing it keeps every variant of the kernel (and the host emulator) bit-identical
+TALFE_HD cf cmul(cf a, cf b) { return make_float2(fmaf(a.x, b.x, -(a.y * b.y)), fmaf(a.x, b.y, a.y * b.x)); }
 
 // 5-point DFT constants (forward transform, W5 = exp(-2 pi i / 5))
 #define TALFE_C1 0.30901699437494742f    /* cos(2 pi / 5) */

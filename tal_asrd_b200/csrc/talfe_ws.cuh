@@ -40,18 +40,31 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* gmem_src, unsigned 
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
 }
 
+// try_wait with a suspend-time hint: the waiting warp sleeps in hardware instead of spinning on issue slots
+__device__ __forceinline__ void mbar_wait_sleep(unsigned long long* bar, unsigned parity) {
+    unsigned done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u)
+            : "memory");
+    }
+}
+
+// Everything about tile (row, tq) that the roles need; recomputed where it is used (a handful of integer
+// operations) instead of being carried across the FFTs in registers.
 struct WsTile {
-    int row, tq;
     int t0, L, t_end;
     bool active, full, bulk;
-    const void* src;               // first sample of the tile in global memory (bulk tiles)
+    long long src_off;             // element offset of tile sample 0 from a.wave (bulk tiles)
 };
 
-template <typename XT>
-__device__ __forceinline__ void ws_tile_fill(const KernelArgs& a, WsTile& ti) {
-    ti.t0 = a.frame0 + ti.tq * kWsFrames;
+__device__ __forceinline__ WsTile ws_tile(const KernelArgs& a, int row, int tq) {
+    WsTile ti;
+    ti.t0 = a.frame0 + tq * kWsFrames;
     if (a.lens) {
-        ti.L = (int)min(a.lens[ti.row], (long long)kMaxSamples);
+        ti.L = (int)min(a.lens[row], (long long)kMaxSamples);
         ti.t_end = min(a.frame_end, ti.L > kHalf ? 1 + ti.L / kHop : 0);
     } else {
         ti.L = a.total_len;
@@ -63,16 +76,17 @@ __device__ __forceinline__ void ws_tile_fill(const KernelArgs& a, WsTile& ti) {
     const int b0 = s0 - a.origin;
     const bool interior = s0 >= 0 && s0 + kWsTileSamples <= ti.L && b0 >= 0 && b0 + kWsTileSamples <= a.buf_len;
     ti.bulk = ti.active && interior && a.align_ok;
-    ti.src = reinterpret_cast<const XT*>(a.wave) + (long long)ti.row * a.row_stride + b0;
+    ti.src_off = (long long)row * a.row_stride + b0;
+    return ti;
 }
 
-__device__ __forceinline__ void ws_tile_advance(const KernelArgs& a, WsTile& ti, int step) {
-    ti.tq += step;
-    while (ti.tq >= a.tiles_per_row) { ti.tq -= a.tiles_per_row; ++ti.row; }
+__device__ __forceinline__ void ws_advance(const KernelArgs& a, int& row, int& tq, int step) {
+    tq += step;
+    while (tq >= a.tiles_per_row) { tq -= a.tiles_per_row; ++row; }
 }
 
 // ------------------------------------------------------------------------------------------ producers
-template <typename XT, bool kTwReg>
+template <typename XT, bool kTwReg, bool kWinReg>
 __device__ __forceinline__ void ws_producer(const KernelArgs& a, unsigned char* smem, XT* s_x0, cf* s_e0, unsigned long long* s_bar,
                                             const int tid) {
     unsigned long long* x_full = s_bar;            // [2]
@@ -85,7 +99,7 @@ __device__ __forceinline__ void ws_producer(const KernelArgs& a, unsigned char* 
     constexpr int kXBufBytes = kXFloats * (int)sizeof(float);           // both element sizes use the fp32-sized buffer
 
     float win[20];
-    load_window(j, reinterpret_cast<const float*>(smem), XLayout<XT>::kScale, win);
+    if (kWinReg) load_window(j, reinterpret_cast<const float*>(smem), XLayout<XT>::kScale, win);
     const cf* s_tw = reinterpret_cast<const cf*>(smem + a.off_tw) + j * 10;
     cf tw[10];
     if (kTwReg) {
@@ -96,57 +110,61 @@ __device__ __forceinline__ void ws_producer(const KernelArgs& a, unsigned char* 
             tw[2 * h + 1] = make_float2(tt.z, tt.w);
         }
     }
-    // this warp's one or two pieces (of 17) of a tile fetch
-    const int pb0 = warp, pb1 = warp + kWsRoleWarps;
-    const unsigned dst0 = smem_u32(s_x0 + pb0 * kXG), dst1 = smem_u32(s_x0 + pb1 * kXG);
-    const int off0 = pb0 * kXBlock, off1 = pb1 * kXBlock;
-    const unsigned bytes0 = (unsigned)(min(kXBlock, kWsTileSamples - off0) * (int)sizeof(XT));
-    const unsigned bytes1 = off1 < kWsTileSamples ? (unsigned)(min(kXBlock, kWsTileSamples - off1) * (int)sizeof(XT)) : 0u;
-    const unsigned long long policy = l2_evict_first_policy();
-    auto issue = [&](const WsTile& t, int buf) {                        // called by lane 0 of every producer warp
-        const XT* src = reinterpret_cast<const XT*>(t.src);
+    // a tile fetch = 17 pieces of <= 320 samples (one per skew block); warp w issues pieces w and w + 10
+    auto issue = [&](const WsTile& t, int buf) {                        // lane 0 of every producer warp
+        const XT* src = reinterpret_cast<const XT*>(a.wave) + t.src_off;
+        const unsigned long long policy = l2_evict_first_policy();
         if (tid == 0) mbar_expect_tx(x_full + buf, kWsTileSamples * (int)sizeof(XT));
-        bulk_g2s_u32(dst0 + buf * kXBufBytes, src + off0, bytes0, x_full + buf, policy);
-        if (bytes1) bulk_g2s_u32(dst1 + buf * kXBufBytes, src + off1, bytes1, x_full + buf, policy);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int pb = warp + h * kWsRoleWarps;
+            if (pb * kXBlock < kWsTileSamples)
+                bulk_g2s_u32(smem_u32(s_x0 + pb * kXG) + buf * kXBufBytes, src + pb * kXBlock,
+                             (unsigned)(min(kXBlock, kWsTileSamples - pb * kXBlock) * (int)sizeof(XT)), x_full + buf, policy);
+        }
     };
 
     const int step = (int)gridDim.x;
     int tile = blockIdx.x;
-    WsTile ti, tn;
-    ti.row = tile / a.tiles_per_row;
-    ti.tq = tile - ti.row * a.tiles_per_row;
-    ws_tile_fill<XT>(a, ti);
-    if (ti.bulk && lane == 0) issue(ti, 0);
+    int row = tile / a.tiles_per_row, tq = tile - row * a.tiles_per_row;
+    if (lane == 0) {
+        const WsTile t0 = ws_tile(a, row, tq);
+        if (t0.bulk) issue(t0, 0);
+    }
+    __syncwarp();
     unsigned xfull_par = 0;                                             // bit b: parity of the next x_full[b] phase to wait for
+    const XT* xg = s_x0 + kXG * g1 + j;
+    cf* col0 = s_e0 + ws_e_base(g1) + j;
     for (int k = 0; tile < a.n_tiles; tile += step, ++k) {
         const int buf = k & 1;
-        const bool has_next = tile + step < a.n_tiles;
-        if (has_next) {
-            tn = ti;
-            ws_tile_advance(a, tn, step);
-            ws_tile_fill<XT>(a, tn);
-            if (tn.bulk && lane == 0) {
-                if (k >= 1) mbar_wait(x_empty + (buf ^ 1), ((k - 1) >> 1) & 1);     // tile k-1 has left that buffer
+        if (lane == 0 && tile + step < a.n_tiles) {                     // tile k+1: HBM -> shared memory; tile k+2: HBM -> L2
+            int rn = row, qn = tq;
+            ws_advance(a, rn, qn, step);
+            const WsTile tn = ws_tile(a, rn, qn);
+            if (tn.bulk) {
+                if (k >= 1) mbar_wait_sleep(x_empty + (buf ^ 1), ((k - 1) >> 1) & 1);   // tile k-1 has left that buffer
                 issue(tn, buf ^ 1);
             }
-            if (a.l2_prefetch && tid == 0 && tile + 2 * step < a.n_tiles) {          // tile k+2: HBM -> L2 only
-                WsTile tp = tn;
-                ws_tile_advance(a, tp, step);
-                ws_tile_fill<XT>(a, tp);
-                if (tp.bulk) bulk_prefetch_l2(tp.src, kWsTileSamples * (int)sizeof(XT));
+            if (a.l2_prefetch && tid == 0 && tile + 2 * step < a.n_tiles) {
+                ws_advance(a, rn, qn, step);
+                const WsTile tp = ws_tile(a, rn, qn);
+                if (tp.bulk) bulk_prefetch_l2(reinterpret_cast<const XT*>(a.wave) + tp.src_off, kWsTileSamples * (int)sizeof(XT));
             }
         }
-        XT* s_x = reinterpret_cast<XT*>(reinterpret_cast<unsigned char*>(s_x0) + buf * kXBufBytes);
+        __syncwarp();                                                   // reconverge before the FFT (lane 0 took a detour)
+        const WsTile ti = ws_tile(a, row, tq);
+        const bool active = ti.active;
         cf z[20];
-        if (ti.active) {
+        if (active) {
+            XT* s_x = reinterpret_cast<XT*>(reinterpret_cast<unsigned char*>(s_x0) + buf * kXBufBytes);
             if (ti.bulk) {
-                mbar_wait(x_full + buf, (xfull_par >> buf) & 1);
+                mbar_wait_sleep(x_full + buf, (xfull_par >> buf) & 1);
                 xfull_par ^= 1u << buf;
             } else {
                 // edge tile (reflection), unaligned row or chunk boundary: element-wise staging by all producers
-                if (k >= 2) mbar_wait(x_empty + buf, ((k - 2) >> 1) & 1);
+                if (k >= 2) mbar_wait_sleep(x_empty + buf, ((k - 2) >> 1) & 1);
                 const int s0 = kHop * ti.t0 - kHalf;
-                const XT* rowp = reinterpret_cast<const XT*>(a.wave) + (long long)ti.row * a.row_stride;
+                const XT* rowp = reinterpret_cast<const XT*>(a.wave) + (long long)row * a.row_stride;
                 for (int i = tid; i < kWsTileSamples; i += kWsRoleThreads) {
                     int g = s0 + i;
                     if (g < 0) g = -g;                                  // reflect, no edge repeat
@@ -158,13 +176,15 @@ __device__ __forceinline__ void ws_producer(const KernelArgs& a, unsigned char* 
                 }
                 named_bar_sync(2, kWsRoleThreads);
             }
-            stage1_ws_fft<XT>(s_x + kXG * g1 + j, win, z);
+            if (!kWinReg) load_window(j, reinterpret_cast<const float*>(smem), XLayout<XT>::kScale, win);
+            stage1_ws_fft<XT>(reinterpret_cast<const XT*>(reinterpret_cast<const unsigned char*>(xg) + buf * kXBufBytes), win, z);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(x_empty + buf);                      // this warp no longer reads x[buf]
-        if (ti.active) {
-            if (k >= 2) mbar_wait(e_empty + buf, ((k - 2) >> 1) & 1);   // consumers have loaded E[buf] of tile k-2
-            cf* col = s_e0 + buf * kWsECf + ws_e_base(g1) + j;
+        __syncwarp();
+        // every tile, active or not: a producer never runs more than one phase ahead of the consumers
+        if (k >= 2) mbar_wait_sleep(e_empty + buf, ((k - 2) >> 1) & 1); // consumers have loaded E[buf] of tile k-2
+        if (active) {
             if (!kTwReg) {
 #pragma unroll
                 for (int h = 0; h < 5; ++h) {
@@ -173,11 +193,12 @@ __device__ __forceinline__ void ws_producer(const KernelArgs& a, unsigned char* 
                     tw[2 * h + 1] = make_float2(tt.z, tt.w);
                 }
             }
-            stage1_ws_store(z, tw, col);
+            stage1_ws_store(z, tw, col0 + buf * kWsECf);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(e_full + buf);
-        ti = tn;
+        __syncwarp();
+        ws_advance(a, row, tq, step);
     }
 }
 
@@ -185,8 +206,8 @@ __device__ __forceinline__ void ws_producer(const KernelArgs& a, unsigned char* 
 // Tile (k-1) leaves shared memory: full tiles of a [.., T, 80] output go out as 16 bulk copies of one 640-byte
 // frame pair each; everything else (partial tiles, zero fill of frames beyond a row's own length, [.., 80, T]
 // layout, unaligned output) takes the cooperative element-wise path.  Returns whether bulk copies were issued.
-__device__ __forceinline__ bool ws_store_tile(const KernelArgs& a, const WsTile& t, const float* s_y, int tid) {
-    float* out_row = a.out + (a.out_offsets ? a.out_offsets[t.row] * kMaxMels : (long long)t.row * a.out_row_stride);
+__device__ __forceinline__ bool ws_store_tile(const KernelArgs& a, int row, const WsTile& t, const float* s_y, int tid) {
+    float* out_row = a.out + (a.out_offsets ? a.out_offsets[row] * kMaxMels : (long long)row * a.out_row_stride);
     if (t.active && t.full && a.out_layout == TALFE_LAYOUT_TM && a.out_align_ok) {
         // the two frames of a pair are contiguous in Y (ws_y_off): 16 copies of 640 bytes, pair w and w + 10 by lane 0
         // of consumer warp w (per-lane bulk copies are serialised by the hardware interface, so spread them over warps)
@@ -199,6 +220,7 @@ __device__ __forceinline__ bool ws_store_tile(const KernelArgs& a, const WsTile&
                          2 * kMaxMels * (unsigned)sizeof(float));
             bulk_commit();
         }
+        __syncwarp();
         return true;
     }
     if (!t.active && a.out_offsets) return false;                       // packed output has no padding frames
@@ -217,7 +239,7 @@ __device__ __forceinline__ bool ws_store_tile(const KernelArgs& a, const WsTile&
     return false;
 }
 
-template <typename XT>
+template <typename XT, bool kMelReg>
 __device__ __forceinline__ void ws_consumer(const KernelArgs& a, unsigned char* smem, const cf* s_e0, cf* s_p, float* s_y0,
                                             unsigned long long* s_bar, const int tid) {
     unsigned long long* e_full = s_bar + 4;
@@ -225,12 +247,12 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, unsigned char* 
     const int warp = tid >> 5, lane = tid & 31;
     const int g = tid & (kWsGroups - 1), r = tid >> 4;                  // r: exchange row in stage 2, mel lane in the mel stage
     const bool special = r >= 18;                                       // warp 9: the packed rows, both frames
+    const float4* s_w4 = reinterpret_cast<const float4*>(smem + a.off_w_ws) + r * (kRefWStride / 4);
     float w[kRefWStride];
-    {
-        const float4* w4 = reinterpret_cast<const float4*>(smem + a.off_w_ws) + r * (kRefWStride / 4);
+    if (kMelReg) {
 #pragma unroll
         for (int q = 0; q < kRefWStride / 4; ++q) {
-            const float4 t = w4[q];
+            const float4 t = s_w4[q];
             w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
         }
     }
@@ -240,24 +262,24 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, unsigned char* 
     const cf* e_row0 = s_e0 + ws_e_base(g) + r * kWsERow;
     float* pgf = reinterpret_cast<float*>(s_p) + 2 * g + (r & 1);
     cf* pg = s_p + g;
+    float* yb0 = s_y0 + ws_y_off(2 * g) + r;
     const int k1 = 1 + (r >> 1);
     double acc_s = 0.0, acc_q = 0.0;
 
     const int step = (int)gridDim.x;
     int tile = blockIdx.x;
-    WsTile ti, prev;
-    ti.row = tile / a.tiles_per_row;
-    ti.tq = tile - ti.row * a.tiles_per_row;
-    prev = ti;
+    int row = tile / a.tiles_per_row, tq = tile - row * a.tiles_per_row;
+    int prow = row, ptq = tq;
     int k = 0;
     for (; tile < a.n_tiles; tile += step, ++k) {
         const int buf = k & 1;
-        ws_tile_fill<XT>(a, ti);
+        const WsTile ti = ws_tile(a, row, tq);
         cf v[20];
-        mbar_wait(e_full + buf, (k >> 1) & 1);
+        mbar_wait_sleep(e_full + buf, (k >> 1) & 1);
         if (ti.active) stage2_load(e_row0 + buf * kWsECf, v);
         __syncwarp();
         if (lane == 0) mbar_arrive(e_empty + buf);
+        __syncwarp();
         cf pw[10];
         if (ti.active) {
             if (!special) stage2_ws_power_normal(v, pw);
@@ -265,7 +287,7 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, unsigned char* 
         }
         named_bar_sync(1, kWsRoleThreads);                              // A: mel(k-1) done everywhere: P is free, Y[(k-1)&1] is complete
         bool issued = false;
-        if (k >= 1) issued = ws_store_tile(a, prev, s_y0 + (buf ^ 1) * kWsYFloats, tid);
+        if (k >= 1) issued = ws_store_tile(a, prow, ws_tile(a, prow, ptq), s_y0 + (buf ^ 1) * kWsYFloats, tid);
         if (ti.active) {
             if (!special) stage2_ws_store_normal(k1, pw, pgf);
             else stage2_ws_store_special(r == 18, pw, pg);
@@ -276,9 +298,16 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, unsigned char* 
         named_bar_sync(1, kWsRoleThreads);                              // B: P(k) complete
         float sum = 0.f, sumsq = 0.f;
         if (ti.active) {
+            if (!kMelReg) {
+#pragma unroll
+                for (int q = 0; q < kRefWStride / 4; ++q) {
+                    const float4 t = s_w4[q];
+                    w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
+                }
+            }
             float y[2 * kMelSlots];
             mel_log_ws(pg, w, lo, a.eps, y);
-            float* yb = s_y0 + buf * kWsYFloats + ws_y_off(2 * g) + r;
+            float* yb = yb0 + buf * kWsYFloats;
 #pragma unroll
             for (int i = 0; i < kMelSlots; ++i) {
                 yb[20 * i] = y[2 * i];
@@ -309,11 +338,11 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, unsigned char* 
             acc_s += (double)sum;
             acc_q += (double)sumsq;
         }
-        prev = ti;
-        ws_tile_advance(a, ti, step);
+        prow = row; ptq = tq;
+        ws_advance(a, row, tq, step);
     }
     named_bar_sync(1, kWsRoleThreads);
-    if (k >= 1) ws_store_tile(a, prev, s_y0 + ((k - 1) & 1) * kWsYFloats, tid);
+    if (k >= 1) ws_store_tile(a, prow, ws_tile(a, prow, ptq), s_y0 + ((k - 1) & 1) * kWsYFloats, tid);
     if (!a.partials_per_tile) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -332,7 +361,9 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, unsigned char* 
     if (lane == 0) bulk_wait_all<0>();                                  // shared memory must outlive the copies that read it
 }
 
-template <typename XT, bool kTwReg>
+// kCfg bit 0: twiddles in producer registers, bit 1: window taps in producer registers, bit 2: mel weights in consumer
+// registers (a cleared bit = re-read from the shared-memory tables once per tile)
+template <typename XT, int kCfg>
 __global__ void __launch_bounds__(kWsThreads, 1) logmel_ws_kernel(const KernelArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     // carve-up: tables | x[2] | E[2] | P | Y[2] | 8 mbarriers
@@ -357,8 +388,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) logmel_ws_kernel(const KernelAr
     }
     __syncthreads();
     cudaGridDependencySynchronize();
-    if (tid < kWsRoleThreads) ws_producer<XT, kTwReg>(a, smem, s_x0, s_e0, s_bar, tid);
-    else ws_consumer<XT>(a, smem, s_e0, s_p, s_y0, s_bar, tid - kWsRoleThreads);
+    if (tid < kWsRoleThreads) ws_producer<XT, (kCfg & 1) != 0, (kCfg & 2) != 0>(a, smem, s_x0, s_e0, s_bar, tid);
+    else ws_consumer<XT, (kCfg & 4) != 0>(a, smem, s_e0, s_p, s_y0, s_bar, tid - kWsRoleThreads);
 }
 
 constexpr size_t ws_smem_bytes(size_t blob_bytes) {

@@ -55,9 +55,12 @@ def timeit(mod, norm):
 
 variants = {
     "legacy": {"TALFE_KERNEL": "legacy"},
-    "ws_tw1_pf1": {"TALFE_KERNEL": "ws", "TALFE_TW_REG": "1", "TALFE_L2_PREFETCH": "1"},
-    "ws_tw0_pf1": {"TALFE_KERNEL": "ws", "TALFE_TW_REG": "0", "TALFE_L2_PREFETCH": "1"},
-    "ws_tw1_pf0": {"TALFE_KERNEL": "ws", "TALFE_TW_REG": "1", "TALFE_L2_PREFETCH": "0"},
+    "ws_cfg1": {"TALFE_KERNEL": "ws", "TALFE_WS_CFG": "1"},
+    "ws_cfg0": {"TALFE_KERNEL": "ws", "TALFE_WS_CFG": "0"},
+    "ws_cfg2": {"TALFE_KERNEL": "ws", "TALFE_WS_CFG": "2"},
+    "ws_cfg3": {"TALFE_KERNEL": "ws", "TALFE_WS_CFG": "3"},
+    "ws_cfg5": {"TALFE_KERNEL": "ws", "TALFE_WS_CFG": "5"},
+    "ws_cfg1_nopf": {"TALFE_KERNEL": "ws", "TALFE_WS_CFG": "1", "TALFE_L2_PREFETCH": "0"},
 }
 res = {}
 ref = None
@@ -70,6 +73,6 @@ for name, env in variants.items():
     k_ms, k_host = timeit(mod, "none")
     f_ms, f_host = timeit(mod, "batch")
     res[name] = {"kernel_ms": k_ms, "forward_ms": f_ms, "host_ms_per_call": k_host,
-                 "gframes_per_s_kernel": B * T / k_ms / 1e6, "equal_to_legacy": bool(torch.equal(y, ref)),
+                 "gframes_per_s_kernel": B * T / k_ms / 1e6, "equal_to_legacy": bool(torch.equal(y, ref)), "max_abs_diff_vs_legacy": float((y - ref).abs().max()),
                  "frac_of_6445GBs": B * T * 960 / (k_ms * 1e-3) / 6445.3e9}
 print(json.dumps(res, indent=1))
