@@ -727,7 +727,8 @@ int talfe_plan_create(talfe_plan** plan_out, int device, int n_mels, const float
         p->ws_cfg = env_int("TALFE_WS_CFG", 1) & 7;
         p->l2_prefetch = env_int("TALFE_L2_PREFETCH", 1);
     }
-    p->smem_bytes = t.blob_bytes + (size_t)kXFloats * sizeof(float) +
+    // the legacy kernel stages only its own tables (the blob's prefix up to the ws tables): 2 CTAs per SM need <= 113.5 KB each
+    p->smem_bytes = t.off_w_ws + (size_t)kXFloats * sizeof(float) +
                     (size_t)kGroupsPerCta * kEGroup * sizeof(cf) + (size_t)kGroupsPerCta * t.pstride * sizeof(cf) + 16;
     cudaError_t e = cudaMalloc(&p->blob_dev, t.blob_bytes);
     if (e == cudaSuccess) e = cudaMemcpy(p->blob_dev, t.blob.data(), t.blob_bytes, cudaMemcpyHostToDevice);
@@ -777,6 +778,7 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
     if (job->norm < TALFE_NORM_NONE || job->norm > TALFE_NORM_ROW_MEL_MEANVAR) return TALFE_ERR_INVALID;
     if (job->out_layout != TALFE_LAYOUT_TM && job->out_layout != TALFE_LAYOUT_MT) return TALFE_ERR_INVALID;
     if (job->row_stride < job->buf_len) return TALFE_ERR_INVALID;
+    if (!(job->eps >= 1.1754944e-38f)) return TALFE_ERR_UNSUPPORTED;    // the log is the bare MUFU.LG2 (subnormals flush): eps keeps its argument normal
     if (!job->lens) {
         if (job->total_len <= kHalf) return TALFE_ERR_TOO_SHORT;
         if (job->frame0 + job->n_frames > 1 + job->total_len / kHop) return TALFE_ERR_INVALID;
@@ -816,7 +818,7 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
     if (w.n_tiles > 0x7fffffffLL) return TALFE_ERR_UNSUPPORTED;
     a.tiles_per_row = (int)w.tiles_per_row; a.n_tiles = (int)w.n_tiles;
     a.partials = reinterpret_cast<double2*>(ws + w.partials);
-    a.blob = plan->blob_dev; a.blob_bytes = (int)plan->blob_bytes;
+    a.blob = plan->blob_dev; a.blob_bytes = (int)(plan->variant == 1 ? plan->blob_bytes : plan->off_w_ws);
     a.off_tw = (int)plan->off_tw; a.off_w = (int)plan->off_w; a.off_lo = (int)plan->off_lo; a.off_id = (int)plan->off_id;
     a.layout = plan->layout; a.pstride = plan->pstride;
 

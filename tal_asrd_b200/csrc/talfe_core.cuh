@@ -289,9 +289,13 @@ TALFE_HD bool is_reference_layout(const MelLayout& ml) {
            ml.width[2] == kRefW2 && ml.width[3] == kRefW3 && ml.wstride == kRefWStride;
 }
 
+// ln(x) for x >= eps > 0 (power + eps is never subnormal for any sensible eps): the bare MUFU.LG2 without the
+// subnormal-range rescue that __logf wraps around it (3 extra instructions per value)
 TALFE_HD float fast_log(float x) {
 #ifdef __CUDA_ARCH__
-    return __logf(x);
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r * 0.693147180559945309f;
 #else
     return logf(x);
 #endif

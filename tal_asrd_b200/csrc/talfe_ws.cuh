@@ -1,9 +1,12 @@
 // talfe_ws.cuh — warp-specialised version of K1 (included by talfe.cu after its helpers).
 //
 // One persistent CTA per SM, 640 threads:
-//   warps  0..9   PRODUCERS  waveform tile (TMA, double-buffered) -> window -> FFT-20 -> untangle/twiddle -> exchange E
+//   warps  0..9   PRODUCERS  waveform tile -> window -> FFT-20 -> untangle/twiddle -> exchange E; in turn (tile k by
+//                            warp k % 10) also the loader: tile descriptor, TMA fetch of the waveform tile one tile
+//                            ahead (double-buffered), L2 prefetch two tiles ahead
 //   warps 10..19  CONSUMERS  exchange E -> FFT-20 -> power P -> mel projection -> log -> staged feature tile Y
-//                            -> cp.async.bulk store to global memory (one 320-byte row per frame)
+//                            -> cp.async.bulk store to global memory (640 bytes per frame pair)
+// (a 21st warp for the loader would cost 16 registers per thread: 6 warps on one scheduler's 16K-register file)
 // Each role keeps only its own constants in registers (producers: 20 window taps + 10 twiddles; consumers: 28
 // mel weights), so the steady state reads NO tables from shared memory.  The roles meet through mbarriers
 // (x_full / x_empty / e_full / e_empty, two buffers each); the consumers synchronise among themselves with one
@@ -19,7 +22,7 @@ namespace {
 
 constexpr int kWsRoleThreads = kWsGroups * kGroup;          // 320
 constexpr int kWsRoleWarps = kWsRoleThreads / 32;           // 10
-constexpr int kWsThreads = 2 * kWsRoleThreads;              // 640
+constexpr int kWsThreads = 2 * kWsRoleThreads;              // 640: 10 producer warps, 10 consumer warps (5 per scheduler: 96 registers each)
 constexpr int kWsTileSamples = kHop * kWsFrames + (kNfft - kHop);   // 5360
 static_assert(kWsTileSamples == kTileSamples && kWsRoleWarps == kWarps, "tile geometry is shared with the legacy kernel");
 
@@ -52,32 +55,42 @@ __device__ __forceinline__ void mbar_wait_sleep(unsigned long long* bar, unsigne
     }
 }
 
-// Everything about tile (row, tq) that the roles need; recomputed where it is used (a handful of integer
-// operations) instead of being carried across the FFTs in registers.
-struct WsTile {
-    int t0, L, t_end;
-    bool active, full, bulk;
-    long long src_off;             // element offset of tile sample 0 from a.wave (bulk tiles)
+// Tile descriptor: written once per tile by the loader warp, read by the two compute roles (one LDS.128 + one LDS.64)
+// so that no compute warp spends instructions on tile bookkeeping.  Ring of 8: the loader is at most two tiles
+// ahead of the producers (x double buffer), the producers at most three ahead of the consumers' mel stage.
+struct __align__(16) WsDesc {
+    int t0, t_end, L, row;
+    int flags;                     // bit 0 active, bit 1 full, bit 2 x tile fetched by the copy engine, bit 3 bulk store allowed
+    int pad;
+    float* out_tile;               // &out[row][t0 - frame0][0] for [.., T, 80] outputs
 };
+constexpr int kWsDescRing = 8;
+enum { kWsActive = 1, kWsFull = 2, kWsBulkX = 4, kWsBulkY = 8 };
 
-__device__ __forceinline__ WsTile ws_tile(const KernelArgs& a, int row, int tq) {
-    WsTile ti;
-    ti.t0 = a.frame0 + tq * kWsFrames;
+__device__ __forceinline__ WsDesc ws_describe(const KernelArgs& a, int row, int tq, long long& src_off) {
+    WsDesc d;
+    d.t0 = a.frame0 + tq * kWsFrames;
     if (a.lens) {
-        ti.L = (int)min(a.lens[row], (long long)kMaxSamples);
-        ti.t_end = min(a.frame_end, ti.L > kHalf ? 1 + ti.L / kHop : 0);
+        d.L = (int)min(a.lens[row], (long long)kMaxSamples);
+        d.t_end = min(a.frame_end, d.L > kHalf ? 1 + d.L / kHop : 0);
     } else {
-        ti.L = a.total_len;
-        ti.t_end = a.t_end_const;
+        d.L = a.total_len;
+        d.t_end = a.t_end_const;
     }
-    ti.active = ti.t0 < ti.t_end;
-    ti.full = ti.t0 + kWsFrames <= ti.t_end;
-    const int s0 = kHop * ti.t0 - kHalf;
+    d.row = row;
+    const bool active = d.t0 < d.t_end;
+    const bool full = d.t0 + kWsFrames <= d.t_end;
+    const int s0 = kHop * d.t0 - kHalf;
     const int b0 = s0 - a.origin;
-    const bool interior = s0 >= 0 && s0 + kWsTileSamples <= ti.L && b0 >= 0 && b0 + kWsTileSamples <= a.buf_len;
-    ti.bulk = ti.active && interior && a.align_ok;
-    ti.src_off = (long long)row * a.row_stride + b0;
-    return ti;
+    const bool interior = s0 >= 0 && s0 + kWsTileSamples <= d.L && b0 >= 0 && b0 + kWsTileSamples <= a.buf_len;
+    const bool bulk_x = active && interior && a.align_ok;
+    const bool bulk_y = active && full && a.out_layout == TALFE_LAYOUT_TM && a.out_align_ok;
+    d.flags = (active ? kWsActive : 0) | (full ? kWsFull : 0) | (bulk_x ? kWsBulkX : 0) | (bulk_y ? kWsBulkY : 0);
+    d.pad = 0;
+    d.out_tile = a.out + (a.out_offsets ? a.out_offsets[row] * kMaxMels : (long long)row * a.out_row_stride) +
+                 (long long)(d.t0 - a.frame0) * kMaxMels;
+    src_off = (long long)row * a.row_stride + b0;
+    return d;
 }
 
 __device__ __forceinline__ void ws_advance(const KernelArgs& a, int& row, int& tq, int step) {
@@ -87,8 +100,8 @@ __device__ __forceinline__ void ws_advance(const KernelArgs& a, int& row, int& t
 
 // ------------------------------------------------------------------------------------------ producers
 template <typename XT, bool kTwReg, bool kWinReg>
-__device__ __forceinline__ void ws_producer(const KernelArgs& a, unsigned char* smem, XT* s_x0, cf* s_e0, unsigned long long* s_bar,
-                                            const int tid) {
+__device__ __forceinline__ void ws_producer(const KernelArgs& a, unsigned char* smem, XT* s_x0, cf* s_e0, WsDesc* s_desc,
+                                            unsigned long long* s_bar, const int tid, const int n_my) {
     unsigned long long* x_full = s_bar;            // [2]
     unsigned long long* x_empty = s_bar + 2;       // [2]
     unsigned long long* e_full = s_bar + 4;        // [2]
@@ -110,68 +123,64 @@ __device__ __forceinline__ void ws_producer(const KernelArgs& a, unsigned char* 
             tw[2 * h + 1] = make_float2(tt.z, tt.w);
         }
     }
-    // a tile fetch = 17 pieces of <= 320 samples (one per skew block); warp w issues pieces w and w + 10
-    auto issue = [&](const WsTile& t, int buf) {                        // lane 0 of every producer warp
-        const XT* src = reinterpret_cast<const XT*>(a.wave) + t.src_off;
-        const unsigned long long policy = l2_evict_first_policy();
-        if (tid == 0) mbar_expect_tx(x_full + buf, kWsTileSamples * (int)sizeof(XT));
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int pb = warp + h * kWsRoleWarps;
-            if (pb * kXBlock < kWsTileSamples)
-                bulk_g2s_u32(smem_u32(s_x0 + pb * kXG) + buf * kXBufBytes, src + pb * kXBlock,
-                             (unsigned)(min(kXBlock, kWsTileSamples - pb * kXBlock) * (int)sizeof(XT)), x_full + buf, policy);
-        }
-    };
-
-    const int step = (int)gridDim.x;
-    int tile = blockIdx.x;
-    int row = tile / a.tiles_per_row, tq = tile - row * a.tiles_per_row;
-    if (lane == 0) {
-        const WsTile t0 = ws_tile(a, row, tq);
-        if (t0.bulk) issue(t0, 0);
-    }
-    __syncwarp();
-    unsigned xfull_par = 0;                                             // bit b: parity of the next x_full[b] phase to wait for
     const XT* xg = s_x0 + kXG * g1 + j;
     cf* col0 = s_e0 + ws_e_base(g1) + j;
-    for (int k = 0; tile < a.n_tiles; tile += step, ++k) {
-        const int buf = k & 1;
-        if (lane == 0 && tile + step < a.n_tiles) {                     // tile k+1: HBM -> shared memory; tile k+2: HBM -> L2
-            int rn = row, qn = tq;
-            ws_advance(a, rn, qn, step);
-            const WsTile tn = ws_tile(a, rn, qn);
-            if (tn.bulk) {
-                if (k >= 1) mbar_wait_sleep(x_empty + (buf ^ 1), ((k - 1) >> 1) & 1);   // tile k-1 has left that buffer
-                issue(tn, buf ^ 1);
-            }
-            if (a.l2_prefetch && tid == 0 && tile + 2 * step < a.n_tiles) {
-                ws_advance(a, rn, qn, step);
-                const WsTile tp = ws_tile(a, rn, qn);
-                if (tp.bulk) bulk_prefetch_l2(reinterpret_cast<const XT*>(a.wave) + tp.src_off, kWsTileSamples * (int)sizeof(XT));
-            }
+    // Loader duty, taken in turn by the producer warps (tile kk by warp kk % 10, one tile ahead of the FFTs): all 32
+    // lanes run it (no divergent waiting): descriptor, wait for x[kk & 1] to be free, byte count, the 17 pieces of the
+    // tile fetch (lane i = piece i, one per 320-sample skew block), then an L2 prefetch of the tile after next.
+    const int step = (int)gridDim.x;
+    auto load_duty = [&](int kk) {
+        const int tile = (int)blockIdx.x + kk * step;
+        const int row = tile / a.tiles_per_row, tq = tile - row * a.tiles_per_row;
+        const int lbuf = kk & 1;
+        long long src_off;
+        const WsDesc d = ws_describe(a, row, tq, src_off);
+        if (lane == 0) s_desc[kk & (kWsDescRing - 1)] = d;
+        if (kk >= 2) mbar_wait_sleep(x_empty + lbuf, ((kk - 2) >> 1) & 1);               // tile kk-2 has left x[lbuf]
+        if (d.flags & kWsBulkX) {
+            const XT* src = reinterpret_cast<const XT*>(a.wave) + src_off;
+            if (lane == 0) mbar_expect_tx(x_full + lbuf, kWsTileSamples * (int)sizeof(XT));   // release: publishes the descriptor too
+            __syncwarp();
+            if (lane * kXBlock < kWsTileSamples)
+                bulk_g2s_u32(smem_u32(s_x0 + lane * kXG) + lbuf * kXBufBytes, src + lane * kXBlock,
+                             (unsigned)(min(kXBlock, kWsTileSamples - lane * kXBlock) * (int)sizeof(XT)), x_full + lbuf,
+                             l2_evict_first_policy());
+        } else if (lane == 0) {
+            mbar_arrive(x_full + lbuf);                                                  // nothing in flight: descriptor only
         }
-        __syncwarp();                                                   // reconverge before the FFT (lane 0 took a detour)
-        const WsTile ti = ws_tile(a, row, tq);
-        const bool active = ti.active;
+        __syncwarp();
+        if (a.l2_prefetch && lane == 0 && tile + 2 * step < a.n_tiles) {                 // tile kk+2: HBM -> L2
+            int r2 = row, q2 = tq;
+            ws_advance(a, r2, q2, 2 * step);
+            long long off2;
+            const WsDesc d2 = ws_describe(a, r2, q2, off2);
+            if (d2.flags & kWsBulkX) bulk_prefetch_l2(reinterpret_cast<const XT*>(a.wave) + off2, kWsTileSamples * (int)sizeof(XT));
+        }
+        __syncwarp();
+    };
+    if (warp == 0) load_duty(0);
+    for (int k = 0; k < n_my; ++k) {
+        const int buf = k & 1;
+        if (k + 1 < n_my && (k + 1) % kWsRoleWarps == warp) load_duty(k + 1);
+        mbar_wait_sleep(x_full + buf, (k >> 1) & 1);                    // descriptor published, bulk tile landed
+        const int flags = s_desc[k & (kWsDescRing - 1)].flags;
+        const bool active = flags & kWsActive;
         cf z[20];
         if (active) {
-            XT* s_x = reinterpret_cast<XT*>(reinterpret_cast<unsigned char*>(s_x0) + buf * kXBufBytes);
-            if (ti.bulk) {
-                mbar_wait_sleep(x_full + buf, (xfull_par >> buf) & 1);
-                xfull_par ^= 1u << buf;
-            } else {
+            if (!(flags & kWsBulkX)) {
                 // edge tile (reflection), unaligned row or chunk boundary: element-wise staging by all producers
-                if (k >= 2) mbar_wait_sleep(x_empty + buf, ((k - 2) >> 1) & 1);
-                const int s0 = kHop * ti.t0 - kHalf;
-                const XT* rowp = reinterpret_cast<const XT*>(a.wave) + (long long)row * a.row_stride;
+                // (x[buf] is free: the loader waited for x_empty before it arrived on x_full)
+                const WsDesc d = s_desc[k & (kWsDescRing - 1)];
+                XT* s_x = reinterpret_cast<XT*>(reinterpret_cast<unsigned char*>(s_x0) + buf * kXBufBytes);
+                const int s0 = kHop * d.t0 - kHalf;
+                const XT* rowp = reinterpret_cast<const XT*>(a.wave) + (long long)d.row * a.row_stride;
                 for (int i = tid; i < kWsTileSamples; i += kWsRoleThreads) {
                     int g = s0 + i;
                     if (g < 0) g = -g;                                  // reflect, no edge repeat
-                    if (g >= ti.L) g = 2 * (ti.L - 1) - g;
+                    if (g >= d.L) g = 2 * (d.L - 1) - g;
                     const int bi = g - a.origin;
                     XT v = XT(0.f);
-                    if (g >= 0 && g < ti.L && bi >= 0 && bi < a.buf_len) v = __ldg(rowp + bi);
+                    if (g >= 0 && g < d.L && bi >= 0 && bi < a.buf_len) v = __ldg(rowp + bi);
                     s_x[xskew<XT>(i)] = v;
                 }
                 named_bar_sync(2, kWsRoleThreads);
@@ -198,22 +207,21 @@ __device__ __forceinline__ void ws_producer(const KernelArgs& a, unsigned char* 
         __syncwarp();
         if (lane == 0) mbar_arrive(e_full + buf);
         __syncwarp();
-        ws_advance(a, row, tq, step);
     }
 }
 
 // ------------------------------------------------------------------------------------------ consumers
 // Tile (k-1) leaves shared memory: full tiles of a [.., T, 80] output go out as 16 bulk copies of one 640-byte
-// frame pair each; everything else (partial tiles, zero fill of frames beyond a row's own length, [.., 80, T]
-// layout, unaligned output) takes the cooperative element-wise path.  Returns whether bulk copies were issued.
-__device__ __forceinline__ bool ws_store_tile(const KernelArgs& a, int row, const WsTile& t, const float* s_y, int tid) {
-    float* out_row = a.out + (a.out_offsets ? a.out_offsets[row] * kMaxMels : (long long)row * a.out_row_stride);
-    if (t.active && t.full && a.out_layout == TALFE_LAYOUT_TM && a.out_align_ok) {
-        // the two frames of a pair are contiguous in Y (ws_y_off): 16 copies of 640 bytes, pair w and w + 10 by lane 0
-        // of consumer warp w (per-lane bulk copies are serialised by the hardware interface, so spread them over warps)
+// frame pair each (pair w and w + 10 by lane 0 of consumer warp w: per-lane bulk copies are serialised by the
+// hardware interface, so they are spread over the warps); everything else (partial tiles, zero fill of frames
+// beyond a row's own length, [.., 80, T] layout, unaligned output) takes the cooperative element-wise path.
+// Returns whether bulk copies were issued.
+__device__ __forceinline__ bool ws_store_tile(const KernelArgs& a, const WsDesc* dp, const float* s_y, int tid) {
+    const int flags = dp->flags;
+    if (flags & kWsBulkY) {
         if ((tid & 31) == 0) {
             const int w = tid >> 5;
-            float* dst = out_row + (long long)(t.t0 - a.frame0) * kMaxMels;
+            float* dst = dp->out_tile;
             bulk_s2g(dst + 2 * w * kMaxMels, smem_u32(s_y + ws_y_off(2 * w)), 2 * kMaxMels * (unsigned)sizeof(float));
             if (w + kWsRoleWarps < kWsGroups)
                 bulk_s2g(dst + 2 * (w + kWsRoleWarps) * kMaxMels, smem_u32(s_y + ws_y_off(2 * (w + kWsRoleWarps))),
@@ -223,14 +231,17 @@ __device__ __forceinline__ bool ws_store_tile(const KernelArgs& a, int row, cons
         __syncwarp();
         return true;
     }
-    if (!t.active && a.out_offsets) return false;                       // packed output has no padding frames
+    const WsDesc t = *dp;
+    const bool active = flags & kWsActive;
+    if (!active && a.out_offsets) return false;                         // packed output has no padding frames
+    float* out_row = a.out + (a.out_offsets ? a.out_offsets[t.row] * kMaxMels : (long long)t.row * a.out_row_stride);
     const int nfr = min(kWsFrames, a.frame_end - t.t0);
     for (int i = tid; i < nfr * kMaxMels; i += kWsRoleThreads) {
         int f, m;
         if (a.out_layout == TALFE_LAYOUT_TM) { f = i / kMaxMels; m = i - f * kMaxMels; }
         else { m = i / nfr; f = i - m * nfr; }                          // frame fastest: contiguous in [.., 80, T]
         const int t_abs = t.t0 + f;
-        const bool valid = t.active && t_abs < t.t_end;
+        const bool valid = active && t_abs < t.t_end;
         if (!valid && a.out_offsets) continue;
         const float v = valid ? s_y[ws_y_off(f) + m] : 0.f;
         if (a.out_layout == TALFE_LAYOUT_TM) out_row[(long long)(t_abs - a.frame0) * kMaxMels + m] = v;
@@ -241,7 +252,7 @@ __device__ __forceinline__ bool ws_store_tile(const KernelArgs& a, int row, cons
 
 template <typename XT, bool kMelReg>
 __device__ __forceinline__ void ws_consumer(const KernelArgs& a, unsigned char* smem, const cf* s_e0, cf* s_p, float* s_y0,
-                                            unsigned long long* s_bar, const int tid) {
+                                            const WsDesc* s_desc, unsigned long long* s_bar, const int tid, const int n_my) {
     unsigned long long* e_full = s_bar + 4;
     unsigned long long* e_empty = s_bar + 6;
     const int warp = tid >> 5, lane = tid & 31;
@@ -266,29 +277,26 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, unsigned char* 
     const int k1 = 1 + (r >> 1);
     double acc_s = 0.0, acc_q = 0.0;
 
-    const int step = (int)gridDim.x;
-    int tile = blockIdx.x;
-    int row = tile / a.tiles_per_row, tq = tile - row * a.tiles_per_row;
-    int prow = row, ptq = tq;
-    int k = 0;
-    for (; tile < a.n_tiles; tile += step, ++k) {
+    for (int k = 0; k < n_my; ++k) {
         const int buf = k & 1;
-        const WsTile ti = ws_tile(a, row, tq);
+        const WsDesc* dp = s_desc + (k & (kWsDescRing - 1));
         cf v[20];
         mbar_wait_sleep(e_full + buf, (k >> 1) & 1);
-        if (ti.active) stage2_load(e_row0 + buf * kWsECf, v);
+        const int flags = dp->flags;
+        const bool active = flags & kWsActive;
+        if (active) stage2_load(e_row0 + buf * kWsECf, v);
         __syncwarp();
         if (lane == 0) mbar_arrive(e_empty + buf);
         __syncwarp();
         cf pw[10];
-        if (ti.active) {
+        if (active) {
             if (!special) stage2_ws_power_normal(v, pw);
             else stage2_ws_power_special(r == 18, v, pw);
         }
         named_bar_sync(1, kWsRoleThreads);                              // A: mel(k-1) done everywhere: P is free, Y[(k-1)&1] is complete
         bool issued = false;
-        if (k >= 1) issued = ws_store_tile(a, prow, ws_tile(a, prow, ptq), s_y0 + (buf ^ 1) * kWsYFloats, tid);
-        if (ti.active) {
+        if (k >= 1) issued = ws_store_tile(a, s_desc + ((k - 1) & (kWsDescRing - 1)), s_y0 + (buf ^ 1) * kWsYFloats, tid);
+        if (active) {
             if (!special) stage2_ws_store_normal(k1, pw, pgf);
             else stage2_ws_store_special(r == 18, pw, pg);
         }
@@ -297,7 +305,7 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, unsigned char* 
         }
         named_bar_sync(1, kWsRoleThreads);                              // B: P(k) complete
         float sum = 0.f, sumsq = 0.f;
-        if (ti.active) {
+        if (active) {
             if (!kMelReg) {
 #pragma unroll
                 for (int q = 0; q < kRefWStride / 4; ++q) {
@@ -313,14 +321,22 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, unsigned char* 
                 yb[20 * i] = y[2 * i];
                 yb[kMaxMels + 20 * i] = y[2 * i + 1];
             }
-            const int ta = ti.t0 + 2 * g;
+            if (flags & kWsFull) {
 #pragma unroll
-            for (int f = 0; f < 2; ++f) {
-                if (ti.full || ta + f < ti.t_end) {
+                for (int i = 0; i < 2 * kMelSlots; ++i) {
+                    sum += y[i];
+                    if (a.want_sumsq) sumsq = fmaf(y[i], y[i], sumsq);
+                }
+            } else {
+                const int ta = dp->t0 + 2 * g, t_end = dp->t_end;
 #pragma unroll
-                    for (int i = 0; i < kMelSlots; ++i) {
-                        sum += y[2 * i + f];
-                        if (a.want_sumsq) sumsq = fmaf(y[2 * i + f], y[2 * i + f], sumsq);
+                for (int f = 0; f < 2; ++f) {
+                    if (ta + f < t_end) {
+#pragma unroll
+                        for (int i = 0; i < kMelSlots; ++i) {
+                            sum += y[2 * i + f];
+                            if (a.want_sumsq) sumsq = fmaf(y[2 * i + f], y[2 * i + f], sumsq);
+                        }
                     }
                 }
             }
@@ -333,16 +349,15 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, unsigned char* 
                 ds += __shfl_xor_sync(0xffffffffu, ds, o);
                 dq += __shfl_xor_sync(0xffffffffu, dq, o);
             }
-            if (lane == 0) a.partials[(long long)tile * kWsRoleWarps + warp] = make_double2(ds, dq);
+            const long long tile = (long long)blockIdx.x + (long long)k * gridDim.x;
+            if (lane == 0) a.partials[tile * kWsRoleWarps + warp] = make_double2(ds, dq);
         } else {
             acc_s += (double)sum;
             acc_q += (double)sumsq;
         }
-        prow = row; ptq = tq;
-        ws_advance(a, row, tq, step);
     }
     named_bar_sync(1, kWsRoleThreads);
-    if (k >= 1) ws_store_tile(a, prow, ws_tile(a, prow, ptq), s_y0 + ((k - 1) & 1) * kWsYFloats, tid);
+    if (n_my >= 1) ws_store_tile(a, s_desc + ((n_my - 1) & (kWsDescRing - 1)), s_y0 + ((n_my - 1) & 1) * kWsYFloats, tid);
     if (!a.partials_per_tile) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -366,16 +381,17 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, unsigned char* 
 template <typename XT, int kCfg>
 __global__ void __launch_bounds__(kWsThreads, 1) logmel_ws_kernel(const KernelArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
-    // carve-up: tables | x[2] | E[2] | P | Y[2] | 8 mbarriers
+    // carve-up: tables | x[2] | E[2] | P | Y[2] | descriptor ring | 8 mbarriers
     XT* s_x0 = reinterpret_cast<XT*>(smem + a.blob_bytes);
     cf* s_e0 = reinterpret_cast<cf*>(smem + a.blob_bytes + 2 * kXFloats * sizeof(float));
     cf* s_p = s_e0 + 2 * kWsECf;
     float* s_y0 = reinterpret_cast<float*>(s_p + kWsPCf);
-    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_y0 + 2 * kWsYFloats);
+    WsDesc* s_desc = reinterpret_cast<WsDesc*>(s_y0 + 2 * kWsYFloats);
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_desc + kWsDescRing);
 
     const int tid = threadIdx.x;
     if (tid == 0) {
-        mbar_init(s_bar + 0, 1); mbar_init(s_bar + 1, 1);                               // x_full: the expect_tx arrival
+        mbar_init(s_bar + 0, 1); mbar_init(s_bar + 1, 1);                               // x_full: the loader's arrival (+ bytes)
         mbar_init(s_bar + 2, kWsRoleWarps); mbar_init(s_bar + 3, kWsRoleWarps);         // x_empty: one arrival per producer warp
         mbar_init(s_bar + 4, kWsRoleWarps); mbar_init(s_bar + 5, kWsRoleWarps);         // e_full
         mbar_init(s_bar + 6, kWsRoleWarps); mbar_init(s_bar + 7, kWsRoleWarps);         // e_empty: one per consumer warp
@@ -388,13 +404,14 @@ __global__ void __launch_bounds__(kWsThreads, 1) logmel_ws_kernel(const KernelAr
     }
     __syncthreads();
     cudaGridDependencySynchronize();
-    if (tid < kWsRoleThreads) ws_producer<XT, (kCfg & 1) != 0, (kCfg & 2) != 0>(a, smem, s_x0, s_e0, s_bar, tid);
-    else ws_consumer<XT, (kCfg & 4) != 0>(a, smem, s_e0, s_p, s_y0, s_bar, tid - kWsRoleThreads);
+    const int n_my = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles blockIdx.x, + gridDim.x, ...
+    if (tid < kWsRoleThreads) ws_producer<XT, (kCfg & 1) != 0, (kCfg & 2) != 0>(a, smem, s_x0, s_e0, s_desc, s_bar, tid, n_my);
+    else ws_consumer<XT, (kCfg & 4) != 0>(a, smem, s_e0, s_p, s_y0, s_desc, s_bar, tid - kWsRoleThreads, n_my);
 }
 
 constexpr size_t ws_smem_bytes(size_t blob_bytes) {
     return blob_bytes + 2 * (size_t)kXFloats * sizeof(float) + 2 * (size_t)kWsECf * sizeof(cf) + (size_t)kWsPCf * sizeof(cf) +
-           2 * (size_t)kWsYFloats * sizeof(float) + 8 * sizeof(unsigned long long);
+           2 * (size_t)kWsYFloats * sizeof(float) + kWsDescRing * sizeof(WsDesc) + 8 * sizeof(unsigned long long);
 }
 
 }  // namespace
