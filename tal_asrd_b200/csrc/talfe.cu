@@ -724,8 +724,8 @@ int talfe_plan_create(talfe_plan** plan_out, int device, int n_mels, const float
         const char* kv = std::getenv("TALFE_KERNEL");
         p->variant = p->ref_layout ? 1 : 0;                               // the warp-specialised kernel is unrolled for the reference filterbank shape
         if (kv && std::strcmp(kv, "legacy") == 0) p->variant = 0;
-        p->ws_cfg = env_int("TALFE_WS_CFG", 1) & 7;
-        p->l2_prefetch = env_int("TALFE_L2_PREFETCH", 1);
+        p->ws_cfg = env_int("TALFE_WS_CFG", 2) & 7;
+        p->l2_prefetch = env_int("TALFE_L2_PREFETCH", 0);
     }
     // the legacy kernel stages only its own tables (the blob's prefix up to the ws tables): 2 CTAs per SM need <= 113.5 KB each
     p->smem_bytes = t.off_w_ws + (size_t)kXFloats * sizeof(float) +

@@ -261,3 +261,50 @@ def test_c_abi_allreduce_stats_two_ranks():
     want = np.arange(163, dtype=np.float64) * 3
     for rank, rc, got in res:
         assert rc == 0 and np.array_equal(got, want)
+
+
+def test_host_pipeline_refuses_to_run_without_cuda():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from tal_asrd_b200 import HostPipeline, LogMelSpec
+    with pytest.raises(RuntimeError, match="no CPU implementation"):
+        HostPipeline(LogMelSpec())
+
+
+@pytest.mark.gpu
+def test_host_pipeline_equals_forward_per_batch():
+    """Seven different host batches through two device slots (every slot reused three times, shapes and dtypes
+    changing on the way): each result must be bit-identical to LogMelSpec.forward on that batch alone, i.e. no
+    batch may see a slot before the previous occupant has been transformed / copied out."""
+    from oracle import logmel_oracle as O
+    from tal_asrd_b200 import HostPipeline, LogMelSpec, synth
+    dev = torch.device("cuda:0")
+    mod = LogMelSpec().to(dev)
+    pipe = HostPipeline(mod, dev, depth=2)
+    shapes = [(6, 160000)] * 4 + [(3, 48000 + 77)] * 2 + [(6, 160000)]
+    ins, outs, evs = [], [], []
+    for i, (b, n) in enumerate(shapes):
+        x = torch.from_numpy(synth.batch(31 + i, b, n))
+        if i == 5:
+            x = (x * 32768.0).round().clamp_(-32768, 32767).to(torch.int16)
+        ins.append(x.pin_memory())
+        outs.append(torch.full((b, 1 + n // 160, 80), float("nan")).pin_memory())
+        evs.append(pipe.submit(ins[-1], outs[-1]))
+    pipe.drain()
+    assert all(e.query() for e in evs)
+    for i, (x, y) in enumerate(zip(ins, outs)):
+        want = mod(x.to(dev)).cpu()
+        assert torch.equal(y, want), f"batch {i}"
+    ref = O.logmel_f64(ins[0].numpy())
+    assert rel_err(outs[0].numpy(), ref) < 1e-4
+    with pytest.raises(ValueError):
+        pipe.submit(ins[0], outs[1][:, :10])
+    with pytest.raises(ValueError):
+        pipe.submit(ins[0].to(dev), outs[0])
+    # per-row semantics and the [B, 80, T] layout ride through unchanged
+    pipe2 = HostPipeline(mod, dev, depth=1, norm="row", layout="mt")
+    lens = torch.tensor([160000, 16000, 201, 99999, 160000, 7777])
+    y2 = torch.empty(6, 80, 1001).pin_memory()
+    pipe2.submit(ins[0], y2, audio_lens=lens).synchronize()
+    want = mod.features(ins[0].to(dev), audio_lens=lens, norm="row", layout="mt").cpu()
+    assert torch.equal(y2, want)
