@@ -55,9 +55,8 @@ struct talfe_plan_impl {
     int ctas_per_sm;
     int ref_layout;                // 80-mel reference filterbank shape -> fully unrolled mel stage
     int variant;                   // 0 = legacy kernel (2 CTAs/SM, every thread runs every stage), 1 = warp-specialised
-    int ws_cfg;                    // ws: which constant tables live in registers (talfe_ws.cuh, kCfg)
     int l2_prefetch;
-    size_t off_w_ws, off_lo_ws, ws_smem;
+    size_t off_ws, ws_bytes, off_tw_ws, off_w_ws, off_lo_ws, ws_smem;   // table section staged by the ws kernel
     MelLayout layout;
     int pstride;
     size_t off_tw, off_w, off_lo, off_id, blob_bytes;
@@ -92,7 +91,8 @@ struct KernelArgs {
     MelLayout layout;
     int pstride;
     // warp-specialised kernel only
-    int off_w_ws, off_lo_ws;       // its mel tables inside the blob
+    int off_w_ws, off_lo_ws;       // its mel tables inside the section it stages (blob = twiddles | w_ws | lo_ws)
+    const float* win_global;       // window taps [20][20] in global memory (read once into producer registers)
     int out_align_ok;              // every frame row of `out` starts 16-byte aligned (bulk stores allowed)
     int l2_prefetch;               // prefetch tile k+2 into L2 while tile k+1 travels to shared memory
 };
@@ -616,23 +616,11 @@ logmel_kernel_t kernel_for(bool ref_layout, int dtype) {
     return dtype == TALFE_F32 ? logmel_kernel<false, float> : dtype == TALFE_F16 ? logmel_kernel<false, __half> : logmel_kernel<false, short>;
 }
 
-template <int kCfg> logmel_kernel_t ws_kernel_dt(int dtype) {
-    return dtype == TALFE_F32 ? logmel_ws_kernel<float, kCfg> : dtype == TALFE_F16 ? logmel_ws_kernel<__half, kCfg> : logmel_ws_kernel<short, kCfg>;
-}
-logmel_kernel_t ws_kernel_for(int dtype, int cfg) {
-    switch (cfg & 7) {
-        case 0: return ws_kernel_dt<0>(dtype);
-        case 1: return ws_kernel_dt<1>(dtype);
-        case 2: return ws_kernel_dt<2>(dtype);
-        case 3: return ws_kernel_dt<3>(dtype);
-        case 4: return ws_kernel_dt<4>(dtype);
-        case 5: return ws_kernel_dt<5>(dtype);
-        case 6: return ws_kernel_dt<6>(dtype);
-        default: return ws_kernel_dt<7>(dtype);
-    }
+logmel_kernel_t ws_kernel_for(int dtype) {
+    return dtype == TALFE_F32 ? logmel_ws_kernel<float> : dtype == TALFE_F16 ? logmel_ws_kernel<__half> : logmel_ws_kernel<short>;
 }
 
-// Development / profiling knobs (read once per plan): TALFE_KERNEL=legacy|ws, TALFE_WS_CFG=0..7 (bit 0 twiddles, bit 1 window, bit 2 mel weights in registers), TALFE_L2_PREFETCH=0|1.
+// Development / profiling knobs (read once per plan): TALFE_KERNEL=legacy|ws, TALFE_L2_PREFETCH=0|1.
 int env_int(const char* name, int dflt) {
     const char* v = std::getenv(name);
     return (v && *v) ? std::atoi(v) : dflt;
@@ -718,17 +706,16 @@ int talfe_plan_create(talfe_plan** plan_out, int device, int n_mels, const float
     p->pstride = t.pstride;
     p->off_tw = t.off_tw; p->off_w = t.off_w; p->off_lo = t.off_lo; p->off_id = t.off_id; p->blob_bytes = t.blob_bytes;
     p->ref_layout = is_reference_layout(t.layout) ? 1 : 0;
-    p->off_w_ws = t.off_w_ws; p->off_lo_ws = t.off_lo_ws;
-    p->ws_smem = ws_smem_bytes(t.blob_bytes);
+    p->off_ws = t.off_ws; p->ws_bytes = t.ws_bytes; p->off_tw_ws = t.off_tw_ws; p->off_w_ws = t.off_w_ws; p->off_lo_ws = t.off_lo_ws;
+    p->ws_smem = ws_smem_bytes(t.ws_bytes);
     {
         const char* kv = std::getenv("TALFE_KERNEL");
         p->variant = p->ref_layout ? 1 : 0;                               // the warp-specialised kernel is unrolled for the reference filterbank shape
         if (kv && std::strcmp(kv, "legacy") == 0) p->variant = 0;
-        p->ws_cfg = env_int("TALFE_WS_CFG", 2) & 7;
         p->l2_prefetch = env_int("TALFE_L2_PREFETCH", 0);
     }
-    // the legacy kernel stages only its own tables (the blob's prefix up to the ws tables): 2 CTAs per SM need <= 113.5 KB each
-    p->smem_bytes = t.off_w_ws + (size_t)kXFloats * sizeof(float) +
+    // the legacy kernel stages only its own tables (the blob's prefix up to the ws section): 2 CTAs per SM need <= 113.5 KB each
+    p->smem_bytes = t.off_ws + (size_t)kXFloats * sizeof(float) +
                     (size_t)kGroupsPerCta * kEGroup * sizeof(cf) + (size_t)kGroupsPerCta * t.pstride * sizeof(cf) + 16;
     cudaError_t e = cudaMalloc(&p->blob_dev, t.blob_bytes);
     if (e == cudaSuccess) e = cudaMemcpy(p->blob_dev, t.blob.data(), t.blob_bytes, cudaMemcpyHostToDevice);
@@ -739,7 +726,7 @@ int talfe_plan_create(talfe_plan** plan_out, int device, int n_mels, const float
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p->ctas_per_sm, kernel_for(p->ref_layout != 0, TALFE_F32), kThreads, p->smem_bytes);
     if (p->variant == 1) {
         for (int dt = TALFE_F32; dt <= TALFE_I16 && e == cudaSuccess; ++dt)
-            e = cudaFuncSetAttribute(ws_kernel_for(dt, p->ws_cfg), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->ws_smem);
+            e = cudaFuncSetAttribute(ws_kernel_for(dt), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->ws_smem);
     }
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
@@ -818,11 +805,12 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
     if (w.n_tiles > 0x7fffffffLL) return TALFE_ERR_UNSUPPORTED;
     a.tiles_per_row = (int)w.tiles_per_row; a.n_tiles = (int)w.n_tiles;
     a.partials = reinterpret_cast<double2*>(ws + w.partials);
-    a.blob = plan->blob_dev; a.blob_bytes = (int)(plan->variant == 1 ? plan->blob_bytes : plan->off_w_ws);
-    a.off_tw = (int)plan->off_tw; a.off_w = (int)plan->off_w; a.off_lo = (int)plan->off_lo; a.off_id = (int)plan->off_id;
+    const bool use_ws = plan->variant == 1;
+    a.blob = plan->blob_dev + (use_ws ? plan->off_ws : 0); a.blob_bytes = (int)(use_ws ? plan->ws_bytes : plan->off_ws);
+    a.win_global = reinterpret_cast<const float*>(plan->blob_dev);
+    a.off_tw = (int)(use_ws ? plan->off_tw_ws : plan->off_tw); a.off_w = (int)plan->off_w; a.off_lo = (int)plan->off_lo; a.off_id = (int)plan->off_id;
     a.layout = plan->layout; a.pstride = plan->pstride;
 
-    const bool use_ws = plan->variant == 1;
     a.off_w_ws = (int)plan->off_w_ws; a.off_lo_ws = (int)plan->off_lo_ws;
     a.l2_prefetch = plan->l2_prefetch;
     a.out_align_ok = ((reinterpret_cast<uintptr_t>(job->out) & 15) == 0 && (ors & 3) == 0) ? 1 : 0;
@@ -840,7 +828,7 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        TALFE_CUDA(cudaLaunchKernelEx(&cfg, use_ws ? ws_kernel_for(a.dtype, plan->ws_cfg) : kernel_for(plan->ref_layout != 0, a.dtype),
+        TALFE_CUDA(cudaLaunchKernelEx(&cfg, use_ws ? ws_kernel_for(a.dtype) : kernel_for(plan->ref_layout != 0, a.dtype),
                                       (const KernelArgs)a));
     }
 

@@ -49,7 +49,9 @@ struct HostTables {
     // power reads are conflict-free for any ownership), weights live in the consumer threads' registers
     std::vector<float> w_ws;        // [20][wstride]
     std::vector<int> lo_ws;         // [4][20] slot-major first bins
-    size_t off_w_ws, off_lo_ws;
+    // section staged by the warp-specialised kernel: [twiddles | w_ws | lo_ws] starting at off_ws (its window taps are
+    // read once from global memory into registers); off_tw_ws / off_w_ws / off_lo_ws are relative to off_ws
+    size_t off_ws, ws_bytes, off_tw_ws, off_w_ws, off_lo_ws;
     // byte offsets inside the blob that is copied to shared memory
     size_t off_win, off_tw, off_w, off_lo, off_id, blob_bytes;
     std::vector<unsigned char> blob;
@@ -170,17 +172,21 @@ inline int build_tables(int n_mels, const float* window, const float* fb, HostTa
     t.off_w = align16(t.off_tw + 400 * sizeof(float));
     t.off_lo = align16(t.off_w + t.w_t.size() * sizeof(float));
     t.off_id = align16(t.off_lo + kMaxMels * sizeof(int));
-    t.off_w_ws = align16(t.off_id + kMaxMels * sizeof(int));
+    t.off_ws = align16(t.off_id + kMaxMels * sizeof(int));
+    t.off_tw_ws = 0;
+    t.off_w_ws = align16(t.off_tw_ws + 400 * sizeof(float));
     t.off_lo_ws = align16(t.off_w_ws + t.w_ws.size() * sizeof(float));
-    t.blob_bytes = align16(t.off_lo_ws + kMaxMels * sizeof(int));
+    t.ws_bytes = align16(t.off_lo_ws + kMaxMels * sizeof(int));
+    t.blob_bytes = t.off_ws + t.ws_bytes;
     t.blob.assign(t.blob_bytes, 0);
     std::memcpy(t.blob.data() + t.off_win, t.win_t.data(), 400 * sizeof(float));
     std::memcpy(t.blob.data() + t.off_tw, t.tw_t.data(), 400 * sizeof(float));
     std::memcpy(t.blob.data() + t.off_w, t.w_t.data(), t.w_t.size() * sizeof(float));
     std::memcpy(t.blob.data() + t.off_lo, t.mel_lo.data(), kMaxMels * sizeof(int));
     std::memcpy(t.blob.data() + t.off_id, t.mel_id.data(), kMaxMels * sizeof(int));
-    std::memcpy(t.blob.data() + t.off_w_ws, t.w_ws.data(), t.w_ws.size() * sizeof(float));
-    std::memcpy(t.blob.data() + t.off_lo_ws, t.lo_ws.data(), kMaxMels * sizeof(int));
+    std::memcpy(t.blob.data() + t.off_ws + t.off_tw_ws, t.tw_t.data(), 400 * sizeof(float));
+    std::memcpy(t.blob.data() + t.off_ws + t.off_w_ws, t.w_ws.data(), t.w_ws.size() * sizeof(float));
+    std::memcpy(t.blob.data() + t.off_ws + t.off_lo_ws, t.lo_ws.data(), kMaxMels * sizeof(int));
     return 0;
 }
 

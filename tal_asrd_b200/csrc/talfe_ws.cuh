@@ -7,10 +7,12 @@
 //   warps 10..19  CONSUMERS  exchange E -> FFT-20 -> power P -> mel projection -> log -> staged feature tile Y
 //                            -> cp.async.bulk store to global memory (640 bytes per frame pair)
 // (a 21st warp for the loader would cost 16 registers per thread: 6 warps on one scheduler's 16K-register file)
-// Each role keeps only its own constants in registers (producers: 20 window taps + 10 twiddles; consumers: 28
-// mel weights), so the steady state reads NO tables from shared memory.  The roles meet through mbarriers
-// (x_full / x_empty / e_full / e_empty, two buffers each); the consumers synchronise among themselves with one
-// named barrier (id 1); there is no CTA-wide barrier inside the tile loop.  Because the FP-heavy stage 1 and the
+// Producers keep their 20 window taps in registers; twiddles (5 LDS.128 per tile) and mel weights (7 LDS.128 per
+// tile) are re-read from shared memory, which measured faster than holding them in registers (B200, A/B in
+// profiles/r01_ab_v7_ws_vs_legacy.json: register pressure in the FFT costs more than the loads).  The roles meet
+// through mbarriers (x_full / x_empty / e_full / e_empty, two buffers each); the consumers synchronise among
+// themselves with ONE named barrier per tile (id 1; the power array is double-buffered, so "P free" needs no
+// barrier of its own); there is no CTA-wide barrier inside the tile loop.  Because the FP-heavy stage 1 and the
 // shared-memory-heavy stage 2 / mel stage now run in different warps, the SM's schedulers overlap them
 // instruction by instruction instead of phase by phase.
 //
@@ -99,7 +101,7 @@ __device__ __forceinline__ void ws_advance(const KernelArgs& a, int& row, int& t
 }
 
 // ------------------------------------------------------------------------------------------ producers
-template <typename XT, bool kTwReg, bool kWinReg>
+template <typename XT>
 __device__ __forceinline__ void ws_producer(const KernelArgs& a, unsigned char* smem, XT* s_x0, cf* s_e0, WsDesc* s_desc,
                                             unsigned long long* s_bar, const int tid, const int n_my) {
     unsigned long long* x_full = s_bar;            // [2]
@@ -112,17 +114,9 @@ __device__ __forceinline__ void ws_producer(const KernelArgs& a, unsigned char* 
     constexpr int kXBufBytes = kXFloats * (int)sizeof(float);           // both element sizes use the fp32-sized buffer
 
     float win[20];
-    if (kWinReg) load_window(j, reinterpret_cast<const float*>(smem), XLayout<XT>::kScale, win);
+    load_window(j, a.win_global, XLayout<XT>::kScale, win);            // once per CTA, straight from global memory
     const cf* s_tw = reinterpret_cast<const cf*>(smem + a.off_tw) + j * 10;
     cf tw[10];
-    if (kTwReg) {
-#pragma unroll
-        for (int h = 0; h < 5; ++h) {
-            const float4 tt = reinterpret_cast<const float4*>(s_tw)[h];
-            tw[2 * h] = make_float2(tt.x, tt.y);
-            tw[2 * h + 1] = make_float2(tt.z, tt.w);
-        }
-    }
     const XT* xg = s_x0 + kXG * g1 + j;
     cf* col0 = s_e0 + ws_e_base(g1) + j;
     // Loader duty, taken in turn by the producer warps (tile kk by warp kk % 10, one tile ahead of the FFTs): all 32
@@ -185,7 +179,6 @@ __device__ __forceinline__ void ws_producer(const KernelArgs& a, unsigned char* 
                 }
                 named_bar_sync(2, kWsRoleThreads);
             }
-            if (!kWinReg) load_window(j, reinterpret_cast<const float*>(smem), XLayout<XT>::kScale, win);
             stage1_ws_fft<XT>(reinterpret_cast<const XT*>(reinterpret_cast<const unsigned char*>(xg) + buf * kXBufBytes), win, z);
         }
         __syncwarp();
@@ -194,13 +187,11 @@ __device__ __forceinline__ void ws_producer(const KernelArgs& a, unsigned char* 
         // every tile, active or not: a producer never runs more than one phase ahead of the consumers
         if (k >= 2) mbar_wait_sleep(e_empty + buf, ((k - 2) >> 1) & 1); // consumers have loaded E[buf] of tile k-2
         if (active) {
-            if (!kTwReg) {
 #pragma unroll
-                for (int h = 0; h < 5; ++h) {
-                    const float4 tt = reinterpret_cast<const float4*>(s_tw)[h];
-                    tw[2 * h] = make_float2(tt.x, tt.y);
-                    tw[2 * h + 1] = make_float2(tt.z, tt.w);
-                }
+            for (int h = 0; h < 5; ++h) {
+                const float4 tt = reinterpret_cast<const float4*>(s_tw)[h];
+                tw[2 * h] = make_float2(tt.x, tt.y);
+                tw[2 * h + 1] = make_float2(tt.z, tt.w);
             }
             stage1_ws_store(z, tw, col0 + buf * kWsECf);
         }
@@ -250,8 +241,8 @@ __device__ __forceinline__ bool ws_store_tile(const KernelArgs& a, const WsDesc*
     return false;
 }
 
-template <typename XT, bool kMelReg>
-__device__ __forceinline__ void ws_consumer(const KernelArgs& a, unsigned char* smem, const cf* s_e0, cf* s_p, float* s_y0,
+template <typename XT>
+__device__ __forceinline__ void ws_consumer(const KernelArgs& a, unsigned char* smem, const cf* s_e0, cf* s_p0, float* s_y0,
                                             const WsDesc* s_desc, unsigned long long* s_bar, const int tid, const int n_my) {
     unsigned long long* e_full = s_bar + 4;
     unsigned long long* e_empty = s_bar + 6;
@@ -259,24 +250,19 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, unsigned char* 
     const int g = tid & (kWsGroups - 1), r = tid >> 4;                  // r: exchange row in stage 2, mel lane in the mel stage
     const bool special = r >= 18;                                       // warp 9: the packed rows, both frames
     const float4* s_w4 = reinterpret_cast<const float4*>(smem + a.off_w_ws) + r * (kRefWStride / 4);
-    float w[kRefWStride];
-    if (kMelReg) {
-#pragma unroll
-        for (int q = 0; q < kRefWStride / 4; ++q) {
-            const float4 t = s_w4[q];
-            w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
-        }
-    }
     int lo[kMelSlots];
 #pragma unroll
     for (int i = 0; i < kMelSlots; ++i) lo[i] = reinterpret_cast<const int*>(smem + a.off_lo_ws)[i * 20 + r];
     const cf* e_row0 = s_e0 + ws_e_base(g) + r * kWsERow;
-    float* pgf = reinterpret_cast<float*>(s_p) + 2 * g + (r & 1);
-    cf* pg = s_p + g;
     float* yb0 = s_y0 + ws_y_off(2 * g) + r;
     const int k1 = 1 + (r >> 1);
     double acc_s = 0.0, acc_q = 0.0;
 
+    // Per tile k (buffers b = k & 1):  E[b] -> registers -> FFT-20 -> power -> P[b]  |barrier|  store of tile k-1 from
+    // Y[b^1] issued, mel stage P[b] -> Y[b].  Hazards the single barrier covers: every warp arriving at barrier(k) has
+    // finished mel(k-1), so Y[b^1] is complete and P[b^1] is free for stage 2 of tile k+1; P[b] was last read by
+    // mel(k-2), which every warp finished before barrier(k-1); Y[b] was last read by the bulk store of tile k-2, whose
+    // issuing lanes wait for their reads before they arrive at barrier(k).
     for (int k = 0; k < n_my; ++k) {
         const int buf = k & 1;
         const WsDesc* dp = s_desc + (k & (kWsDescRing - 1));
@@ -288,33 +274,30 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, unsigned char* 
         __syncwarp();
         if (lane == 0) mbar_arrive(e_empty + buf);
         __syncwarp();
-        cf pw[10];
+        cf* s_p = s_p0 + buf * kWsPCf;
         if (active) {
-            if (!special) stage2_ws_power_normal(v, pw);
-            else stage2_ws_power_special(r == 18, v, pw);
+            cf pw[10];
+            if (!special) {
+                stage2_ws_power_normal(v, pw);
+                stage2_ws_store_normal(k1, pw, reinterpret_cast<float*>(s_p) + 2 * g + (r & 1));
+            } else {
+                stage2_ws_power_special(r == 18, v, pw);
+                stage2_ws_store_special(r == 18, pw, s_p + g);
+            }
         }
-        named_bar_sync(1, kWsRoleThreads);                              // A: mel(k-1) done everywhere: P is free, Y[(k-1)&1] is complete
-        bool issued = false;
-        if (k >= 1) issued = ws_store_tile(a, s_desc + ((k - 1) & (kWsDescRing - 1)), s_y0 + (buf ^ 1) * kWsYFloats, tid);
-        if (active) {
-            if (!special) stage2_ws_store_normal(k1, pw, pgf);
-            else stage2_ws_store_special(r == 18, pw, pg);
-        }
-        if (lane == 0) {                                                // this lane's store of tile k-2 must have finished reading Y[buf]
-            if (issued) bulk_wait_read<1>(); else bulk_wait_read<0>();
-        }
-        named_bar_sync(1, kWsRoleThreads);                              // B: P(k) complete
+        if (lane == 0) bulk_wait_read<0>();                             // this lane's store of tile k-2 has finished reading Y[buf]
+        named_bar_sync(1, kWsRoleThreads);                              // P[buf](k) and Y[buf^1](k-1) complete
+        if (k >= 1) ws_store_tile(a, s_desc + ((k - 1) & (kWsDescRing - 1)), s_y0 + (buf ^ 1) * kWsYFloats, tid);
         float sum = 0.f, sumsq = 0.f;
         if (active) {
-            if (!kMelReg) {
+            float w[kRefWStride];
 #pragma unroll
-                for (int q = 0; q < kRefWStride / 4; ++q) {
-                    const float4 t = s_w4[q];
-                    w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
-                }
+            for (int q = 0; q < kRefWStride / 4; ++q) {
+                const float4 t = s_w4[q];
+                w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
             }
             float y[2 * kMelSlots];
-            mel_log_ws(pg, w, lo, a.eps, y);
+            mel_log_ws(s_p + g, w, lo, a.eps, y);
             float* yb = yb0 + buf * kWsYFloats;
 #pragma unroll
             for (int i = 0; i < kMelSlots; ++i) {
@@ -364,7 +347,7 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, unsigned char* 
             acc_s += __shfl_xor_sync(0xffffffffu, acc_s, o);
             acc_q += __shfl_xor_sync(0xffffffffu, acc_q, o);
         }
-        double2* s_red = reinterpret_cast<double2*>(s_p);               // the power array is free after the last barrier
+        double2* s_red = reinterpret_cast<double2*>(s_p0);              // the power arrays are free after the last barrier
         if (lane == 0) s_red[warp] = make_double2(acc_s, acc_q);
         named_bar_sync(1, kWsRoleThreads);
         if (tid == 0) {
@@ -376,16 +359,14 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, unsigned char* 
     if (lane == 0) bulk_wait_all<0>();                                  // shared memory must outlive the copies that read it
 }
 
-// kCfg bit 0: twiddles in producer registers, bit 1: window taps in producer registers, bit 2: mel weights in consumer
-// registers (a cleared bit = re-read from the shared-memory tables once per tile)
-template <typename XT, int kCfg>
+template <typename XT>
 __global__ void __launch_bounds__(kWsThreads, 1) logmel_ws_kernel(const KernelArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
-    // carve-up: tables | x[2] | E[2] | P | Y[2] | descriptor ring | 8 mbarriers
+    // carve-up: tables (twiddles | mel weights | first bins) | x[2] | E[2] | P[2] | Y[2] | descriptor ring | 8 mbarriers
     XT* s_x0 = reinterpret_cast<XT*>(smem + a.blob_bytes);
     cf* s_e0 = reinterpret_cast<cf*>(smem + a.blob_bytes + 2 * kXFloats * sizeof(float));
-    cf* s_p = s_e0 + 2 * kWsECf;
-    float* s_y0 = reinterpret_cast<float*>(s_p + kWsPCf);
+    cf* s_p0 = s_e0 + 2 * kWsECf;
+    float* s_y0 = reinterpret_cast<float*>(s_p0 + 2 * kWsPCf);
     WsDesc* s_desc = reinterpret_cast<WsDesc*>(s_y0 + 2 * kWsYFloats);
     unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_desc + kWsDescRing);
 
@@ -400,18 +381,19 @@ __global__ void __launch_bounds__(kWsThreads, 1) logmel_ws_kernel(const KernelAr
         const int4* src = reinterpret_cast<const int4*>(a.blob);
         int4* dst = reinterpret_cast<int4*>(smem);
         for (int i = tid; i < a.blob_bytes / 16; i += kWsThreads) dst[i] = __ldg(src + i);
-        for (int i = tid; i < kWsPCf; i += kWsThreads) s_p[i] = make_float2(0.f, 0.f);   // incl. the never-written read padding
+        for (int i = tid; i < 2 * kWsPCf; i += kWsThreads) s_p0[i] = make_float2(0.f, 0.f);   // incl. the never-written read padding
     }
     __syncthreads();
     cudaGridDependencySynchronize();
     const int n_my = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles blockIdx.x, + gridDim.x, ...
-    if (tid < kWsRoleThreads) ws_producer<XT, (kCfg & 1) != 0, (kCfg & 2) != 0>(a, smem, s_x0, s_e0, s_desc, s_bar, tid, n_my);
-    else ws_consumer<XT, (kCfg & 4) != 0>(a, smem, s_e0, s_p, s_y0, s_desc, s_bar, tid - kWsRoleThreads, n_my);
+    if (tid < kWsRoleThreads) ws_producer<XT>(a, smem, s_x0, s_e0, s_desc, s_bar, tid, n_my);
+    else ws_consumer<XT>(a, smem, s_e0, s_p0, s_y0, s_desc, s_bar, tid - kWsRoleThreads, n_my);
 }
 
-constexpr size_t ws_smem_bytes(size_t blob_bytes) {
-    return blob_bytes + 2 * (size_t)kXFloats * sizeof(float) + 2 * (size_t)kWsECf * sizeof(cf) + (size_t)kWsPCf * sizeof(cf) +
+constexpr size_t ws_smem_bytes(size_t table_bytes) {
+    return table_bytes + 2 * (size_t)kXFloats * sizeof(float) + 2 * (size_t)kWsECf * sizeof(cf) + 2 * (size_t)kWsPCf * sizeof(cf) +
            2 * (size_t)kWsYFloats * sizeof(float) + kWsDescRing * sizeof(WsDesc) + 8 * sizeof(unsigned long long);
 }
+static_assert(ws_smem_bytes(4160) <= 232448, "the ws kernel's shared memory must fit one SM (227 KB)");
 
 }  // namespace

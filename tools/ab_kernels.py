@@ -55,14 +55,8 @@ def timeit(mod, norm):
 
 variants = {
     "legacy": {"TALFE_KERNEL": "legacy"},
-    "ws_cfg1": {"TALFE_KERNEL": "ws", "TALFE_WS_CFG": "1"},
-    "ws_cfg0": {"TALFE_KERNEL": "ws", "TALFE_WS_CFG": "0"},
-    "ws_cfg2": {"TALFE_KERNEL": "ws", "TALFE_WS_CFG": "2"},
-    "ws_cfg3": {"TALFE_KERNEL": "ws", "TALFE_WS_CFG": "3"},
-    "ws_cfg4": {"TALFE_KERNEL": "ws", "TALFE_WS_CFG": "4"},
-    "ws_cfg6": {"TALFE_KERNEL": "ws", "TALFE_WS_CFG": "6"},
-    "ws_cfg2_nopf": {"TALFE_KERNEL": "ws", "TALFE_WS_CFG": "2", "TALFE_L2_PREFETCH": "0"},
-    "ws_cfg1_nopf": {"TALFE_KERNEL": "ws", "TALFE_WS_CFG": "1", "TALFE_L2_PREFETCH": "0"},
+    "ws": {"TALFE_KERNEL": "ws"},
+    "ws_l2pf": {"TALFE_KERNEL": "ws", "TALFE_L2_PREFETCH": "1"},
 }
 res = {}
 ref = None
