@@ -414,7 +414,9 @@ TALFE_HD void stage1_ws_store(const cf (&z)[20], const cf (&tw)[10], cf* __restr
 // Stage 2 (consumer thread (g, r)): |FFT-20(row r)|^2 kept in registers until the power array is free.
 // Normal rows r < 18: pw[q] = (bin k1 + 20 q, bin (20 - k1) + 20 q) of frame r & 1, k1 = 1 + r / 2.
 TALFE_HD void stage2_ws_power_normal(cf (&v)[20], cf (&pw)[10]) {
+#if !(defined(TALFE_ABLATE) && (TALFE_ABLATE & 4))
     fft20(v);
+#endif
 #pragma unroll
     for (int q = 0; q < 10; ++q)
         pw[q] = make_float2(fmaf(v[q].x, v[q].x, v[q].y * v[q].y), fmaf(v[19 - q].x, v[19 - q].x, v[19 - q].y * v[19 - q].y));

@@ -179,7 +179,15 @@ __device__ __forceinline__ void ws_producer(const KernelArgs& a, unsigned char* 
                 }
                 named_bar_sync(2, kWsRoleThreads);
             }
+#if defined(TALFE_ABLATE) && (TALFE_ABLATE & 2)
+            {   // timing experiment only: window multiply without the FFT-20
+                const XT* p = reinterpret_cast<const XT*>(reinterpret_cast<const unsigned char*>(xg) + buf * kXBufBytes);
+#pragma unroll
+                for (int m = 0; m < 20; ++m) z[m] = make_float2(win[m] * x_to_float(p[20 * m]), win[m] * x_to_float(p[20 * m + 8]));
+            }
+#else
             stage1_ws_fft<XT>(reinterpret_cast<const XT*>(reinterpret_cast<const unsigned char*>(xg) + buf * kXBufBytes), win, z);
+#endif
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(x_empty + buf);                      // this warp no longer reads x[buf]
@@ -297,7 +305,12 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, unsigned char* 
                 w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
             }
             float y[2 * kMelSlots];
+#if defined(TALFE_ABLATE) && (TALFE_ABLATE & 1)
+#pragma unroll
+            for (int i = 0; i < 2 * kMelSlots; ++i) y[i] = w[i] + s_p[g + 16 * lo[i & 3]].x;   // timing experiment only: no mel stage
+#else
             mel_log_ws(s_p + g, w, lo, a.eps, y);
+#endif
             float* yb = yb0 + buf * kWsYFloats;
 #pragma unroll
             for (int i = 0; i < kMelSlots; ++i) {
