@@ -10,9 +10,9 @@ rank processes its own batch of the same shape (episode-sharded, weak scaling, n
 collective — the reference's mean is rank-local); value = frames of all ranks / max time.
 
 Prints ONE JSON line (rank 0).  Keys beyond the base contract:
-  roofline      dominant kernel (logmel_kernel) vs the measured HBM copy bandwidth
+  roofline      dominant kernel (logmel_ws_kernel) vs the measured HBM copy bandwidth
   cpu_baseline  the oracle's fp32 port of the reference op sequence, timed on this box's host cores
-  e2e           same metric through the public call with HOST (pinned) buffers, copies inside the timing
+  e2e           same metric through the public host-side API (HostPipeline) with pinned HOST buffers, copies inside the timing
 """
 from __future__ import annotations
 
@@ -226,7 +226,7 @@ def run_ours(args):
             traffic = json.load(fh).get("logmel_kernel_bytes_per_launch")
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "logmel_kernel", "achieved": achieved, "peak": peaks["hbm_gbs"],
+    roofline = {"bound": "hbm", "kernel": "logmel_ws_kernel", "achieved": achieved, "peak": peaks["hbm_gbs"],
                 "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_kind": peak_kind,
                 "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / ms_per_step,
                 "algorithmic_bytes_per_launch": FRAMES_PER_STEP * ALGO_BYTES_PER_FRAME}
