@@ -371,7 +371,8 @@ TALFE_HD void mel_log_ref(int c, const cf* __restrict__ p2, const float* __restr
 //   power      P[bin][g] (float2: frame a, frame b): stage 2 writes words 32 bin + 2 g + f (one wavefront per
 //              warp store), the mel stage reads 16 consecutive float2 per half-warp (one wavefront);
 //   features   Y[frame][80] staged per tile, row fr at float offset 80 fr + 4 (fr >> 1) (16-byte aligned rows
-//              for the bulk store to global memory; the pad leaves the scalar stores 2-way conflicted).
+//              for the bulk store to global memory; the pad leaves the scalar stores 2-way conflicted); for
+//              [.., 80, T] outputs the tile is staged transposed (ws_yt_off) and leaves by coalesced stores.
 constexpr int kWsGroups = 16;
 constexpr int kWsFrames = 2 * kWsGroups;
 constexpr int kWsERow = 20;
@@ -379,9 +380,13 @@ constexpr int kWsEGroup = 404;
 constexpr int kWsECf = kWsGroups * kWsEGroup + 4;                       // complex entries per exchange buffer
 constexpr int kWsPBins = 216;                                           // 200 bins + read padding of the widest slot
 constexpr int kWsPCf = kWsPBins * kWsGroups;
-constexpr int kWsYFloats = kWsFrames * kMaxMels + 4 * kWsGroups;
+constexpr int kWsYtStride = kWsFrames + 1;                              // transposed staging (layout [.., 80, T]): mel row stride 33
+constexpr int kWsYFloats = kMaxMels * kWsYtStride;                      // 2640 >= 32 * 80 + 4 * 16 (the [.., T, 80] staging)
 TALFE_HD constexpr int ws_e_base(int g) { return g * kWsEGroup + 2 * ((g >> 2) & 1); }
 TALFE_HD constexpr int ws_y_off(int fr) { return fr * kMaxMels + 4 * (fr >> 1); }
+// [.., 80, T] outputs stage the tile transposed, Yt[mel][frame] at mel * 33 + frame: the mel stage's stores (lanes = 16
+// pairs x 2 adjacent mels -> words 2 g + f + 33 r) and the store loop's reads (lane = frame) are both conflict-free
+TALFE_HD constexpr int ws_yt_off(int mel, int fr) { return mel * kWsYtStride + fr; }
 
 // Stage 1, first half: 28 waveform samples -> window -> complex FFT-20 of (frame a + i frame b), in registers.
 template <typename XT>

@@ -131,7 +131,11 @@ __device__ __forceinline__ void ws_producer(const KernelArgs& a, unsigned char* 
         const WsDesc d = ws_describe(a, row, tq, src_off);
         if (lane == 0) s_desc[kk & (kWsDescRing - 1)] = d;
         if (kk >= 2) mbar_wait_sleep(x_empty + lbuf, ((kk - 2) >> 1) & 1);               // tile kk-2 has left x[lbuf]
+#if defined(TALFE_ABLATE) && (TALFE_ABLATE & 16)
+        if (false) {                                                     // timing experiment only: no waveform fetch
+#else
         if (d.flags & kWsBulkX) {
+#endif
             const XT* src = reinterpret_cast<const XT*>(a.wave) + src_off;
             if (lane == 0) mbar_expect_tx(x_full + lbuf, kWsTileSamples * (int)sizeof(XT));   // release: publishes the descriptor too
             __syncwarp();
@@ -216,6 +220,9 @@ __device__ __forceinline__ void ws_producer(const KernelArgs& a, unsigned char* 
 // beyond a row's own length, [.., 80, T] layout, unaligned output) takes the cooperative element-wise path.
 // Returns whether bulk copies were issued.
 __device__ __forceinline__ bool ws_store_tile(const KernelArgs& a, const WsDesc* dp, const float* s_y, int tid) {
+#if defined(TALFE_ABLATE) && (TALFE_ABLATE & 8)
+    return false;                                                        // timing experiment only: features never leave shared memory
+#endif
     const int flags = dp->flags;
     if (flags & kWsBulkY) {
         if ((tid & 31) == 0) {
@@ -235,16 +242,32 @@ __device__ __forceinline__ bool ws_store_tile(const KernelArgs& a, const WsDesc*
     if (!active && a.out_offsets) return false;                         // packed output has no padding frames
     float* out_row = a.out + (a.out_offsets ? a.out_offsets[t.row] * kMaxMels : (long long)t.row * a.out_row_stride);
     const int nfr = min(kWsFrames, a.frame_end - t.t0);
+    if (a.out_layout == TALFE_LAYOUT_MT) {
+        // transposed staging Yt[mel][frame]: lane = frame, one mel row (<= 128 contiguous bytes of the output) per warp store
+        float* dst = out_row + (t.t0 - a.frame0);
+        if (nfr == kWsFrames) {
+            const int f = tid & 31;
+            const float keep = (active && t.t0 + f < t.t_end) ? 1.f : 0.f;
+#pragma unroll
+            for (int q = 0; q < kMaxMels * kWsFrames / kWsRoleThreads; ++q) {
+                const int m = (tid >> 5) + q * kWsRoleWarps;
+                dst[(long long)m * a.n_frames + f] = keep != 0.f ? s_y[ws_yt_off(m, f)] : 0.f;
+            }
+        } else {
+            for (int i = tid; i < nfr * kMaxMels; i += kWsRoleThreads) {
+                const int m = i / nfr, f = i - m * nfr;
+                const bool valid = active && t.t0 + f < t.t_end;
+                dst[(long long)m * a.n_frames + f] = valid ? s_y[ws_yt_off(m, f)] : 0.f;
+            }
+        }
+        return false;
+    }
     for (int i = tid; i < nfr * kMaxMels; i += kWsRoleThreads) {
-        int f, m;
-        if (a.out_layout == TALFE_LAYOUT_TM) { f = i / kMaxMels; m = i - f * kMaxMels; }
-        else { m = i / nfr; f = i - m * nfr; }                          // frame fastest: contiguous in [.., 80, T]
+        const int f = i / kMaxMels, m = i - f * kMaxMels;
         const int t_abs = t.t0 + f;
         const bool valid = active && t_abs < t.t_end;
         if (!valid && a.out_offsets) continue;
-        const float v = valid ? s_y[ws_y_off(f) + m] : 0.f;
-        if (a.out_layout == TALFE_LAYOUT_TM) out_row[(long long)(t_abs - a.frame0) * kMaxMels + m] = v;
-        else out_row[(long long)m * a.n_frames + (t_abs - a.frame0)] = v;
+        out_row[(long long)(t_abs - a.frame0) * kMaxMels + m] = valid ? s_y[ws_y_off(f) + m] : 0.f;
     }
     return false;
 }
@@ -262,7 +285,8 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, unsigned char* 
 #pragma unroll
     for (int i = 0; i < kMelSlots; ++i) lo[i] = reinterpret_cast<const int*>(smem + a.off_lo_ws)[i * 20 + r];
     const cf* e_row0 = s_e0 + ws_e_base(g) + r * kWsERow;
-    float* yb0 = s_y0 + ws_y_off(2 * g) + r;
+    const bool mt = a.out_layout == TALFE_LAYOUT_MT;
+    float* yb0 = s_y0 + (mt ? ws_yt_off(r, 2 * g) : ws_y_off(2 * g) + r);
     const int k1 = 1 + (r >> 1);
     double acc_s = 0.0, acc_q = 0.0;
 
@@ -312,10 +336,18 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, unsigned char* 
             mel_log_ws(s_p + g, w, lo, a.eps, y);
 #endif
             float* yb = yb0 + buf * kWsYFloats;
+            if (!mt) {
 #pragma unroll
-            for (int i = 0; i < kMelSlots; ++i) {
-                yb[20 * i] = y[2 * i];
-                yb[kMaxMels + 20 * i] = y[2 * i + 1];
+                for (int i = 0; i < kMelSlots; ++i) {
+                    yb[20 * i] = y[2 * i];
+                    yb[kMaxMels + 20 * i] = y[2 * i + 1];
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < kMelSlots; ++i) {
+                    yb[20 * i * kWsYtStride] = y[2 * i];
+                    yb[20 * i * kWsYtStride + 1] = y[2 * i + 1];
+                }
             }
             if (flags & kWsFull) {
 #pragma unroll
@@ -407,6 +439,7 @@ constexpr size_t ws_smem_bytes(size_t table_bytes) {
     return table_bytes + 2 * (size_t)kXFloats * sizeof(float) + 2 * (size_t)kWsECf * sizeof(cf) + 2 * (size_t)kWsPCf * sizeof(cf) +
            2 * (size_t)kWsYFloats * sizeof(float) + kWsDescRing * sizeof(WsDesc) + 8 * sizeof(unsigned long long);
 }
+static_assert(kMaxMels * kWsFrames % kWsRoleThreads == 0 && kWsYFloats >= kWsFrames * kMaxMels + 4 * kWsGroups, "Y staging");
 static_assert(ws_smem_bytes(4160) <= 232448, "the ws kernel's shared memory must fit one SM (227 KB)");
 
 }  // namespace
