@@ -1,0 +1,160 @@
+"""Model check of the hand-off protocols of logmel_ws_kernel (csrc/talfe_ws.cuh): 10 producer warps, 10 consumer
+warps, mbarriers with the phase-parity semantics of mbarrier.try_wait.parity (a wait on parity p passes iff the
+barrier's current phase has the other parity — adjacent phases only) and the consumers' named barrier.  Random warp
+interleavings must neither deadlock nor let a buffer be read before it is complete or overwritten before it was read.
+
+Two protocols are modelled:
+  * ``stores="consumers"`` — the shipped kernel: x_full / x_empty / e_full / e_empty, the feature tile is sent by the
+    consumers after their barrier (Y hazards are then covered by program order + that barrier);
+  * ``stores="producers"`` — an experiment measured on B200 and not adopted (87.1 us against 85.3 us):
+    producer warps send tile k at their iteration k + 3, with y_full / y_empty / c_done.  Its first version hung on
+    the GPU; this model reproduced the hang (a parity wait for the last tile passing two phases early in the drain)
+    and validated the fix before more GPU time was spent, which is why it stays here.
+(Host-side logic only; the arithmetic has its own tests.)"""
+import random
+
+import pytest
+
+W = 10  # warps per role
+
+
+class MBar:
+    def __init__(self, count):
+        self.count, self.pending, self.phase = count, count, 0
+
+    def arrive(self):
+        self.pending -= 1
+        assert self.pending >= 0
+        if self.pending == 0:
+            self.phase += 1
+            self.pending = self.count
+
+    def passed(self, parity):
+        return (self.phase & 1) != parity
+
+
+def run(n_my, seed, stores="producers"):
+    by_producers = stores == "producers"
+    rnd = random.Random(seed)
+    xf, xe = [MBar(1), MBar(1)], [MBar(W), MBar(W)]
+    ef, ee = [MBar(W), MBar(W)], [MBar(W), MBar(W)]
+    yf, ye = [MBar(W), MBar(W)], [MBar(1), MBar(1)]
+    cd = MBar(W)
+    bar = {"n": 0, "gen": 0}
+    x_tile, x_readers = [None, None], [0, 0]          # which tile sits in x[b]; producer warps still to read it
+    e_tile, e_written, e_read = [None, None], [0, 0], [0, 0]
+    mel_done, sent = {}, set()
+
+    def load_duty(kk):
+        if kk >= 2:
+            yield ("wait", xe[kk & 1], ((kk - 2) >> 1) & 1, f"x_empty({kk - 2})")
+        assert x_readers[kk & 1] == 0, "waveform tile overwritten while producers still read it"
+        x_tile[kk & 1], x_readers[kk & 1] = kk, W
+        xf[kk & 1].arrive()
+
+    def producer(w):
+        if w == 0:
+            yield from load_duty(0)
+        for k in range(n_my + 3):
+            turn = by_producers and k >= 3 and (k - 3) % W == w
+            ks = k - 3
+            if k >= n_my:                                   # drain
+                if turn:
+                    if ks == n_my - 1:
+                        yield ("wait", cd, 0, "c_done")
+                    else:
+                        yield ("wait", yf[ks & 1], (ks >> 1) & 1, f"y_full({ks}) drain")
+                    assert mel_done.get(ks, 0) == W, "tile sent before its mel stage finished"
+                    sent.add(ks)
+                    ye[ks & 1].arrive()
+                continue
+            if k + 1 < n_my and (k + 1) % W == w:
+                yield from load_duty(k + 1)
+            yield ("wait", xf[k & 1], (k >> 1) & 1, f"x_full({k})")
+            assert x_tile[k & 1] == k
+            yield ("work",)                                 # stage 1 reads x[k & 1]
+            x_readers[k & 1] -= 1
+            xe[k & 1].arrive()
+            if k >= 2:
+                yield ("wait", ee[k & 1], ((k - 2) >> 1) & 1, f"e_empty({k - 2})")
+            if turn:
+                yield ("wait", yf[ks & 1], (ks >> 1) & 1, f"y_full({ks})")
+                assert mel_done.get(ks, 0) == W, "tile sent before its mel stage finished"
+            if e_tile[k & 1] != k:
+                assert e_tile[k & 1] is None or e_read[k & 1] == W, "exchange buffer overwritten before it was read"
+                e_tile[k & 1], e_written[k & 1], e_read[k & 1] = k, 0, 0
+            yield ("work",)                                 # stage 1 writes E[k & 1]
+            e_written[k & 1] += 1
+            ef[k & 1].arrive()
+            if turn:
+                yield ("work",)                             # bulk copies read Y[ks & 1]
+                sent.add(ks)
+                ye[ks & 1].arrive()
+
+    def consumer(w):
+        for k in range(n_my):
+            yield ("wait", ef[k & 1], (k >> 1) & 1, f"e_full({k})")
+            assert e_tile[k & 1] == k and e_written[k & 1] == W, "exchange buffer read before it was complete"
+            e_read[k & 1] += 1
+            ee[k & 1].arrive()
+            yield ("work",)                                 # FFT, power -> P[k & 1]
+            gen = bar["gen"]
+            bar["n"] += 1
+            if bar["n"] == W:
+                bar["n"], bar["gen"] = 0, bar["gen"] + 1
+            yield ("bar", gen)
+            if not by_producers and k >= 1:
+                assert mel_done.get(k - 1, 0) == W, "tile sent before its mel stage finished"
+                sent.add(k - 1)                             # bulk stores of tile k-1, issued after the barrier
+            if by_producers and k >= 2:
+                yield ("wait", ye[k & 1], ((k - 2) >> 1) & 1, f"y_empty({k - 2})")
+            if k >= 2:
+                assert (k - 2) in sent, "feature tile overwritten before it was sent"
+            yield ("work",)                                 # mel stage -> Y[k & 1]
+            mel_done[k] = mel_done.get(k, 0) + 1
+            yf[k & 1].arrive()
+        cd.arrive()
+        if not by_producers and n_my >= 1:
+            gen = bar["gen"]
+            bar["n"] += 1
+            if bar["n"] == W:
+                bar["n"], bar["gen"] = 0, bar["gen"] + 1
+            yield ("bar", gen)
+            assert mel_done.get(n_my - 1, 0) == W
+            sent.add(n_my - 1)
+
+    state = {}
+    for name, gen in [(f"P{w}", producer(w)) for w in range(W)] + [(f"C{w}", consumer(w)) for w in range(W)]:
+        try:
+            state[name] = (gen, next(gen))
+        except StopIteration:
+            pass
+    while state:
+        ready = [n for n, (_, c) in state.items()
+                 if c[0] == "work" or (c[0] == "wait" and c[1].passed(c[2])) or (c[0] == "bar" and bar["gen"] > c[1])]
+        assert ready, f"deadlock (n_my={n_my}, seed={seed}): " + str({n: c[-1] for n, (_, c) in state.items()})
+        name = rnd.choice(ready)
+        gen = state[name][0]
+        try:
+            state[name] = (gen, next(gen))
+        except StopIteration:
+            del state[name]
+    assert sent == set(range(n_my))
+
+
+@pytest.mark.parametrize("stores", ["consumers", "producers"])
+@pytest.mark.parametrize("n_my", [1, 2, 3, 4, 5, 6, 7, 9, 10, 11, 13, 21, 41])
+def test_pipeline_protocol_is_live_and_safe(n_my, stores):
+    for seed in range(80):
+        run(n_my, seed, stores)
+
+
+def test_drain_needs_c_done():
+    """The bug this model caught: waiting for the LAST tile's y_full phase by parity alone lets the wait pass while the
+    barrier is still two phases behind.  Re-create that variant and check the model sees it."""
+    def broken(n_my, seed):
+        rnd = random.Random(seed)
+        yf = [MBar(W), MBar(W)]
+        # barrier still in phase 0 (tile 0 incomplete): a wait for tile 2 (parity 1) passes spuriously
+        return yf[0].passed((2 >> 1) & 1)
+    assert broken(3, 0)
