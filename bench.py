@@ -237,6 +237,8 @@ def run_ours(args):
     # host batches alternate.  Also reported: the same step as ONE blocking call (forward_host: copy-in, transform,
     # copy-out back to back) and the pipeline fed with int16 PCM (the on-disk format).
     from tal_asrd_b200 import HostPipeline
+    from tal_asrd_b200.hostpipe import bind_host_thread_to_gpu
+    numa_cpus = bind_host_thread_to_gpu(local_rank) if world > 1 else None   # one rank per GPU: pin next to its own GPU
     host_in = [torch.empty(BATCH, N_SAMPLES, dtype=torch.float32).pin_memory() for _ in range(2)]
     for i in range(2):
         host_in[i].copy_(waves[i].cpu())
@@ -285,6 +287,7 @@ def run_ours(args):
            "wall_ms_per_step": e2e_wall_ms,
            "h2d_bytes_per_step": host_in[0].numel() * 4, "d2h_bytes_per_step": host_out[0].numel() * 4, "steps": e2e_steps,
            "api": "HostPipeline.submit per step (3 streams, 2 device slots), drain at the end; fp32 waveforms in, fp32 features out",
+           "host_cpus_rank0": (f"{numa_cpus[0]}-{numa_cpus[-1]} ({len(numa_cpus)} CPUs local to the GPU)" if numa_cpus else "unbound"),
            "blocking_call": {"value": world * FRAMES_PER_STEP / (blocking_ms * 1e-3), "ms_per_step": blocking_ms,
                              "api": "LogMelSpec.forward_host (copy-in, transform, copy-out back to back)"},
            "pcm16_input": {"value": world * FRAMES_PER_STEP / (pcm_ms * 1e-3), "ms_per_step": pcm_ms,

@@ -11,11 +11,33 @@ sum.  Each batch is still exactly ``LogMelSpec.forward`` on that batch (its own 
 """
 from __future__ import annotations
 
-from typing import Iterable, Optional, Tuple
+import os
+from typing import Iterable, List, Optional, Tuple
 
 import torch
 
 from .frontend import LogMelSpec, num_frames
+
+
+def bind_host_thread_to_gpu(device_index: int) -> Optional[List[int]]:
+    """Restricts the calling process to the CPUs NVML reports as local to GPU ``device_index`` (its NUMA node), so that
+    pinned buffers allocated afterwards land in memory next to that GPU's PCIe root.  On multi-socket hosts with one
+    rank per GPU this keeps H2D/D2H traffic off the inter-socket link.  Returns the CPU list, or None when NVML or
+    the affinity call is unavailable (then nothing is changed)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        words = (max(os.cpu_count() or 1, 1) + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cpus = {64 * i + b for i, w in enumerate(mask) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:
+        return None
 
 
 class HostPipeline:
