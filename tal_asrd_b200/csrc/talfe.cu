@@ -40,7 +40,7 @@ constexpr int kXFloats = (kTileSamples + 24 * ((kTileSamples - 1) / kXBlock) + 3
 constexpr int kNormalThreads = 18 * kGroupsPerCta;          // 288 = 9 full warps; warp 9 = packed rows 0/10
 constexpr int kMaxSamples = 0x7fff0000;                     // sample / frame indices are 32-bit on the device
 constexpr int kMaxBands = 16;                               // SpecAugment bands per row and axis
-constexpr int kColChunk = 2048;                             // frames per block in the per-mel statistics pass
+constexpr int kColChunk = 256;                              // frames per block in the per-mel statistics pass
 static_assert(kNormalThreads % 32 == 0, "special rows must fill whole warps");
 
 thread_local int g_last_cuda_error = 0;
@@ -420,15 +420,39 @@ __global__ void __launch_bounds__(320) colstats_kernel(const float* __restrict__
                                                        long long n_frames, int n_mels, const long long* __restrict__ lens,
                                                        long long total_len, long long frame0, double* __restrict__ colpart,
                                                        const long long* __restrict__ out_offsets) {
-    __shared__ double s_sum[4][kMaxMels], s_sq[4][kMaxMels];
+    __shared__ double s_sum[16][kMaxMels], s_sq[16][kMaxMels];
     const long long row = blockIdx.y, chunk = blockIdx.x;
     const long long L = lens ? lens[row] : total_len;
     const long long T_row = L > kHalf ? 1 + L / kHop : 0;
     long long valid = min(frame0 + n_frames, T_row) - frame0;
     if (valid < 0) valid = 0;
-    const int m = threadIdx.x % kMaxMels, lane_f = threadIdx.x / kMaxMels;       // 80 mels x 4 frame lanes
     const long long f_lo = chunk * kColChunk, f_hi = min(f_lo + kColChunk, valid);
     const float* base = feats + (out_offsets ? out_offsets[row] * n_mels : row * out_row_stride);
+    double* o = colpart + (row * gridDim.x + chunk) * 2 * kMaxMels;
+    if (out_layout == TALFE_LAYOUT_TM && n_mels == kMaxMels && (reinterpret_cast<unsigned long long>(base) & 15ull) == 0) {
+        // 20 float4 lanes x 16 frame lanes: every frame row is read as 320 contiguous bytes; fixed summation order
+        const int q = threadIdx.x % 20, fl = threadIdx.x / 20;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
+        const float4* b4 = reinterpret_cast<const float4*>(base) + q;
+#pragma unroll 4
+        for (long long f = f_lo + fl; f < f_hi; f += 16) {
+            const float4 v = b4[f * 20];
+            a0 += v.x; a1 += v.y; a2 += v.z; a3 += v.w;
+            b0 += (double)v.x * v.x; b1 += (double)v.y * v.y; b2 += (double)v.z * v.z; b3 += (double)v.w * v.w;
+        }
+        s_sum[fl][4 * q] = a0; s_sum[fl][4 * q + 1] = a1; s_sum[fl][4 * q + 2] = a2; s_sum[fl][4 * q + 3] = a3;
+        s_sq[fl][4 * q] = b0; s_sq[fl][4 * q + 1] = b1; s_sq[fl][4 * q + 2] = b2; s_sq[fl][4 * q + 3] = b3;
+        __syncthreads();
+        if (threadIdx.x < kMaxMels) {
+            const int m = threadIdx.x;
+            double a = 0.0, b = 0.0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { a += s_sum[i][m]; b += s_sq[i][m]; }
+            o[m] = a; o[kMaxMels + m] = b;
+        }
+        return;
+    }
+    const int m = threadIdx.x % kMaxMels, lane_f = threadIdx.x / kMaxMels;       // 80 mels x 4 frame lanes
     double a = 0.0, b = 0.0;
     if (m < n_mels)
         for (long long f = f_lo + lane_f; f < f_hi; f += 4) {
@@ -438,7 +462,6 @@ __global__ void __launch_bounds__(320) colstats_kernel(const float* __restrict__
     s_sum[lane_f][m] = a; s_sq[lane_f][m] = b;
     __syncthreads();
     if (lane_f == 0 && m < n_mels) {
-        double* o = colpart + (row * gridDim.x + chunk) * 2 * kMaxMels;
         o[m] = (s_sum[0][m] + s_sum[1][m]) + (s_sum[2][m] + s_sum[3][m]);
         o[kMaxMels + m] = (s_sq[0][m] + s_sq[1][m]) + (s_sq[2][m] + s_sq[3][m]);
     }
