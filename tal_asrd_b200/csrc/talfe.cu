@@ -385,18 +385,19 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const KernelArgs a)
 // ------------------------------------------------------------------------------------------ K2
 // One block per statistics block (1 for batch-wide, B for per-row).  Fixed-order tree in shared
 // memory: the result does not depend on scheduling.
-__global__ void __launch_bounds__(256) reduce_partials_kernel(const double2* __restrict__ partials, long long slots_per_block,
+constexpr int kReduceThreads = 1024;
+__global__ void __launch_bounds__(kReduceThreads) reduce_partials_kernel(const double2* __restrict__ partials, long long slots_per_block,
                                                               const long long* __restrict__ lens, long long total_len,
                                                               long long frame0, long long n_frames, long long rows_per_block,
                                                               int n_mels, int accumulate, double* __restrict__ stats) {
-    __shared__ double s_a[256], s_b[256];
+    __shared__ double s_a[kReduceThreads], s_b[kReduceThreads];
     const long long blk = blockIdx.x;
     const double2* p = partials + blk * slots_per_block;
     double a = 0.0, b = 0.0;
-    for (long long i = threadIdx.x; i < slots_per_block; i += 256) { double2 v = p[i]; a += v.x; b += v.y; }
+    for (long long i = threadIdx.x; i < slots_per_block; i += kReduceThreads) { double2 v = p[i]; a += v.x; b += v.y; }
     s_a[threadIdx.x] = a; s_b[threadIdx.x] = b;
     __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
+    for (int o = kReduceThreads / 2; o > 0; o >>= 1) {
         if (threadIdx.x < o) { s_a[threadIdx.x] += s_a[threadIdx.x + o]; s_b[threadIdx.x] += s_b[threadIdx.x + o]; }
         __syncthreads();
     }
@@ -467,16 +468,25 @@ __global__ void __launch_bounds__(320) colstats_kernel(const float* __restrict__
     }
 }
 
-__global__ void colstats_finish_kernel(const double* __restrict__ colpart, int chunks, int n_mels, int accumulate,
-                                       double* __restrict__ stats) {
+constexpr int kFinishLanes = 12;
+__global__ void __launch_bounds__(kFinishLanes * kMaxMels) colstats_finish_kernel(const double* __restrict__ colpart, int chunks, int n_mels,
+                                                                                   int accumulate, double* __restrict__ stats) {
+    // 80 mels x 12 chunk lanes (an hour-long row has 1 407 chunks): lane l sums chunks l, l + 12, ...; fixed order throughout
+    __shared__ double s_a[kFinishLanes][kMaxMels], s_b[kFinishLanes][kMaxMels];
     const long long row = blockIdx.x;
-    const int m = threadIdx.x;
-    if (m >= n_mels) return;
+    const int m = threadIdx.x % kMaxMels, l = threadIdx.x / kMaxMels;
     double a = 0.0, b = 0.0;
-    for (int ch = 0; ch < chunks; ++ch) {
-        const double* o = colpart + (row * chunks + ch) * 2 * kMaxMels;
-        a += o[m]; b += o[kMaxMels + m];
-    }
+    if (m < n_mels)
+        for (int ch = l; ch < chunks; ch += kFinishLanes) {
+            const double* o = colpart + (row * chunks + ch) * 2 * kMaxMels;
+            a += o[m]; b += o[kMaxMels + m];
+        }
+    s_a[l][m] = a; s_b[l][m] = b;
+    __syncthreads();
+    if (l != 0 || m >= n_mels) return;
+    a = 0.0; b = 0.0;
+#pragma unroll
+    for (int i = 0; i < kFinishLanes; ++i) { a += s_a[i][m]; b += s_b[i][m]; }
     double* s = stats + row * TALFE_STATS_DOUBLES(n_mels);
     if (accumulate) { s[3 + m] += a; s[3 + n_mels + m] += b; }
     else { s[3 + m] = a; s[3 + n_mels + m] = b; }
@@ -879,7 +889,7 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
     const long long blocks = per_row ? job->batch : 1;
     const long long rows_per_block = per_row ? 1 : job->batch;
     const long long slots_per_block = per_row ? w.tiles_per_row * kWarps : grid;
-    reduce_partials_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a.partials, slots_per_block, a.lens, a.total_len,
+    reduce_partials_kernel<<<(unsigned)blocks, kReduceThreads, 0, stream>>>(a.partials, slots_per_block, a.lens, a.total_len,
                                                                   a.frame0, a.n_frames, rows_per_block, M, accumulate, stats);
     TALFE_CUDA(cudaGetLastError());
     if (job->norm == TALFE_NORM_ROW_MEL_MEAN || job->norm == TALFE_NORM_ROW_MEL_MEANVAR) {
@@ -887,7 +897,7 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
         colstats_kernel<<<dim3((unsigned)w.chunks, (unsigned)job->batch), 320, 0, stream>>>(job->out, ors, job->out_layout, job->n_frames, M,
                                                                                            a.lens, a.total_len, a.frame0, colpart, a.out_offsets);
         TALFE_CUDA(cudaGetLastError());
-        colstats_finish_kernel<<<(unsigned)job->batch, 96, 0, stream>>>(colpart, w.chunks, M, accumulate, stats);
+        colstats_finish_kernel<<<(unsigned)job->batch, kFinishLanes * kMaxMels, 0, stream>>>(colpart, w.chunks, M, accumulate, stats);
         TALFE_CUDA(cudaGetLastError());
     }
     if (job->norm == TALFE_NORM_NONE || job->defer_normalise) return TALFE_OK;
