@@ -66,20 +66,27 @@ def pass2(total):
 
 for _ in range(2):                      # warm-up of both passes on a few episodes
     mod.features(pool[0], norm="row_mel_var", stats=blocks[:1], defer_normalise=True, out=out[0])
-barrier()
-ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-ev[0].record()
-total = pass1()
-ev[1].record()
-total.all_reduce()
-ev[2].record()
-pass2(total)
-ev[3].record()
-barrier()
-t = torch.tensor([ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3])], dtype=torch.float64, device=dev)
+REPS = 3                                # the whole two-pass job, repeated; the fastest repetition (max over ranks) is reported:
+best = None                             # at 40 ms per pass one descheduled host thread on one rank is visible
+for rep in range(REPS):
+    barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    ev[0].record()
+    total = pass1()
+    ev[1].record()
+    total.all_reduce()
+    ev[2].record()
+    pass2(total)
+    ev[3].record()
+    barrier()
+    t = torch.tensor([ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3])], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if best is None or float(t.sum()) < float(best.sum()):
+        best = t
+t = best
 n_local = torch.tensor([len(mine)], dtype=torch.float64, device=dev)
 if world > 1:
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dist.all_reduce(n_local, op=dist.ReduceOp.SUM)
 if rank == 0:
     frames = float(n_local.item()) * T
@@ -93,6 +100,6 @@ if rank == 0:
         "both_passes_frames_per_s": frames / ((t1 + tr + t2) * 1e-3),
         "both_passes_x_realtime": hours * 3600 / ((t1 + tr + t2) * 1e-3),
         "global_mean": total.mean, "global_count": total.count,
-        "pool": f"{POOL} distinct resident episodes per rank visited in turn (inputs 1.8 GB >> L2)"}))
+        "repetitions": REPS, "pool": f"{POOL} distinct resident episodes per rank visited in turn (inputs 1.8 GB >> L2)"}))
 if world > 1:
     dist.destroy_process_group()
