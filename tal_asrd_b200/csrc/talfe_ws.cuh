@@ -45,6 +45,9 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* gmem_src, unsigned 
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
 }
 
+#ifndef TALFE_WS_WAIT_HINT_NS
+#define TALFE_WS_WAIT_HINT_NS 1000000
+#endif
 // try_wait with a suspend-time hint: the waiting warp sleeps in hardware instead of spinning on issue slots
 __device__ __forceinline__ void mbar_wait_sleep(unsigned long long* bar, unsigned parity) {
     unsigned done = 0;
@@ -52,7 +55,7 @@ __device__ __forceinline__ void mbar_wait_sleep(unsigned long long* bar, unsigne
         asm volatile(
             "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u)
+            : "r"(smem_u32(bar)), "r"(parity), "r"((unsigned)TALFE_WS_WAIT_HINT_NS)
             : "memory");
     }
 }
