@@ -9,7 +9,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libtalfe.so")
 SOURCES = ["talfe.cu"]
-HEADERS = ["talfe_core.cuh", "talfe_tables.h", os.path.join("..", "..", "include", "talfe.h")]
+HEADERS = ["talfe_core.cuh", "talfe_ws.cuh", "talfe_tables.h", os.path.join("..", "..", "include", "talfe.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
               "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo"]
 

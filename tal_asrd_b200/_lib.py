@@ -45,8 +45,10 @@ def load() -> ctypes.CDLL:
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = _build.LIB_PATH
+    path = os.environ.get("TALFE_LIB") or _build.LIB_PATH              # TALFE_LIB: an experiment build (tools/_abl/)
     if not os.path.isfile(path):
+        if os.environ.get("TALFE_LIB"):
+            raise FileNotFoundError(f"TALFE_LIB={path} does not exist")
         # build on first use where a toolchain exists (the GPU box receives the prebuilt .so)
         path = _build.build()
     lib = ctypes.CDLL(path)

@@ -16,7 +16,9 @@
 //                        symmetry, the real-input FFT-20 of both frames: A_a[k1], A_b[k1],
 //                        k1 = 0..10.  Twiddle by W400^(j k1).  Exchange rows for stage 2:
 //                          row 2(k1-1)   : A_a[k1] W^(j k1)   k1 = 1..9       (frame a)
-//                          row 2(k1-1)+1 : A_b[k1] W^(j k1)   k1 = 1..9       (frame b)
+//                          row 2(k1-1)+1 : i A_b[k1] W^(j k1) k1 = 1..9       (frame b; the unit factor i drops out of
+//                                                                              the power spectrum and makes the packed form
+//                                                                              of the ws kernel's stage 1 one instruction shorter)
 //                          row 18        : A_a[0] + i A_b[0]                  (both real -> packed)
 //                          row 19        : (A_a[10] + i A_b[10]) W^(10 j)     (both real -> packed)
 //   stage 2 (thread = row): complex FFT-20 over j.  Rows 0..17 give 20 spectrum bins of one frame
@@ -117,12 +119,53 @@ TALFE_HD cf cmul_s(float s, cf t) { return make_float2(s * t.x, s * t.y); }
 // to the next; fixing it keeps every variant of the kernel (and the host emulator) bit-identical
 TALFE_HD cf cmul(cf a, cf b) { return make_float2(fmaf(a.x, b.x, -(a.y * b.y)), fmaf(a.x, b.y, a.y * b.x)); }
 
+// a - i b and a + i b.  Scalar form: two FADDs on mixed halves.  Packed form (kPacked, device only): ONE FFMA2 whose
+// first operand is b with its halves swapped and a per-lane sign (SASS: Rb.F32x2.LO_HI.NP times the constant pair
+// (1, 1)); fma(y, +-1, x) rounds exactly like x +- y, so both forms are bit-identical (tests: ws vs legacy kernel).
+template <bool kPacked> TALFE_HD cf csub_i(cf a, cf b) {
+#ifdef __CUDA_ARCH__
+    if (kPacked) {
+        cf r;
+        asm("{ .reg .b64 ra, rb, rc, rr; mov.b64 ra, {%2,%3}; mov.b64 rb, {%5,%4}; mov.b64 rc, {%6,%7}; fma.rn.f32x2 rr, rb, rc, ra; mov.b64 {%0,%1}, rr; }"
+            : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(1.0f), "f"(-1.0f));
+        return r;
+    }
+#endif
+    return make_float2(a.x + b.y, a.y - b.x);
+}
+template <bool kPacked> TALFE_HD cf cadd_i(cf a, cf b) {
+#ifdef __CUDA_ARCH__
+    if (kPacked) {
+        cf r;
+        asm("{ .reg .b64 ra, rb, rc, rr; mov.b64 ra, {%2,%3}; mov.b64 rb, {%5,%4}; mov.b64 rc, {%6,%7}; fma.rn.f32x2 rr, rb, rc, ra; mov.b64 {%0,%1}, rr; }"
+            : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(-1.0f), "f"(1.0f));
+        return r;
+    }
+#endif
+    return make_float2(a.x - b.y, a.y + b.x);
+}
+// i w = (-w.y, w.x): one packed multiply by the constant pair (1, 1) with swap + per-lane sign on the device
+TALFE_HD cf times_i(cf w) {
+#ifdef __CUDA_ARCH__
+    cf r;
+    asm("{ .reg .b64 rb, rc, rr; mov.b64 rb, {%3,%2}; mov.b64 rc, {%4,%5}; mul.rn.f32x2 rr, rb, rc; mov.b64 {%0,%1}, rr; }"
+        : "=f"(r.x), "=f"(r.y) : "f"(w.x), "f"(w.y), "f"(-1.0f), "f"(1.0f));
+    return r;
+#else
+    return make_float2(-w.y, w.x);
+#endif
+}
+// s1 * u + s2 * v for real scalars s1, s2 (v's product is rounded first): FMUL2 + FFMA2 with scalar-broadcast operands.
+// With u = w, v = i w this is the complex product (s1 + i s2) w, bit-identical to cmul((s1, s2), w).
+TALFE_HD cf cfma_ss(float s1, cf u, float s2, cf v) { return cfma_s(s1, u, cmul_s(s2, v)); }
+
 // 5-point DFT constants (forward transform, W5 = exp(-2 pi i / 5))
 #define TALFE_C1 0.30901699437494742f    /* cos(2 pi / 5) */
 #define TALFE_C2 (-0.80901699437494742f) /* cos(4 pi / 5) */
 #define TALFE_S1 0.95105651629515357f    /* sin(2 pi / 5) */
 #define TALFE_S2 0.58778525229247313f    /* sin(4 pi / 5) */
 
+template <bool kPacked = false>
 TALFE_HD void dft5(cf a0, cf a1, cf a2, cf a3, cf a4, cf& y0, cf& y1, cf& y2, cf& y3, cf& y4) {
     const cf t1 = cadd(a1, a4), t2 = cadd(a2, a3), t3 = csub(a1, a4), t4 = csub(a2, a3);
     y0 = cadd(cadd(a0, t1), t2);
@@ -131,14 +174,16 @@ TALFE_HD void dft5(cf a0, cf a1, cf a2, cf a3, cf a4, cf& y0, cf& y1, cf& y2, cf
     const cf s1 = cfma_s(TALFE_S2, t4, cmul_s(TALFE_S1, t3));
     const cf s2 = cfma_s(-TALFE_S1, t4, cmul_s(TALFE_S2, t3));
     // y1 = m1 - i s1, y4 = m1 + i s1, y2 = m2 - i s2, y3 = m2 + i s2   ( -i (x + i y) = y - i x )
-    y1 = make_float2(m1.x + s1.y, m1.y - s1.x);
-    y4 = make_float2(m1.x - s1.y, m1.y + s1.x);
-    y2 = make_float2(m2.x + s2.y, m2.y - s2.x);
-    y3 = make_float2(m2.x - s2.y, m2.y + s2.x);
+    y1 = csub_i<kPacked>(m1, s1);
+    y4 = cadd_i<kPacked>(m1, s1);
+    y2 = csub_i<kPacked>(m2, s2);
+    y3 = cadd_i<kPacked>(m2, s2);
 }
 
 // In-place 20-point complex DFT, natural order in and out (all indices compile-time).
 // Good-Thomas: n = (5 n1 + 4 n2) mod 20, k = (5 k1 + 16 k2) mod 20, n1,k1 in 0..3, n2,k2 in 0..4.
+// kPacked selects the single-instruction forms of the multiplications by -+i (same bits, fewer issue slots).
+template <bool kPacked = false>
 TALFE_HD void fft20(cf (&v)[20]) {
     cf t[4][5];
 #pragma unroll
@@ -147,13 +192,13 @@ TALFE_HD void fft20(cf (&v)[20]) {
         cf s02 = cadd(a0, a2), d02 = csub(a0, a2), s13 = cadd(a1, a3), d13 = csub(a1, a3);
         t[0][n2] = cadd(s02, s13);
         t[2][n2] = csub(s02, s13);
-        t[1][n2] = make_float2(d02.x + d13.y, d02.y - d13.x);   // d02 - i d13
-        t[3][n2] = make_float2(d02.x - d13.y, d02.y + d13.x);   // d02 + i d13
+        t[1][n2] = csub_i<kPacked>(d02, d13);                   // d02 - i d13
+        t[3][n2] = cadd_i<kPacked>(d02, d13);                   // d02 + i d13
     }
 #pragma unroll
     for (int k1 = 0; k1 < 4; ++k1) {
         cf y0, y1, y2, y3, y4;
-        dft5(t[k1][0], t[k1][1], t[k1][2], t[k1][3], t[k1][4], y0, y1, y2, y3, y4);
+        dft5<kPacked>(t[k1][0], t[k1][1], t[k1][2], t[k1][3], t[k1][4], y0, y1, y2, y3, y4);
         v[(5 * k1) % 20] = y0;
         v[(5 * k1 + 16) % 20] = y1;
         v[(5 * k1 + 32) % 20] = y2;
@@ -219,7 +264,8 @@ TALFE_HD void stage1(int j, const XT* __restrict__ xg, const float (&win)[20],
                 const cf aa = make_float2(sm.x, df.y);                  // A_a[k1] = C[k1] + conj C[20-k1]
                 const cf ab = make_float2(sm.y, -df.x);                 // A_b[k1] = (C[k1] - conj C[20-k1]) / i
                 col[row_slot(2 * (k1 - 1)) * kERow] = cmul(aa, w);
-                col[row_slot(2 * (k1 - 1) + 1) * kERow] = cmul(ab, w);
+                const cf cb = cmul(ab, w);
+                col[row_slot(2 * (k1 - 1) + 1) * kERow] = make_float2(-cb.y, cb.x);   // i A_b W: see the row table above
             } else {
                 col[row_slot(19) * kERow] = cmul(z[10], w);                       // row 19: (A_a[10] + i A_b[10]) W^(10 j) / 2
             }
@@ -298,6 +344,17 @@ TALFE_HD float fast_log(float x) {
     return r * 0.693147180559945309f;
 #else
     return logf(x);
+#endif
+}
+// the same for the two frames of a pair: two MUFU.LG2 and ONE packed multiply (bit-identical to two fast_log calls)
+TALFE_HD cf fast_log2x(cf x) {
+#ifdef __CUDA_ARCH__
+    float ra, rb;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(ra) : "f"(x.x));
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(rb) : "f"(x.y));
+    return cmul_s(0.693147180559945309f, make_float2(ra, rb));
+#else
+    return make_float2(logf(x.x), logf(x.y));
 #endif
 }
 
@@ -396,31 +453,34 @@ TALFE_HD void stage1_ws_fft(const XT* __restrict__ p /* xg + j */, const float (
     for (int m = 0; m < 20; ++m) {
         const int ia = 20 * m + (20 * m >= kXBlock ? kSkew : 0);
         const int ib = 20 * m + kHop + (20 * m + kHop >= kXBlock ? kSkew : 0);
-        z[m] = make_float2(win[m] * x_to_float(p[ia]), win[m] * x_to_float(p[ib]));
+        z[m] = cmul_s(win[m], make_float2(x_to_float(p[ia]), x_to_float(p[ib])));     // one FMUL2 (scalar-broadcast operand)
     }
-    fft20(z);
+    fft20<true>(z);
 }
 
 // Stage 1, second half: untangle the two real-input transforms, twiddle by tw[k1-1] = W400^(j k1), write
 // column j of the pair's 20 exchange rows (same row meaning as the legacy stage1; rows in natural order).
 TALFE_HD void stage1_ws_store(const cf (&z)[20], const cf (&tw)[10], cf* __restrict__ col /* E + ws_e_base(g1) + j */) {
+    // With A_a = (sm.x, df.y), A_b = (sm.y, -df.x), w = tw[k1-1] and iw = i w:
+    //   A_a w   = sm.x w  + df.y iw        i A_b w = sm.y iw + df.x w
+    // each an FMUL2 + FFMA2 with scalar-broadcast operands (7 instructions per k1 against 10 for two scalar complex
+    // products), with the same fused/unfused roundings as cmul(): bit-identical to the legacy stage1().
     col[18 * kWsERow] = z[0];
 #pragma unroll
     for (int k1 = 1; k1 < 10; ++k1) {
         const cf sm = cadd(z[k1], z[20 - k1]), df = csub(z[k1], z[20 - k1]);
-        const cf aa = make_float2(sm.x, df.y);
-        const cf ab = make_float2(sm.y, -df.x);
-        col[(2 * (k1 - 1)) * kWsERow] = cmul(aa, tw[k1 - 1]);
-        col[(2 * (k1 - 1) + 1) * kWsERow] = cmul(ab, tw[k1 - 1]);
+        const cf w = tw[k1 - 1], iw = times_i(w);
+        col[(2 * (k1 - 1)) * kWsERow] = cfma_ss(sm.x, w, df.y, iw);
+        col[(2 * (k1 - 1) + 1) * kWsERow] = cfma_ss(sm.y, iw, df.x, w);
     }
-    col[19 * kWsERow] = cmul(z[10], tw[9]);
+    col[19 * kWsERow] = cfma_ss(z[10].x, tw[9], z[10].y, times_i(tw[9]));
 }
 
 // Stage 2 (consumer thread (g, r)): |FFT-20(row r)|^2 kept in registers until the power array is free.
 // Normal rows r < 18: pw[q] = (bin k1 + 20 q, bin (20 - k1) + 20 q) of frame r & 1, k1 = 1 + r / 2.
 TALFE_HD void stage2_ws_power_normal(cf (&v)[20], cf (&pw)[10]) {
 #if !(defined(TALFE_ABLATE) && (TALFE_ABLATE & 4))
-    fft20(v);
+    fft20<true>(v);
 #endif
 #pragma unroll
     for (int q = 0; q < 10; ++q)
@@ -437,7 +497,7 @@ TALFE_HD void stage2_ws_store_normal(int k1, const cf (&pw)[10], float* __restri
 }
 // Packed rows: r == 18 (zero = true) -> bins 20 (q + 1); r == 19 -> bins 10 + 20 q; both frames per entry.
 TALFE_HD void stage2_ws_power_special(bool zero, cf (&v)[20], cf (&pw)[10]) {
-    fft20(v);
+    fft20<true>(v);
 #pragma unroll
     for (int q = 0; q < 10; ++q) {
         const cf p = zero ? v[q + 1] : v[q];
@@ -456,15 +516,15 @@ TALFE_HD void stage2_ws_store_special(bool zero, const cf (&pw)[10], cf* __restr
 // Mel stage (consumer thread (g, c)): mels c, 20 + c, 40 + c, 60 + c; weights in registers.
 template <int W, int OFF>
 TALFE_HD void mel_slot_ws(const cf* __restrict__ p /* P + g + 16 lo */, const float (&w)[kRefWStride], float eps, float& ya, float& yb) {
-    float acc_a = 0.f, acc_b = 0.f;
+    // both frames of the pair ride in one packed accumulator: FFMA2 with the weight as scalar-broadcast operand
+    // (the same two IEEE fmas as the scalar form, half the issue slots)
+    cf acc = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int r = 0; r < W; ++r) {
-        const cf pw = p[kWsGroups * r];
-        acc_a = fmaf(w[OFF + r], pw.x, acc_a);
-        acc_b = fmaf(w[OFF + r], pw.y, acc_b);
-    }
-    ya = fast_log(acc_a + eps);
-    yb = fast_log(acc_b + eps);
+    for (int r = 0; r < W; ++r) acc = cfma_s(w[OFF + r], p[kWsGroups * r], acc);
+    const cf le = cadd(acc, make_float2(eps, eps));
+    const cf y2 = fast_log2x(le);
+    ya = y2.x;
+    yb = y2.y;
 }
 TALFE_HD void mel_log_ws(const cf* __restrict__ pg /* P + g */, const float (&w)[kRefWStride], const int (&lo)[kMelSlots], float eps,
                          float (&y)[2 * kMelSlots]) {

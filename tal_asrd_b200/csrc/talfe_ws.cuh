@@ -34,6 +34,30 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// TALFE_WS_NAMEDBAR (build-time experiment): the exchange hand-offs (E full / E empty) go through hardware named
+// barriers (arriving role: bar.arrive, waiting role: bar.sync, 640 threads each) instead of mbarriers, so that a
+// waiting warp is parked by the barrier unit and spends no issue slots on try_wait / nanosleep polling.  The
+// barrier's completion orders the arriving threads' prior shared-memory accesses before the waiters' later ones.
+#ifndef TALFE_WS_NAMEDBAR
+#define TALFE_WS_NAMEDBAR 0
+#endif
+// TALFE_WS_WCONST (build-time experiment): the consumers read their 28 mel weights from the constant bank (indexed
+// LDC, two distinct rows per warp) instead of shared memory: 8.75 of the 75 shared-memory wavefronts per frame.
+#ifndef TALFE_WS_WCONST
+#define TALFE_WS_WCONST 0
+#endif
+#ifndef TALFE_WS_TWREG
+#define TALFE_WS_TWREG 0
+#endif
+#if TALFE_WS_WCONST
+constexpr int kWConstSlots = 16;                                        // distinct filterbanks alive per device (35.8 KB of the bank)
+constexpr int kWConstVec = 20 * kRefWStride / 4;                        // float4 per slot
+__constant__ float4 c_w_ws[kWConstSlots * kWConstVec];
+#endif
+constexpr int kBarEFull = 4, kBarEEmpty = 6;                            // ids 4,5 / 6,7 (0: __syncthreads, 1: consumers, 2: producers)
 __device__ __forceinline__ void bulk_s2g(void* gmem_dst, unsigned smem_src, unsigned bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_src), "r"(bytes) : "memory");
 }
@@ -120,6 +144,16 @@ __device__ __forceinline__ void ws_producer(const KernelArgs& a, unsigned char* 
     load_window(j, a.win_global, XLayout<XT>::kScale, win);            // once per CTA, straight from global memory
     const cf* s_tw = reinterpret_cast<const cf*>(smem + a.off_tw) + j * 10;
     cf tw[10];
+#if TALFE_WS_TWREG
+    // build-time experiment: the 10 twiddles live in registers for the whole tile loop (6.25 fewer shared-memory
+    // wavefronts per frame, 20 more live registers in the producers)
+#pragma unroll
+    for (int h = 0; h < 5; ++h) {
+        const float4 tt = reinterpret_cast<const float4*>(s_tw)[h];
+        tw[2 * h] = make_float2(tt.x, tt.y);
+        tw[2 * h + 1] = make_float2(tt.z, tt.w);
+    }
+#endif
     const XT* xg = s_x0 + kXG * g1 + j;
     cf* col0 = s_e0 + ws_e_base(g1) + j;
     // Loader duty, taken in turn by the producer warps (tile kk by warp kk % 10, one tile ahead of the FFTs): all 32
@@ -200,19 +234,30 @@ __device__ __forceinline__ void ws_producer(const KernelArgs& a, unsigned char* 
         if (lane == 0) mbar_arrive(x_empty + buf);                      // this warp no longer reads x[buf]
         __syncwarp();
         // every tile, active or not: a producer never runs more than one phase ahead of the consumers
+#if TALFE_WS_NAMEDBAR
+        if (k >= 2) named_bar_sync(kBarEEmpty + buf, kWsThreads);       // consumers have loaded E[buf] of tile k-2
+#else
         if (k >= 2) mbar_wait_sleep(e_empty + buf, ((k - 2) >> 1) & 1); // consumers have loaded E[buf] of tile k-2
+#endif
         if (active) {
+#if !TALFE_WS_TWREG
 #pragma unroll
             for (int h = 0; h < 5; ++h) {
                 const float4 tt = reinterpret_cast<const float4*>(s_tw)[h];
                 tw[2 * h] = make_float2(tt.x, tt.y);
                 tw[2 * h + 1] = make_float2(tt.z, tt.w);
             }
+#endif
             stage1_ws_store(z, tw, col0 + buf * kWsECf);
         }
+#if TALFE_WS_NAMEDBAR
+        __syncwarp();
+        named_bar_arrive(kBarEFull + buf, kWsThreads);
+#else
         __syncwarp();
         if (lane == 0) mbar_arrive(e_full + buf);
         __syncwarp();
+#endif
     }
 }
 
@@ -283,7 +328,11 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, unsigned char* 
     const int warp = tid >> 5, lane = tid & 31;
     const int g = tid & (kWsGroups - 1), r = tid >> 4;                  // r: exchange row in stage 2, mel lane in the mel stage
     const bool special = r >= 18;                                       // warp 9: the packed rows, both frames
+#if TALFE_WS_WCONST
+    const float4* s_w4 = c_w_ws + a.w_slot * kWConstVec + r * (kRefWStride / 4);
+#else
     const float4* s_w4 = reinterpret_cast<const float4*>(smem + a.off_w_ws) + r * (kRefWStride / 4);
+#endif
     int lo[kMelSlots];
 #pragma unroll
     for (int i = 0; i < kMelSlots; ++i) lo[i] = reinterpret_cast<const int*>(smem + a.off_lo_ws)[i * 20 + r];
@@ -302,13 +351,22 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, unsigned char* 
         const int buf = k & 1;
         const WsDesc* dp = s_desc + (k & (kWsDescRing - 1));
         cf v[20];
+#if TALFE_WS_NAMEDBAR
+        named_bar_sync(kBarEFull + buf, kWsThreads);
+#else
         mbar_wait_sleep(e_full + buf, (k >> 1) & 1);
+#endif
         const int flags = dp->flags;
         const bool active = flags & kWsActive;
         if (active) stage2_load(e_row0 + buf * kWsECf, v);
+#if TALFE_WS_NAMEDBAR
+        __syncwarp();
+        if (k + 2 < n_my) named_bar_arrive(kBarEEmpty + buf, kWsThreads);   // only arrivals a producer will wait for
+#else
         __syncwarp();
         if (lane == 0) mbar_arrive(e_empty + buf);
         __syncwarp();
+#endif
         cf* s_p = s_p0 + buf * kWsPCf;
         if (active) {
             cf pw[10];
