@@ -44,6 +44,12 @@
 #define TALFE_HD __host__ __device__ __forceinline__
 #endif
 
+// Which packed-operand forms the ws kernel uses (bit 1 FFT rotations, 2 stage-1 store, 3 mel + log):
+// all of them; single bits are build-time experiments (bisection of bit-exactness against the scalar forms).
+#ifndef TALFE_PK
+#define TALFE_PK 15
+#endif
+
 namespace talfe {
 
 constexpr int kNfft = 400;
@@ -183,6 +189,10 @@ TALFE_HD void dft5(cf a0, cf a1, cf a2, cf a3, cf a4, cf& y0, cf& y1, cf& y2, cf
 // In-place 20-point complex DFT, natural order in and out (all indices compile-time).
 // Good-Thomas: n = (5 n1 + 4 n2) mod 20, k = (5 k1 + 16 k2) mod 20, n1,k1 in 0..3, n2,k2 in 0..4.
 // kPacked selects the single-instruction forms of the multiplications by -+i (same bits, fewer issue slots).
+// Second half (the four 5-point DFTs) of the 20-point transform; t[k1][n2] come from the 4-point stage.
+template <bool kPacked>
+TALFE_HD void fft20_dft5s(cf (&t)[4][5], cf (&v)[20]);
+
 template <bool kPacked = false>
 TALFE_HD void fft20(cf (&v)[20]) {
     cf t[4][5];
@@ -195,6 +205,33 @@ TALFE_HD void fft20(cf (&v)[20]) {
         t[1][n2] = csub_i<kPacked>(d02, d13);                   // d02 - i d13
         t[3][n2] = cadd_i<kPacked>(d02, d13);                   // d02 + i d13
     }
+    fft20_dft5s<kPacked>(t, v);
+}
+
+// The same transform of the WINDOWED input v[m] = win[m] x[m], with the window folded into the first butterflies:
+//   a0 = w0 x0,  s02 = fma(w2, x2, a0),  d02 = fma(-w2, x2, a0)   (likewise a1, s13, d13)
+// i.e. 10 multiplies + 20 fused multiply-adds instead of 20 multiplies + 20 adds, and one rounding fewer on half of
+// the terms.  Written out explicitly (ptxas would contract a packed multiply feeding a packed add on its own, but
+// which pairs it picks is its business) so that every kernel and the host emulator round identically.
+template <bool kPacked = false>
+TALFE_HD void fft20_windowed(const cf (&x)[20], const float (&win)[20], cf (&v)[20]) {
+    cf t[4][5];
+#pragma unroll
+    for (int n2 = 0; n2 < 5; ++n2) {
+        const int i0 = (4 * n2) % 20, i1 = (5 + 4 * n2) % 20, i2 = (10 + 4 * n2) % 20, i3 = (15 + 4 * n2) % 20;
+        const cf a0 = cmul_s(win[i0], x[i0]), a1 = cmul_s(win[i1], x[i1]);
+        const cf s02 = cfma_s(win[i2], x[i2], a0), d02 = cfma_s(-win[i2], x[i2], a0);
+        const cf s13 = cfma_s(win[i3], x[i3], a1), d13 = cfma_s(-win[i3], x[i3], a1);
+        t[0][n2] = cadd(s02, s13);
+        t[2][n2] = csub(s02, s13);
+        t[1][n2] = csub_i<kPacked>(d02, d13);
+        t[3][n2] = cadd_i<kPacked>(d02, d13);
+    }
+    fft20_dft5s<kPacked>(t, v);
+}
+
+template <bool kPacked>
+TALFE_HD void fft20_dft5s(cf (&t)[4][5], cf (&v)[20]) {
 #pragma unroll
     for (int k1 = 0; k1 < 4; ++k1) {
         cf y0, y1, y2, y3, y4;
@@ -238,7 +275,7 @@ TALFE_HD void load_window(int j, const float* __restrict__ win_t, float scale, f
 template <typename XT>
 TALFE_HD void stage1(int j, const XT* __restrict__ xg, const float (&win)[20],
                      const cf* __restrict__ tw_t, cf* __restrict__ e_group) {
-    cf z[20];
+    cf xin[20], z[20];
     const XT* p = xg + j;
     constexpr int kSkew = XLayout<XT>::kSkew;
 #pragma unroll
@@ -246,9 +283,9 @@ TALFE_HD void stage1(int j, const XT* __restrict__ xg, const float (&win)[20],
         // sample j + 20 m of frame a, j + 20 m + 160 of the pair for frame b, with the block skew
         const int ia = 20 * m + (20 * m >= kXBlock ? kSkew : 0);
         const int ib = 20 * m + kHop + (20 * m + kHop >= kXBlock ? kSkew : 0);
-        z[m] = make_float2(win[m] * x_to_float(p[ia]), win[m] * x_to_float(p[ib]));
+        xin[m] = make_float2(x_to_float(p[ia]), x_to_float(p[ib]));
     }
-    fft20(z);
+    fft20_windowed(xin, win, z);
     const float4* t4 = reinterpret_cast<const float4*>(tw_t + j * 10);
     cf* col = e_group + j;
     col[row_slot(18) * kERow] = z[0];                                             // row 18: (A_a[0] + i A_b[0]) / 2
@@ -449,13 +486,14 @@ TALFE_HD constexpr int ws_yt_off(int mel, int fr) { return mel * kWsYtStride + f
 template <typename XT>
 TALFE_HD void stage1_ws_fft(const XT* __restrict__ p /* xg + j */, const float (&win)[20], cf (&z)[20]) {
     constexpr int kSkew = XLayout<XT>::kSkew;
+    cf xin[20];
 #pragma unroll
     for (int m = 0; m < 20; ++m) {
         const int ia = 20 * m + (20 * m >= kXBlock ? kSkew : 0);
         const int ib = 20 * m + kHop + (20 * m + kHop >= kXBlock ? kSkew : 0);
-        z[m] = cmul_s(win[m], make_float2(x_to_float(p[ia]), x_to_float(p[ib])));     // one FMUL2 (scalar-broadcast operand)
+        xin[m] = make_float2(x_to_float(p[ia]), x_to_float(p[ib]));
     }
-    fft20<true>(z);
+    fft20_windowed<(TALFE_PK & 2) != 0>(xin, win, z);                  // window taps as scalar-broadcast operands of FMUL2 / FFMA2
 }
 
 // Stage 1, second half: untangle the two real-input transforms, twiddle by tw[k1-1] = W400^(j k1), write
@@ -469,18 +507,30 @@ TALFE_HD void stage1_ws_store(const cf (&z)[20], const cf (&tw)[10], cf* __restr
 #pragma unroll
     for (int k1 = 1; k1 < 10; ++k1) {
         const cf sm = cadd(z[k1], z[20 - k1]), df = csub(z[k1], z[20 - k1]);
+#if TALFE_PK & 4
         const cf w = tw[k1 - 1], iw = times_i(w);
         col[(2 * (k1 - 1)) * kWsERow] = cfma_ss(sm.x, w, df.y, iw);
         col[(2 * (k1 - 1) + 1) * kWsERow] = cfma_ss(sm.y, iw, df.x, w);
+#else
+        const cf aa = make_float2(sm.x, df.y);
+        const cf ab = make_float2(sm.y, -df.x);
+        col[(2 * (k1 - 1)) * kWsERow] = cmul(aa, tw[k1 - 1]);
+        const cf cb = cmul(ab, tw[k1 - 1]);
+        col[(2 * (k1 - 1) + 1) * kWsERow] = make_float2(-cb.y, cb.x);
+#endif
     }
+#if TALFE_PK & 4
     col[19 * kWsERow] = cfma_ss(z[10].x, tw[9], z[10].y, times_i(tw[9]));
+#else
+    col[19 * kWsERow] = cmul(z[10], tw[9]);
+#endif
 }
 
 // Stage 2 (consumer thread (g, r)): |FFT-20(row r)|^2 kept in registers until the power array is free.
 // Normal rows r < 18: pw[q] = (bin k1 + 20 q, bin (20 - k1) + 20 q) of frame r & 1, k1 = 1 + r / 2.
 TALFE_HD void stage2_ws_power_normal(cf (&v)[20], cf (&pw)[10]) {
 #if !(defined(TALFE_ABLATE) && (TALFE_ABLATE & 4))
-    fft20<true>(v);
+    fft20<(TALFE_PK & 2) != 0>(v);
 #endif
 #pragma unroll
     for (int q = 0; q < 10; ++q)
@@ -497,7 +547,7 @@ TALFE_HD void stage2_ws_store_normal(int k1, const cf (&pw)[10], float* __restri
 }
 // Packed rows: r == 18 (zero = true) -> bins 20 (q + 1); r == 19 -> bins 10 + 20 q; both frames per entry.
 TALFE_HD void stage2_ws_power_special(bool zero, cf (&v)[20], cf (&pw)[10]) {
-    fft20<true>(v);
+    fft20<(TALFE_PK & 2) != 0>(v);
 #pragma unroll
     for (int q = 0; q < 10; ++q) {
         const cf p = zero ? v[q + 1] : v[q];
@@ -518,6 +568,7 @@ template <int W, int OFF>
 TALFE_HD void mel_slot_ws(const cf* __restrict__ p /* P + g + 16 lo */, const float (&w)[kRefWStride], float eps, float& ya, float& yb) {
     // both frames of the pair ride in one packed accumulator: FFMA2 with the weight as scalar-broadcast operand
     // (the same two IEEE fmas as the scalar form, half the issue slots)
+#if TALFE_PK & 8
     cf acc = make_float2(0.f, 0.f);
 #pragma unroll
     for (int r = 0; r < W; ++r) acc = cfma_s(w[OFF + r], p[kWsGroups * r], acc);
@@ -525,6 +576,17 @@ TALFE_HD void mel_slot_ws(const cf* __restrict__ p /* P + g + 16 lo */, const fl
     const cf y2 = fast_log2x(le);
     ya = y2.x;
     yb = y2.y;
+#else
+    float acc_a = 0.f, acc_b = 0.f;
+#pragma unroll
+    for (int r = 0; r < W; ++r) {
+        const cf pw = p[kWsGroups * r];
+        acc_a = fmaf(w[OFF + r], pw.x, acc_a);
+        acc_b = fmaf(w[OFF + r], pw.y, acc_b);
+    }
+    ya = fast_log(acc_a + eps);
+    yb = fast_log(acc_b + eps);
+#endif
 }
 TALFE_HD void mel_log_ws(const cf* __restrict__ pg /* P + g */, const float (&w)[kRefWStride], const int (&lo)[kMelSlots], float eps,
                          float (&y)[2 * kMelSlots]) {

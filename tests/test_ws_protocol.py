@@ -33,8 +33,26 @@ class MBar:
         return (self.phase & 1) != parity
 
 
-def run(n_my, seed, stores="producers"):
+class NBar:
+    """Hardware named barrier shared by both roles (bar.arrive by one role, bar.sync by the other): completes when
+    all 2 W warps have arrived, then resets.  A warp must not arrive twice at the same generation."""
+    def __init__(self, count):
+        self.count, self.who, self.gen = count, set(), 0
+
+    def arrive(self, name):
+        assert name not in self.who, f"{name} arrived twice at a named barrier before it completed"
+        gen = self.gen
+        self.who.add(name)
+        if len(self.who) == self.count:
+            self.who, self.gen = set(), self.gen + 1
+        return gen
+
+
+def run(n_my, seed, stores="producers", handoff="mbar"):
     by_producers = stores == "producers"
+    named = handoff == "named"                              # TALFE_WS_NAMEDBAR builds: E full / E empty on named barriers
+    assert not (named and by_producers)
+    efn, een = [NBar(2 * W), NBar(2 * W)], [NBar(2 * W), NBar(2 * W)]
     rnd = random.Random(seed)
     xf, xe = [MBar(1), MBar(1)], [MBar(W), MBar(W)]
     ef, ee = [MBar(W), MBar(W)], [MBar(W), MBar(W)]
@@ -75,7 +93,9 @@ def run(n_my, seed, stores="producers"):
             yield ("work",)                                 # stage 1 reads x[k & 1]
             x_readers[k & 1] -= 1
             xe[k & 1].arrive()
-            if k >= 2:
+            if k >= 2 and named:
+                yield ("nbar", een[k & 1], een[k & 1].arrive(f"P{w}"), f"e_empty({k - 2}) bar.sync")
+            elif k >= 2:
                 yield ("wait", ee[k & 1], ((k - 2) >> 1) & 1, f"e_empty({k - 2})")
             if turn:
                 yield ("wait", yf[ks & 1], (ks >> 1) & 1, f"y_full({ks})")
@@ -85,7 +105,10 @@ def run(n_my, seed, stores="producers"):
                 e_tile[k & 1], e_written[k & 1], e_read[k & 1] = k, 0, 0
             yield ("work",)                                 # stage 1 writes E[k & 1]
             e_written[k & 1] += 1
-            ef[k & 1].arrive()
+            if named:
+                efn[k & 1].arrive(f"P{w}")                  # bar.arrive: does not block
+            else:
+                ef[k & 1].arrive()
             if turn:
                 yield ("work",)                             # bulk copies read Y[ks & 1]
                 sent.add(ks)
@@ -93,10 +116,16 @@ def run(n_my, seed, stores="producers"):
 
     def consumer(w):
         for k in range(n_my):
-            yield ("wait", ef[k & 1], (k >> 1) & 1, f"e_full({k})")
+            if named:
+                yield ("nbar", efn[k & 1], efn[k & 1].arrive(f"C{w}"), f"e_full({k}) bar.sync")
+            else:
+                yield ("wait", ef[k & 1], (k >> 1) & 1, f"e_full({k})")
             assert e_tile[k & 1] == k and e_written[k & 1] == W, "exchange buffer read before it was complete"
             e_read[k & 1] += 1
-            ee[k & 1].arrive()
+            if not named:
+                ee[k & 1].arrive()
+            elif k + 2 < n_my:                              # only arrivals a producer will wait for
+                een[k & 1].arrive(f"C{w}")
             yield ("work",)                                 # FFT, power -> P[k & 1]
             gen = bar["gen"]
             bar["n"] += 1
@@ -131,7 +160,8 @@ def run(n_my, seed, stores="producers"):
             pass
     while state:
         ready = [n for n, (_, c) in state.items()
-                 if c[0] == "work" or (c[0] == "wait" and c[1].passed(c[2])) or (c[0] == "bar" and bar["gen"] > c[1])]
+                 if c[0] == "work" or (c[0] == "wait" and c[1].passed(c[2])) or (c[0] == "bar" and bar["gen"] > c[1])
+                 or (c[0] == "nbar" and c[1].gen > c[2])]
         assert ready, f"deadlock (n_my={n_my}, seed={seed}): " + str({n: c[-1] for n, (_, c) in state.items()})
         name = rnd.choice(ready)
         gen = state[name][0]
@@ -140,6 +170,7 @@ def run(n_my, seed, stores="producers"):
         except StopIteration:
             del state[name]
     assert sent == set(range(n_my))
+    assert all(not b.who for b in efn + een), "a named barrier is left with pending arrivals"
 
 
 @pytest.mark.parametrize("stores", ["consumers", "producers"])
@@ -147,6 +178,14 @@ def run(n_my, seed, stores="producers"):
 def test_pipeline_protocol_is_live_and_safe(n_my, stores):
     for seed in range(80):
         run(n_my, seed, stores)
+
+
+@pytest.mark.parametrize("n_my", [1, 2, 3, 4, 5, 6, 7, 9, 10, 11, 13, 21, 41])
+def test_named_barrier_handoff_is_live_and_safe(n_my):
+    """TALFE_WS_NAMEDBAR: no deadlock, no double arrival at a named barrier, no exchange-buffer hazard, and every named
+    barrier is left with no pending arrivals at the end."""
+    for seed in range(80):
+        run(n_my, seed, "consumers", handoff="named")
 
 
 def test_drain_needs_c_done():
