@@ -193,9 +193,9 @@ TALFE_HD void dft5(cf a0, cf a1, cf a2, cf a3, cf a4, cf& y0, cf& y1, cf& y2, cf
 template <bool kPacked>
 TALFE_HD void fft20_dft5s(cf (&t)[4][5], cf (&v)[20]);
 
-template <bool kPacked = false>
-TALFE_HD void fft20(cf (&v)[20]) {
-    cf t[4][5];
+// First half: the five 4-point DFTs.
+template <bool kPacked>
+TALFE_HD void fft20_fft4s(const cf (&v)[20], cf (&t)[4][5]) {
 #pragma unroll
     for (int n2 = 0; n2 < 5; ++n2) {
         cf a0 = v[(4 * n2) % 20], a1 = v[(5 + 4 * n2) % 20], a2 = v[(10 + 4 * n2) % 20], a3 = v[(15 + 4 * n2) % 20];
@@ -205,6 +205,12 @@ TALFE_HD void fft20(cf (&v)[20]) {
         t[1][n2] = csub_i<kPacked>(d02, d13);                   // d02 - i d13
         t[3][n2] = cadd_i<kPacked>(d02, d13);                   // d02 + i d13
     }
+}
+
+template <bool kPacked = false>
+TALFE_HD void fft20(cf (&v)[20]) {
+    cf t[4][5];
+    fft20_fft4s<kPacked>(v, t);
     fft20_dft5s<kPacked>(t, v);
 }
 

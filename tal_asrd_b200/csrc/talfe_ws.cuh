@@ -52,6 +52,12 @@ __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
 #ifndef TALFE_WS_TWREG
 #define TALFE_WS_TWREG 0
 #endif
+#ifndef TALFE_WS_WREG
+#define TALFE_WS_WREG 0
+#endif
+#ifndef TALFE_WS_COOPSTORE
+#define TALFE_WS_COOPSTORE 0
+#endif
 #if TALFE_WS_WCONST
 constexpr int kWConstSlots = 16;                                        // distinct filterbanks alive per device (35.8 KB of the bank)
 constexpr int kWConstVec = 20 * kRefWStride / 4;                        // float4 per slot
@@ -272,6 +278,19 @@ __device__ __forceinline__ bool ws_store_tile(const KernelArgs& a, const WsDesc*
     return false;                                                        // timing experiment only: features never leave shared memory
 #endif
     const int flags = dp->flags;
+#if TALFE_WS_COOPSTORE
+    // build-time experiment: full tiles leave by two coalesced 16-byte loads + stores per thread (the tile is one
+    // contiguous 10 240-byte block of a [.., T, 80] output) instead of bulk copies: no proxy fence, no bulk waits
+    if (flags & kWsBulkY) {
+        const int fr = tid / 20, c4 = tid - 20 * fr;                    // 640 float4 per tile, 320 threads
+        const float4 v0 = *reinterpret_cast<const float4*>(s_y + ws_y_off(fr) + 4 * c4);
+        const float4 v1 = *reinterpret_cast<const float4*>(s_y + ws_y_off(fr + 16) + 4 * c4);
+        float4* dst = reinterpret_cast<float4*>(dp->out_tile) + tid;
+        dst[0] = v0;
+        dst[kWsRoleThreads] = v1;
+        return false;
+    }
+#endif
     if (flags & kWsBulkY) {
         if ((tid & 31) == 0) {
             const int w = tid >> 5;
@@ -327,7 +346,11 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, unsigned char* 
     unsigned long long* e_empty = s_bar + 6;
     const int warp = tid >> 5, lane = tid & 31;
     const int g = tid & (kWsGroups - 1), r = tid >> 4;                  // r: exchange row in stage 2, mel lane in the mel stage
+#if defined(TALFE_ABLATE) && (TALFE_ABLATE & 32)
+    const bool special = false;                                         // timing experiment only: no straggler warp at the barrier
+#else
     const bool special = r >= 18;                                       // warp 9: the packed rows, both frames
+#endif
 #if TALFE_WS_WCONST
     const float4* s_w4 = c_w_ws + a.w_slot * kWConstVec + r * (kRefWStride / 4);
 #else
@@ -341,6 +364,14 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, unsigned char* 
     float* yb0 = s_y0 + (mt ? ws_yt_off(r, 2 * g) : ws_y_off(2 * g) + r);
     const int k1 = 1 + (r >> 1);
     double acc_s = 0.0, acc_q = 0.0;
+#if TALFE_WS_WREG
+    float w[kRefWStride];                                               // build-time experiment: mel weights live in registers
+#pragma unroll
+    for (int q = 0; q < kRefWStride / 4; ++q) {
+        const float4 t = s_w4[q];
+        w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
+    }
+#endif
 
     // Per tile k (buffers b = k & 1):  E[b] -> registers -> FFT-20 -> power -> P[b]  |barrier|  store of tile k-1 from
     // Y[b^1] issued, mel stage P[b] -> Y[b].  Hazards the single barrier covers: every warp arriving at barrier(k) has
@@ -378,17 +409,23 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, unsigned char* 
                 stage2_ws_store_special(r == 18, pw, s_p + g);
             }
         }
+#if !TALFE_WS_COOPSTORE
         if (lane == 0) bulk_wait_read<0>();                             // this lane's store of tile k-2 has finished reading Y[buf]
+#endif
+#if !(defined(TALFE_ABLATE) && (TALFE_ABLATE & 64))                     // (64: timing experiment only, racy: no consumer barrier)
         named_bar_sync(1, kWsRoleThreads);                              // P[buf](k) and Y[buf^1](k-1) complete
+#endif
         if (k >= 1) ws_store_tile(a, s_desc + ((k - 1) & (kWsDescRing - 1)), s_y0 + (buf ^ 1) * kWsYFloats, tid);
         float sum = 0.f, sumsq = 0.f;
         if (active) {
+#if !TALFE_WS_WREG
             float w[kRefWStride];
 #pragma unroll
             for (int q = 0; q < kRefWStride / 4; ++q) {
                 const float4 t = s_w4[q];
                 w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
             }
+#endif
             float y[2 * kMelSlots];
 #if defined(TALFE_ABLATE) && (TALFE_ABLATE & 1)
 #pragma unroll
@@ -430,7 +467,9 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, unsigned char* 
                 }
             }
         }
+#if !TALFE_WS_COOPSTORE
         fence_proxy_async();                                            // Y[buf] writes -> visible to the bulk-copy engine
+#endif
         if (a.partials_per_tile) {
             double ds = (double)sum, dq = (double)sumsq;
 #pragma unroll
@@ -447,6 +486,194 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, unsigned char* 
     }
     named_bar_sync(1, kWsRoleThreads);
     if (n_my >= 1) ws_store_tile(a, s_desc + ((n_my - 1) & (kWsDescRing - 1)), s_y0 + ((n_my - 1) & 1) * kWsYFloats, tid);
+    if (!a.partials_per_tile) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            acc_s += __shfl_xor_sync(0xffffffffu, acc_s, o);
+            acc_q += __shfl_xor_sync(0xffffffffu, acc_q, o);
+        }
+        double2* s_red = reinterpret_cast<double2*>(s_p0);              // the power arrays are free after the last barrier
+        if (lane == 0) s_red[warp] = make_double2(acc_s, acc_q);
+        named_bar_sync(1, kWsRoleThreads);
+        if (tid == 0) {
+            double ts = 0.0, tq2 = 0.0;
+            for (int w2 = 0; w2 < kWsRoleWarps; ++w2) { ts += s_red[w2].x; tq2 += s_red[w2].y; }
+            a.partials[blockIdx.x] = make_double2(ts, tq2);
+        }
+    }
+    if (lane == 0) bulk_wait_all<0>();                                  // shared memory must outlive the copies that read it
+}
+
+// TALFE_WS_SWP: software-pipelined consumers.  Iteration k runs the mel stage of tile k-1 (shared-memory bound: 33
+// loads per thread) and stage 2 of tile k (FP bound: FFT-20 + power, registers only) in ONE straight-line region, so
+// that the scheduler overlaps the two inside every warp instead of the role alternating between a shared-memory
+// phase and an FP phase.  Still one barrier per iteration:
+//   wait E[b](k) -> registers, release E[b] | mel(k-1): P[b^1] -> Y[b^1]  ||  FFT(k), power | P[b] <- power(k)
+//   | fence, barrier(k) | bulk store of tile k-1 from Y[b^1]
+// Hazards: P[b^1] is read by mel(k-1) in iteration k and next written by stage 2 of tile k+1 after barrier(k);
+// P[b] was last read by mel(k-2) before barrier(k-1); Y[b^1] was last read by the store of tile k-3, issued after
+// barrier(k-2), whose lanes wait for their reads before barrier(k-1); the store of tile k-1 follows barrier(k).
+#ifndef TALFE_WS_SWP
+#define TALFE_WS_SWP 0
+#endif
+template <typename XT>
+__device__ __forceinline__ void ws_consumer_swp(const KernelArgs& a, unsigned char* smem, const cf* s_e0, cf* s_p0, float* s_y0,
+                                                const WsDesc* s_desc, unsigned long long* s_bar, const int tid, const int n_my) {
+    unsigned long long* e_full = s_bar + 4;
+    unsigned long long* e_empty = s_bar + 6;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int g = tid & (kWsGroups - 1), r = tid >> 4;
+    const bool special = r >= 18;
+    const float4* s_w4 = reinterpret_cast<const float4*>(smem + a.off_w_ws) + r * (kRefWStride / 4);
+    int lo[kMelSlots];
+#pragma unroll
+    for (int i = 0; i < kMelSlots; ++i) lo[i] = reinterpret_cast<const int*>(smem + a.off_lo_ws)[i * 20 + r];
+    const cf* e_row0 = s_e0 + ws_e_base(g) + r * kWsERow;
+    const bool mt = a.out_layout == TALFE_LAYOUT_MT;
+    float* yb0 = s_y0 + (mt ? ws_yt_off(r, 2 * g) : ws_y_off(2 * g) + r);
+    const int k1 = 1 + (r >> 1);
+    double acc_s = 0.0, acc_q = 0.0;
+
+    // mel stage of tile kp (its power array and feature tile are the buffers kp & 1)
+    auto mel_tile = [&](int kp, float& sum, float& sumsq) {
+        const WsDesc* dq = s_desc + (kp & (kWsDescRing - 1));
+        const int pflags = dq->flags;
+        const cf* s_p = s_p0 + (kp & 1) * kWsPCf;
+        float w[kRefWStride];
+#pragma unroll
+        for (int q = 0; q < kRefWStride / 4; ++q) {
+            const float4 t = s_w4[q];
+            w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
+        }
+        float y[2 * kMelSlots];
+        mel_log_ws(s_p + g, w, lo, a.eps, y);
+        float* yb = yb0 + (kp & 1) * kWsYFloats;
+        if (!mt) {
+#pragma unroll
+            for (int i = 0; i < kMelSlots; ++i) {
+                yb[20 * i] = y[2 * i];
+                yb[kMaxMels + 20 * i] = y[2 * i + 1];
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < kMelSlots; ++i) {
+                yb[20 * i * kWsYtStride] = y[2 * i];
+                yb[20 * i * kWsYtStride + 1] = y[2 * i + 1];
+            }
+        }
+        if (pflags & kWsFull) {
+#pragma unroll
+            for (int i = 0; i < 2 * kMelSlots; ++i) {
+                sum += y[i];
+                if (a.want_sumsq) sumsq = fmaf(y[i], y[i], sumsq);
+            }
+        } else {
+            const int ta = dq->t0 + 2 * g, t_end = dq->t_end;
+#pragma unroll
+            for (int f = 0; f < 2; ++f) {
+                if (ta + f < t_end) {
+#pragma unroll
+                    for (int i = 0; i < kMelSlots; ++i) {
+                        sum += y[2 * i + f];
+                        if (a.want_sumsq) sumsq = fmaf(y[2 * i + f], y[2 * i + f], sumsq);
+                    }
+                }
+            }
+        }
+    };
+    // stage 2 of the tile whose exchange rows sit in v: FFT-20, power, into the power array s_p
+    auto stage2_tile = [&](cf (&v)[20], cf* s_p) {
+        cf pw[10];
+        if (!special) {
+            stage2_ws_power_normal(v, pw);
+            stage2_ws_store_normal(k1, pw, reinterpret_cast<float*>(s_p) + 2 * g + (r & 1));
+        } else {
+            stage2_ws_power_special(r == 18, v, pw);
+            stage2_ws_store_special(r == 18, pw, s_p + g);
+        }
+    };
+
+    // Steady state (previous tile full, [.., T, 80] layout, normal rows): the mel stage of tile k-1 and stage 2 of tile
+    // k written as ONE branch-free region, the two streams alternating in the source so that the scheduler keeps both
+    // the shared-memory pipe and the FP pipe busy.  Same arithmetic, same order of operations per value.
+    auto fused_tile = [&](int kp, cf (&v)[20], cf* s_p, float& sum, float& sumsq) {
+        constexpr bool kPk = (TALFE_PK & 2) != 0;
+        const cf* pg = s_p0 + (kp & 1) * kWsPCf + g;
+        float w[kRefWStride];
+#pragma unroll
+        for (int q = 0; q < kRefWStride / 4; ++q) {
+            const float4 t4 = s_w4[q];
+            w[4 * q] = t4.x; w[4 * q + 1] = t4.y; w[4 * q + 2] = t4.z; w[4 * q + 3] = t4.w;
+        }
+        float y[2 * kMelSlots];
+        cf t[4][5];
+        mel_slot_ws<kRefW0, 0>(pg + kWsGroups * lo[0], w, a.eps, y[0], y[1]);
+        mel_slot_ws<kRefW1, kRefW0>(pg + kWsGroups * lo[1], w, a.eps, y[2], y[3]);
+        fft20_fft4s<kPk>(v, t);
+        mel_slot_ws<kRefW2, kRefW0 + kRefW1>(pg + kWsGroups * lo[2], w, a.eps, y[4], y[5]);
+        fft20_dft5s<kPk>(t, v);
+        mel_slot_ws<kRefW3, kRefW0 + kRefW1 + kRefW2>(pg + kWsGroups * lo[3], w, a.eps, y[6], y[7]);
+        cf pw[10];
+#pragma unroll
+        for (int q = 0; q < 10; ++q)
+            pw[q] = make_float2(fmaf(v[q].x, v[q].x, v[q].y * v[q].y), fmaf(v[19 - q].x, v[19 - q].x, v[19 - q].y * v[19 - q].y));
+        float* yb = yb0 + (kp & 1) * kWsYFloats;
+#pragma unroll
+        for (int i = 0; i < kMelSlots; ++i) {
+            yb[20 * i] = y[2 * i];
+            yb[kMaxMels + 20 * i] = y[2 * i + 1];
+        }
+        stage2_ws_store_normal(k1, pw, reinterpret_cast<float*>(s_p) + 2 * g + (r & 1));
+#pragma unroll
+        for (int i = 0; i < 2 * kMelSlots; ++i) {
+            sum += y[i];
+            sumsq = fmaf(y[i], y[i], sumsq);                            // only read when statistics want it
+        }
+    };
+
+    for (int k = 0; k <= n_my; ++k) {
+        const int buf = k & 1;
+        const bool have_cur = k < n_my;
+        cf v[20];
+        bool act_cur = false;
+        if (have_cur) {
+            mbar_wait_sleep(e_full + buf, (k >> 1) & 1);
+            act_cur = s_desc[k & (kWsDescRing - 1)].flags & kWsActive;
+            if (act_cur) stage2_load(e_row0 + buf * kWsECf, v);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(e_empty + buf);
+            __syncwarp();
+        }
+        const bool act_prev = k >= 1 && (s_desc[(k - 1) & (kWsDescRing - 1)].flags & kWsActive);
+        float sum = 0.f, sumsq = 0.f;
+        cf* s_p = s_p0 + buf * kWsPCf;
+        const bool full_prev = k >= 1 && (s_desc[(k - 1) & (kWsDescRing - 1)].flags & kWsFull);
+        if (act_prev && act_cur && full_prev && !mt && !special) {
+            fused_tile(k - 1, v, s_p, sum, sumsq);
+        } else {
+            if (act_prev) mel_tile(k - 1, sum, sumsq);
+            if (act_cur) stage2_tile(v, s_p);
+        }
+        if (k >= 1) {
+            if (a.partials_per_tile) {
+                double ds = (double)sum, dq = (double)sumsq;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    ds += __shfl_xor_sync(0xffffffffu, ds, o);
+                    dq += __shfl_xor_sync(0xffffffffu, dq, o);
+                }
+                const long long tile = (long long)blockIdx.x + (long long)(k - 1) * gridDim.x;
+                if (lane == 0) a.partials[tile * kWsRoleWarps + warp] = make_double2(ds, dq);
+            } else {
+                acc_s += (double)sum;
+                acc_q += (double)sumsq;
+            }
+        }
+        if (lane == 0) bulk_wait_read<0>();                             // this lane's store of tile k-3 has finished reading Y[buf^1]
+        fence_proxy_async();                                            // Y[buf^1] writes of mel(k-1) -> visible to the bulk-copy engine
+        named_bar_sync(1, kWsRoleThreads);                              // P[buf](k) and Y[buf^1](k-1) complete
+        if (k >= 1) ws_store_tile(a, s_desc + ((k - 1) & (kWsDescRing - 1)), s_y0 + (buf ^ 1) * kWsYFloats, tid);
+    }
     if (!a.partials_per_tile) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -493,7 +720,11 @@ __global__ void __launch_bounds__(kWsThreads, 1) logmel_ws_kernel(const KernelAr
     cudaGridDependencySynchronize();
     const int n_my = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles blockIdx.x, + gridDim.x, ...
     if (tid < kWsRoleThreads) ws_producer<XT>(a, smem, s_x0, s_e0, s_desc, s_bar, tid, n_my);
+#if TALFE_WS_SWP
+    else ws_consumer_swp<XT>(a, smem, s_e0, s_p0, s_y0, s_desc, s_bar, tid - kWsRoleThreads, n_my);
+#else
     else ws_consumer<XT>(a, smem, s_e0, s_p0, s_y0, s_desc, s_bar, tid - kWsRoleThreads, n_my);
+#endif
 }
 
 constexpr size_t ws_smem_bytes(size_t table_bytes) {
