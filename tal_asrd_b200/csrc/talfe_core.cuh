@@ -115,11 +115,19 @@ TALFE_HD cf cmul_s(float s, cf t) {
         : "=f"(r.x), "=f"(r.y) : "f"(s), "f"(t.x), "f"(t.y));
     return r;
 }
+// s * t - a
+TALFE_HD cf cfms_s(float s, cf t, cf a) {
+    cf r;
+    asm("{ .reg .b64 rs, rt, ra, rr; .reg .f32 n0, n1; neg.f32 n0, %5; neg.f32 n1, %6; mov.b64 rs, {%2,%2}; mov.b64 rt, {%3,%4}; mov.b64 ra, {n0,n1}; fma.rn.f32x2 rr, rs, rt, ra; mov.b64 {%0,%1}, rr; }"
+        : "=f"(r.x), "=f"(r.y) : "f"(s), "f"(t.x), "f"(t.y), "f"(a.x), "f"(a.y));
+    return r;
+}
 #else
 TALFE_HD cf cadd(cf a, cf b) { return make_float2(a.x + b.x, a.y + b.y); }
 TALFE_HD cf csub(cf a, cf b) { return make_float2(a.x - b.x, a.y - b.y); }
 TALFE_HD cf cfma_s(float s, cf t, cf a) { return make_float2(fmaf(s, t.x, a.x), fmaf(s, t.y, a.y)); }
 TALFE_HD cf cmul_s(float s, cf t) { return make_float2(s * t.x, s * t.y); }
+TALFE_HD cf cfms_s(float s, cf t, cf a) { return make_float2(fmaf(s, t.x, -a.x), fmaf(s, t.y, -a.y)); }
 #endif
 // explicit fused forms: the contraction the compiler would pick for a.x*b.x - a.y*b.y may differ from one kernel
 // to the next; fixing it keeps every variant of the kernel (and the host emulator) bit-identical
@@ -215,7 +223,7 @@ TALFE_HD void fft20(cf (&v)[20]) {
 }
 
 // The same transform of the WINDOWED input v[m] = win[m] x[m], with the window folded into the first butterflies:
-//   a0 = w0 x0,  s02 = fma(w2, x2, a0),  d02 = fma(-w2, x2, a0)   (likewise a1, s13, d13)
+//   a2 = w2 x2,  s02 = fma(w0, x0, a2),  d02 = fma(w0, x0, -a2)   (likewise a3, s13, d13)
 // i.e. 10 multiplies + 20 fused multiply-adds instead of 20 multiplies + 20 adds, and one rounding fewer on half of
 // the terms.  Written out explicitly (ptxas would contract a packed multiply feeding a packed add on its own, but
 // which pairs it picks is its business) so that every kernel and the host emulator round identically.
@@ -225,9 +233,9 @@ TALFE_HD void fft20_windowed(const cf (&x)[20], const float (&win)[20], cf (&v)[
 #pragma unroll
     for (int n2 = 0; n2 < 5; ++n2) {
         const int i0 = (4 * n2) % 20, i1 = (5 + 4 * n2) % 20, i2 = (10 + 4 * n2) % 20, i3 = (15 + 4 * n2) % 20;
-        const cf a0 = cmul_s(win[i0], x[i0]), a1 = cmul_s(win[i1], x[i1]);
-        const cf s02 = cfma_s(win[i2], x[i2], a0), d02 = cfma_s(-win[i2], x[i2], a0);
-        const cf s13 = cfma_s(win[i3], x[i3], a1), d13 = cfma_s(-win[i3], x[i3], a1);
+        const cf a2 = cmul_s(win[i2], x[i2]), a3 = cmul_s(win[i3], x[i3]);
+        const cf s02 = cfma_s(win[i0], x[i0], a2), d02 = cfms_s(win[i0], x[i0], a2);
+        const cf s13 = cfma_s(win[i1], x[i1], a3), d13 = cfms_s(win[i1], x[i1], a3);
         t[0][n2] = cadd(s02, s13);
         t[2][n2] = csub(s02, s13);
         t[1][n2] = csub_i<kPacked>(d02, d13);
