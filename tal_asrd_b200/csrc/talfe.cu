@@ -56,7 +56,6 @@ struct talfe_plan_impl {
     int ref_layout;                // 80-mel reference filterbank shape -> fully unrolled mel stage
     int variant;                   // 0 = legacy kernel (2 CTAs/SM, every thread runs every stage), 1 = warp-specialised
     int l2_prefetch;
-    int w_slot;                    // constant-bank slot of the ws kernel's mel weights (TALFE_WS_WCONST builds), else -1
     size_t off_ws, ws_bytes, off_tw_ws, off_w_ws, off_lo_ws, ws_smem;   // table section staged by the ws kernel
     MelLayout layout;
     int pstride;
@@ -96,7 +95,6 @@ struct KernelArgs {
     const float* win_global;       // window taps [20][20] in global memory (read once into producer registers)
     int out_align_ok;              // every frame row of `out` starts 16-byte aligned (bulk stores allowed)
     int l2_prefetch;               // prefetch tile k+2 into L2 while tile k+1 travels to shared memory
-    int w_slot;                    // constant-bank slot holding the consumers' mel weights (TALFE_WS_WCONST builds)
 };
 
 // ------------------------------------------------------------------------------------------ K1
@@ -693,43 +691,6 @@ WorkspaceLayout workspace_layout(int n_mels, long long batch, long long n_frames
 
 }  // namespace
 
-#if TALFE_WS_WCONST
-// Constant-bank slots for the ws kernel's mel weights: per device, shared by plans whose weights are bit-identical
-// (the usual case: every plan built from the reference tables), reference counted, freed with the last plan.
-namespace {
-struct WConstSlot { int refs = 0; std::vector<unsigned char> bytes; };
-struct WConstDevice { WConstSlot slot[kWConstSlots]; };
-std::mutex g_wconst_mutex;
-std::vector<WConstDevice*> g_wconst;                                    // indexed by device ordinal
-
-// returns the slot (>= 0), or -1 when all slots hold other tables (*err stays cudaSuccess) or on a CUDA error
-int wconst_acquire(int device, const unsigned char* weights, cudaError_t* err) {
-    const size_t n = (size_t)kWConstVec * sizeof(float4);
-    std::lock_guard<std::mutex> lock(g_wconst_mutex);
-    if ((int)g_wconst.size() <= device) g_wconst.resize(device + 1, nullptr);
-    if (!g_wconst[device]) g_wconst[device] = new WConstDevice();
-    WConstDevice& d = *g_wconst[device];
-    int free_slot = -1;
-    for (int i = 0; i < kWConstSlots; ++i) {
-        if (d.slot[i].refs > 0 && std::memcmp(d.slot[i].bytes.data(), weights, n) == 0) { ++d.slot[i].refs; return i; }
-        if (d.slot[i].refs == 0 && free_slot < 0) free_slot = i;
-    }
-    if (free_slot < 0) return -1;
-    // a slot is rewritten only when no plan refers to it; kernels of destroyed plans may still be in flight on the
-    // caller's streams, and cudaMemcpyToSymbol (legacy default stream) orders itself after them
-    *err = cudaMemcpyToSymbol(c_w_ws, weights, n, (size_t)free_slot * n);
-    if (*err != cudaSuccess) return -1;
-    d.slot[free_slot].bytes.assign(weights, weights + n);
-    d.slot[free_slot].refs = 1;
-    return free_slot;
-}
-void wconst_release(int device, int slot) {
-    if (slot < 0) return;
-    std::lock_guard<std::mutex> lock(g_wconst_mutex);
-    if (device < (int)g_wconst.size() && g_wconst[device] && g_wconst[device]->slot[slot].refs > 0) --g_wconst[device]->slot[slot].refs;
-}
-}  // namespace
-#endif
 
 struct talfe_plan : talfe_plan_impl {};
 
@@ -774,7 +735,6 @@ int talfe_plan_create(talfe_plan** plan_out, int device, int n_mels, const float
     talfe_plan* p = new (std::nothrow) talfe_plan();
     if (!p) return TALFE_ERR_INVALID;
     p->device = device;
-    p->w_slot = -1;
     p->n_mels = n_mels;
     p->layout = t.layout;
     p->pstride = t.pstride;
@@ -802,21 +762,12 @@ int talfe_plan_create(talfe_plan** plan_out, int device, int n_mels, const float
         for (int dt = TALFE_F32; dt <= TALFE_I16 && e == cudaSuccess; ++dt)
             e = cudaFuncSetAttribute(ws_kernel_for(dt), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->ws_smem);
     }
-#if TALFE_WS_WCONST
-    if (e == cudaSuccess && p->variant == 1) {
-        p->w_slot = wconst_acquire(device, t.blob.data() + t.off_ws + t.off_w_ws, &e);
-        if (e == cudaSuccess && p->w_slot < 0) p->variant = 0;            // every slot taken by other filterbanks: legacy kernel
-    }
-#endif
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
         e = cudaEventCreateWithFlags(&p->ev_ready[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_free[i], cudaEventDisableTiming);
     }
     cudaSetDevice(prev);
-#if TALFE_WS_WCONST
-    if (e != cudaSuccess || p->ctas_per_sm < 1) wconst_release(device, p->w_slot);
-#endif
     if (e != cudaSuccess) { if (p->blob_dev) cudaFree(p->blob_dev); delete p; return cuda_fail(e); }
     if (p->ctas_per_sm < 1) { cudaFree(p->blob_dev); delete p; return TALFE_ERR_UNSUPPORTED; }
     *plan_out = p;
@@ -825,9 +776,6 @@ int talfe_plan_create(talfe_plan** plan_out, int device, int n_mels, const float
 
 void talfe_plan_destroy(talfe_plan* plan) {
     if (!plan) return;
-#if TALFE_WS_WCONST
-    wconst_release(plan->device, plan->w_slot);
-#endif
     if (plan->blob_dev) cudaFree(plan->blob_dev);
     if (plan->copy_stream) cudaStreamDestroy(plan->copy_stream);
     for (int i = 0; i < 2; ++i) {
@@ -899,7 +847,6 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
 
     a.off_w_ws = (int)plan->off_w_ws; a.off_lo_ws = (int)plan->off_lo_ws;
     a.l2_prefetch = plan->l2_prefetch;
-    a.w_slot = plan->w_slot;
     a.out_align_ok = ((reinterpret_cast<uintptr_t>(job->out) & 15) == 0 && (ors & 3) == 0) ? 1 : 0;
     long long grid = use_ws ? (long long)plan->sm_count : (long long)plan->sm_count * plan->ctas_per_sm;
     if (grid > w.n_tiles) grid = w.n_tiles;

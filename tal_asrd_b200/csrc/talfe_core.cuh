@@ -44,12 +44,6 @@
 #define TALFE_HD __host__ __device__ __forceinline__
 #endif
 
-// Which packed-operand forms the ws kernel uses (bit 1 FFT rotations, 2 stage-1 store, 3 mel + log):
-// all of them; single bits are build-time experiments (bisection of bit-exactness against the scalar forms).
-#ifndef TALFE_PK
-#define TALFE_PK 15
-#endif
-
 namespace talfe {
 
 constexpr int kNfft = 400;
@@ -507,7 +501,7 @@ TALFE_HD void stage1_ws_fft(const XT* __restrict__ p /* xg + j */, const float (
         const int ib = 20 * m + kHop + (20 * m + kHop >= kXBlock ? kSkew : 0);
         xin[m] = make_float2(x_to_float(p[ia]), x_to_float(p[ib]));
     }
-    fft20_windowed<(TALFE_PK & 2) != 0>(xin, win, z);                  // window taps as scalar-broadcast operands of FMUL2 / FFMA2
+    fft20_windowed<true>(xin, win, z);                  // window taps as scalar-broadcast operands of FMUL2 / FFMA2
 }
 
 // Stage 1, second half: untangle the two real-input transforms, twiddle by tw[k1-1] = W400^(j k1), write
@@ -521,30 +515,18 @@ TALFE_HD void stage1_ws_store(const cf (&z)[20], const cf (&tw)[10], cf* __restr
 #pragma unroll
     for (int k1 = 1; k1 < 10; ++k1) {
         const cf sm = cadd(z[k1], z[20 - k1]), df = csub(z[k1], z[20 - k1]);
-#if TALFE_PK & 4
         const cf w = tw[k1 - 1], iw = times_i(w);
         col[(2 * (k1 - 1)) * kWsERow] = cfma_ss(sm.x, w, df.y, iw);
         col[(2 * (k1 - 1) + 1) * kWsERow] = cfma_ss(sm.y, iw, df.x, w);
-#else
-        const cf aa = make_float2(sm.x, df.y);
-        const cf ab = make_float2(sm.y, -df.x);
-        col[(2 * (k1 - 1)) * kWsERow] = cmul(aa, tw[k1 - 1]);
-        const cf cb = cmul(ab, tw[k1 - 1]);
-        col[(2 * (k1 - 1) + 1) * kWsERow] = make_float2(-cb.y, cb.x);
-#endif
     }
-#if TALFE_PK & 4
     col[19 * kWsERow] = cfma_ss(z[10].x, tw[9], z[10].y, times_i(tw[9]));
-#else
-    col[19 * kWsERow] = cmul(z[10], tw[9]);
-#endif
 }
 
 // Stage 2 (consumer thread (g, r)): |FFT-20(row r)|^2 kept in registers until the power array is free.
 // Normal rows r < 18: pw[q] = (bin k1 + 20 q, bin (20 - k1) + 20 q) of frame r & 1, k1 = 1 + r / 2.
 TALFE_HD void stage2_ws_power_normal(cf (&v)[20], cf (&pw)[10]) {
 #if !(defined(TALFE_ABLATE) && (TALFE_ABLATE & 4))
-    fft20<(TALFE_PK & 2) != 0>(v);
+    fft20<true>(v);
 #endif
 #pragma unroll
     for (int q = 0; q < 10; ++q)
@@ -561,7 +543,7 @@ TALFE_HD void stage2_ws_store_normal(int k1, const cf (&pw)[10], float* __restri
 }
 // Packed rows: r == 18 (zero = true) -> bins 20 (q + 1); r == 19 -> bins 10 + 20 q; both frames per entry.
 TALFE_HD void stage2_ws_power_special(bool zero, cf (&v)[20], cf (&pw)[10]) {
-    fft20<(TALFE_PK & 2) != 0>(v);
+    fft20<true>(v);
 #pragma unroll
     for (int q = 0; q < 10; ++q) {
         const cf p = zero ? v[q + 1] : v[q];
@@ -582,7 +564,6 @@ template <int W, int OFF>
 TALFE_HD void mel_slot_ws(const cf* __restrict__ p /* P + g + 16 lo */, const float (&w)[kRefWStride], float eps, float& ya, float& yb) {
     // both frames of the pair ride in one packed accumulator: FFMA2 with the weight as scalar-broadcast operand
     // (the same two IEEE fmas as the scalar form, half the issue slots)
-#if TALFE_PK & 8
     cf acc = make_float2(0.f, 0.f);
 #pragma unroll
     for (int r = 0; r < W; ++r) acc = cfma_s(w[OFF + r], p[kWsGroups * r], acc);
@@ -590,17 +571,6 @@ TALFE_HD void mel_slot_ws(const cf* __restrict__ p /* P + g + 16 lo */, const fl
     const cf y2 = fast_log2x(le);
     ya = y2.x;
     yb = y2.y;
-#else
-    float acc_a = 0.f, acc_b = 0.f;
-#pragma unroll
-    for (int r = 0; r < W; ++r) {
-        const cf pw = p[kWsGroups * r];
-        acc_a = fmaf(w[OFF + r], pw.x, acc_a);
-        acc_b = fmaf(w[OFF + r], pw.y, acc_b);
-    }
-    ya = fast_log(acc_a + eps);
-    yb = fast_log(acc_b + eps);
-#endif
 }
 TALFE_HD void mel_log_ws(const cf* __restrict__ pg /* P + g */, const float (&w)[kRefWStride], const int (&lo)[kMelSlots], float eps,
                          float (&y)[2 * kMelSlots]) {

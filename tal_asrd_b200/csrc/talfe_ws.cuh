@@ -34,36 +34,6 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
-__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
-    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-// TALFE_WS_NAMEDBAR (build-time experiment): the exchange hand-offs (E full / E empty) go through hardware named
-// barriers (arriving role: bar.arrive, waiting role: bar.sync, 640 threads each) instead of mbarriers, so that a
-// waiting warp is parked by the barrier unit and spends no issue slots on try_wait / nanosleep polling.  The
-// barrier's completion orders the arriving threads' prior shared-memory accesses before the waiters' later ones.
-#ifndef TALFE_WS_NAMEDBAR
-#define TALFE_WS_NAMEDBAR 0
-#endif
-// TALFE_WS_WCONST (build-time experiment): the consumers read their 28 mel weights from the constant bank (indexed
-// LDC, two distinct rows per warp) instead of shared memory: 8.75 of the 75 shared-memory wavefronts per frame.
-#ifndef TALFE_WS_WCONST
-#define TALFE_WS_WCONST 0
-#endif
-#ifndef TALFE_WS_TWREG
-#define TALFE_WS_TWREG 0
-#endif
-#ifndef TALFE_WS_WREG
-#define TALFE_WS_WREG 0
-#endif
-#ifndef TALFE_WS_COOPSTORE
-#define TALFE_WS_COOPSTORE 0
-#endif
-#if TALFE_WS_WCONST
-constexpr int kWConstSlots = 16;                                        // distinct filterbanks alive per device (35.8 KB of the bank)
-constexpr int kWConstVec = 20 * kRefWStride / 4;                        // float4 per slot
-__constant__ float4 c_w_ws[kWConstSlots * kWConstVec];
-#endif
-constexpr int kBarEFull = 4, kBarEEmpty = 6;                            // ids 4,5 / 6,7 (0: __syncthreads, 1: consumers, 2: producers)
 __device__ __forceinline__ void bulk_s2g(void* gmem_dst, unsigned smem_src, unsigned bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_src), "r"(bytes) : "memory");
 }
@@ -150,16 +120,6 @@ __device__ __forceinline__ void ws_producer(const KernelArgs& a, unsigned char* 
     load_window(j, a.win_global, XLayout<XT>::kScale, win);            // once per CTA, straight from global memory
     const cf* s_tw = reinterpret_cast<const cf*>(smem + a.off_tw) + j * 10;
     cf tw[10];
-#if TALFE_WS_TWREG
-    // build-time experiment: the 10 twiddles live in registers for the whole tile loop (6.25 fewer shared-memory
-    // wavefronts per frame, 20 more live registers in the producers)
-#pragma unroll
-    for (int h = 0; h < 5; ++h) {
-        const float4 tt = reinterpret_cast<const float4*>(s_tw)[h];
-        tw[2 * h] = make_float2(tt.x, tt.y);
-        tw[2 * h + 1] = make_float2(tt.z, tt.w);
-    }
-#endif
     const XT* xg = s_x0 + kXG * g1 + j;
     cf* col0 = s_e0 + ws_e_base(g1) + j;
     // Loader duty, taken in turn by the producer warps (tile kk by warp kk % 10, one tile ahead of the FFTs): all 32
@@ -240,30 +200,19 @@ __device__ __forceinline__ void ws_producer(const KernelArgs& a, unsigned char* 
         if (lane == 0) mbar_arrive(x_empty + buf);                      // this warp no longer reads x[buf]
         __syncwarp();
         // every tile, active or not: a producer never runs more than one phase ahead of the consumers
-#if TALFE_WS_NAMEDBAR
-        if (k >= 2) named_bar_sync(kBarEEmpty + buf, kWsThreads);       // consumers have loaded E[buf] of tile k-2
-#else
         if (k >= 2) mbar_wait_sleep(e_empty + buf, ((k - 2) >> 1) & 1); // consumers have loaded E[buf] of tile k-2
-#endif
         if (active) {
-#if !TALFE_WS_TWREG
 #pragma unroll
             for (int h = 0; h < 5; ++h) {
                 const float4 tt = reinterpret_cast<const float4*>(s_tw)[h];
                 tw[2 * h] = make_float2(tt.x, tt.y);
                 tw[2 * h + 1] = make_float2(tt.z, tt.w);
             }
-#endif
             stage1_ws_store(z, tw, col0 + buf * kWsECf);
         }
-#if TALFE_WS_NAMEDBAR
-        __syncwarp();
-        named_bar_arrive(kBarEFull + buf, kWsThreads);
-#else
         __syncwarp();
         if (lane == 0) mbar_arrive(e_full + buf);
         __syncwarp();
-#endif
     }
 }
 
@@ -278,19 +227,6 @@ __device__ __forceinline__ bool ws_store_tile(const KernelArgs& a, const WsDesc*
     return false;                                                        // timing experiment only: features never leave shared memory
 #endif
     const int flags = dp->flags;
-#if TALFE_WS_COOPSTORE
-    // build-time experiment: full tiles leave by two coalesced 16-byte loads + stores per thread (the tile is one
-    // contiguous 10 240-byte block of a [.., T, 80] output) instead of bulk copies: no proxy fence, no bulk waits
-    if (flags & kWsBulkY) {
-        const int fr = tid / 20, c4 = tid - 20 * fr;                    // 640 float4 per tile, 320 threads
-        const float4 v0 = *reinterpret_cast<const float4*>(s_y + ws_y_off(fr) + 4 * c4);
-        const float4 v1 = *reinterpret_cast<const float4*>(s_y + ws_y_off(fr + 16) + 4 * c4);
-        float4* dst = reinterpret_cast<float4*>(dp->out_tile) + tid;
-        dst[0] = v0;
-        dst[kWsRoleThreads] = v1;
-        return false;
-    }
-#endif
     if (flags & kWsBulkY) {
         if ((tid & 31) == 0) {
             const int w = tid >> 5;
@@ -351,11 +287,7 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, unsigned char* 
 #else
     const bool special = r >= 18;                                       // warp 9: the packed rows, both frames
 #endif
-#if TALFE_WS_WCONST
-    const float4* s_w4 = c_w_ws + a.w_slot * kWConstVec + r * (kRefWStride / 4);
-#else
     const float4* s_w4 = reinterpret_cast<const float4*>(smem + a.off_w_ws) + r * (kRefWStride / 4);
-#endif
     int lo[kMelSlots];
 #pragma unroll
     for (int i = 0; i < kMelSlots; ++i) lo[i] = reinterpret_cast<const int*>(smem + a.off_lo_ws)[i * 20 + r];
@@ -364,14 +296,6 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, unsigned char* 
     float* yb0 = s_y0 + (mt ? ws_yt_off(r, 2 * g) : ws_y_off(2 * g) + r);
     const int k1 = 1 + (r >> 1);
     double acc_s = 0.0, acc_q = 0.0;
-#if TALFE_WS_WREG
-    float w[kRefWStride];                                               // build-time experiment: mel weights live in registers
-#pragma unroll
-    for (int q = 0; q < kRefWStride / 4; ++q) {
-        const float4 t = s_w4[q];
-        w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
-    }
-#endif
 
     // Per tile k (buffers b = k & 1):  E[b] -> registers -> FFT-20 -> power -> P[b]  |barrier|  store of tile k-1 from
     // Y[b^1] issued, mel stage P[b] -> Y[b].  Hazards the single barrier covers: every warp arriving at barrier(k) has
@@ -382,22 +306,13 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, unsigned char* 
         const int buf = k & 1;
         const WsDesc* dp = s_desc + (k & (kWsDescRing - 1));
         cf v[20];
-#if TALFE_WS_NAMEDBAR
-        named_bar_sync(kBarEFull + buf, kWsThreads);
-#else
         mbar_wait_sleep(e_full + buf, (k >> 1) & 1);
-#endif
         const int flags = dp->flags;
         const bool active = flags & kWsActive;
         if (active) stage2_load(e_row0 + buf * kWsECf, v);
-#if TALFE_WS_NAMEDBAR
-        __syncwarp();
-        if (k + 2 < n_my) named_bar_arrive(kBarEEmpty + buf, kWsThreads);   // only arrivals a producer will wait for
-#else
         __syncwarp();
         if (lane == 0) mbar_arrive(e_empty + buf);
         __syncwarp();
-#endif
         cf* s_p = s_p0 + buf * kWsPCf;
         if (active) {
             cf pw[10];
@@ -409,23 +324,19 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, unsigned char* 
                 stage2_ws_store_special(r == 18, pw, s_p + g);
             }
         }
-#if !TALFE_WS_COOPSTORE
         if (lane == 0) bulk_wait_read<0>();                             // this lane's store of tile k-2 has finished reading Y[buf]
-#endif
 #if !(defined(TALFE_ABLATE) && (TALFE_ABLATE & 64))                     // (64: timing experiment only, racy: no consumer barrier)
         named_bar_sync(1, kWsRoleThreads);                              // P[buf](k) and Y[buf^1](k-1) complete
 #endif
         if (k >= 1) ws_store_tile(a, s_desc + ((k - 1) & (kWsDescRing - 1)), s_y0 + (buf ^ 1) * kWsYFloats, tid);
         float sum = 0.f, sumsq = 0.f;
         if (active) {
-#if !TALFE_WS_WREG
             float w[kRefWStride];
 #pragma unroll
             for (int q = 0; q < kRefWStride / 4; ++q) {
                 const float4 t = s_w4[q];
                 w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
             }
-#endif
             float y[2 * kMelSlots];
 #if defined(TALFE_ABLATE) && (TALFE_ABLATE & 1)
 #pragma unroll
@@ -467,9 +378,7 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, unsigned char* 
                 }
             }
         }
-#if !TALFE_WS_COOPSTORE
         fence_proxy_async();                                            // Y[buf] writes -> visible to the bulk-copy engine
-#endif
         if (a.partials_per_tile) {
             double ds = (double)sum, dq = (double)sumsq;
 #pragma unroll
@@ -486,194 +395,6 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, unsigned char* 
     }
     named_bar_sync(1, kWsRoleThreads);
     if (n_my >= 1) ws_store_tile(a, s_desc + ((n_my - 1) & (kWsDescRing - 1)), s_y0 + ((n_my - 1) & 1) * kWsYFloats, tid);
-    if (!a.partials_per_tile) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            acc_s += __shfl_xor_sync(0xffffffffu, acc_s, o);
-            acc_q += __shfl_xor_sync(0xffffffffu, acc_q, o);
-        }
-        double2* s_red = reinterpret_cast<double2*>(s_p0);              // the power arrays are free after the last barrier
-        if (lane == 0) s_red[warp] = make_double2(acc_s, acc_q);
-        named_bar_sync(1, kWsRoleThreads);
-        if (tid == 0) {
-            double ts = 0.0, tq2 = 0.0;
-            for (int w2 = 0; w2 < kWsRoleWarps; ++w2) { ts += s_red[w2].x; tq2 += s_red[w2].y; }
-            a.partials[blockIdx.x] = make_double2(ts, tq2);
-        }
-    }
-    if (lane == 0) bulk_wait_all<0>();                                  // shared memory must outlive the copies that read it
-}
-
-// TALFE_WS_SWP: software-pipelined consumers.  Iteration k runs the mel stage of tile k-1 (shared-memory bound: 33
-// loads per thread) and stage 2 of tile k (FP bound: FFT-20 + power, registers only) in ONE straight-line region, so
-// that the scheduler overlaps the two inside every warp instead of the role alternating between a shared-memory
-// phase and an FP phase.  Still one barrier per iteration:
-//   wait E[b](k) -> registers, release E[b] | mel(k-1): P[b^1] -> Y[b^1]  ||  FFT(k), power | P[b] <- power(k)
-//   | fence, barrier(k) | bulk store of tile k-1 from Y[b^1]
-// Hazards: P[b^1] is read by mel(k-1) in iteration k and next written by stage 2 of tile k+1 after barrier(k);
-// P[b] was last read by mel(k-2) before barrier(k-1); Y[b^1] was last read by the store of tile k-3, issued after
-// barrier(k-2), whose lanes wait for their reads before barrier(k-1); the store of tile k-1 follows barrier(k).
-#ifndef TALFE_WS_SWP
-#define TALFE_WS_SWP 0
-#endif
-template <typename XT>
-__device__ __forceinline__ void ws_consumer_swp(const KernelArgs& a, unsigned char* smem, const cf* s_e0, cf* s_p0, float* s_y0,
-                                                const WsDesc* s_desc, unsigned long long* s_bar, const int tid, const int n_my) {
-    unsigned long long* e_full = s_bar + 4;
-    unsigned long long* e_empty = s_bar + 6;
-    const int warp = tid >> 5, lane = tid & 31;
-    const int g = tid & (kWsGroups - 1), r = tid >> 4;
-    const bool special = r >= 18;
-    const float4* s_w4 = reinterpret_cast<const float4*>(smem + a.off_w_ws) + r * (kRefWStride / 4);
-    int lo[kMelSlots];
-#pragma unroll
-    for (int i = 0; i < kMelSlots; ++i) lo[i] = reinterpret_cast<const int*>(smem + a.off_lo_ws)[i * 20 + r];
-    const cf* e_row0 = s_e0 + ws_e_base(g) + r * kWsERow;
-    const bool mt = a.out_layout == TALFE_LAYOUT_MT;
-    float* yb0 = s_y0 + (mt ? ws_yt_off(r, 2 * g) : ws_y_off(2 * g) + r);
-    const int k1 = 1 + (r >> 1);
-    double acc_s = 0.0, acc_q = 0.0;
-
-    // mel stage of tile kp (its power array and feature tile are the buffers kp & 1)
-    auto mel_tile = [&](int kp, float& sum, float& sumsq) {
-        const WsDesc* dq = s_desc + (kp & (kWsDescRing - 1));
-        const int pflags = dq->flags;
-        const cf* s_p = s_p0 + (kp & 1) * kWsPCf;
-        float w[kRefWStride];
-#pragma unroll
-        for (int q = 0; q < kRefWStride / 4; ++q) {
-            const float4 t = s_w4[q];
-            w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
-        }
-        float y[2 * kMelSlots];
-        mel_log_ws(s_p + g, w, lo, a.eps, y);
-        float* yb = yb0 + (kp & 1) * kWsYFloats;
-        if (!mt) {
-#pragma unroll
-            for (int i = 0; i < kMelSlots; ++i) {
-                yb[20 * i] = y[2 * i];
-                yb[kMaxMels + 20 * i] = y[2 * i + 1];
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < kMelSlots; ++i) {
-                yb[20 * i * kWsYtStride] = y[2 * i];
-                yb[20 * i * kWsYtStride + 1] = y[2 * i + 1];
-            }
-        }
-        if (pflags & kWsFull) {
-#pragma unroll
-            for (int i = 0; i < 2 * kMelSlots; ++i) {
-                sum += y[i];
-                if (a.want_sumsq) sumsq = fmaf(y[i], y[i], sumsq);
-            }
-        } else {
-            const int ta = dq->t0 + 2 * g, t_end = dq->t_end;
-#pragma unroll
-            for (int f = 0; f < 2; ++f) {
-                if (ta + f < t_end) {
-#pragma unroll
-                    for (int i = 0; i < kMelSlots; ++i) {
-                        sum += y[2 * i + f];
-                        if (a.want_sumsq) sumsq = fmaf(y[2 * i + f], y[2 * i + f], sumsq);
-                    }
-                }
-            }
-        }
-    };
-    // stage 2 of the tile whose exchange rows sit in v: FFT-20, power, into the power array s_p
-    auto stage2_tile = [&](cf (&v)[20], cf* s_p) {
-        cf pw[10];
-        if (!special) {
-            stage2_ws_power_normal(v, pw);
-            stage2_ws_store_normal(k1, pw, reinterpret_cast<float*>(s_p) + 2 * g + (r & 1));
-        } else {
-            stage2_ws_power_special(r == 18, v, pw);
-            stage2_ws_store_special(r == 18, pw, s_p + g);
-        }
-    };
-
-    // Steady state (previous tile full, [.., T, 80] layout, normal rows): the mel stage of tile k-1 and stage 2 of tile
-    // k written as ONE branch-free region, the two streams alternating in the source so that the scheduler keeps both
-    // the shared-memory pipe and the FP pipe busy.  Same arithmetic, same order of operations per value.
-    auto fused_tile = [&](int kp, cf (&v)[20], cf* s_p, float& sum, float& sumsq) {
-        constexpr bool kPk = (TALFE_PK & 2) != 0;
-        const cf* pg = s_p0 + (kp & 1) * kWsPCf + g;
-        float w[kRefWStride];
-#pragma unroll
-        for (int q = 0; q < kRefWStride / 4; ++q) {
-            const float4 t4 = s_w4[q];
-            w[4 * q] = t4.x; w[4 * q + 1] = t4.y; w[4 * q + 2] = t4.z; w[4 * q + 3] = t4.w;
-        }
-        float y[2 * kMelSlots];
-        cf t[4][5];
-        mel_slot_ws<kRefW0, 0>(pg + kWsGroups * lo[0], w, a.eps, y[0], y[1]);
-        mel_slot_ws<kRefW1, kRefW0>(pg + kWsGroups * lo[1], w, a.eps, y[2], y[3]);
-        fft20_fft4s<kPk>(v, t);
-        mel_slot_ws<kRefW2, kRefW0 + kRefW1>(pg + kWsGroups * lo[2], w, a.eps, y[4], y[5]);
-        fft20_dft5s<kPk>(t, v);
-        mel_slot_ws<kRefW3, kRefW0 + kRefW1 + kRefW2>(pg + kWsGroups * lo[3], w, a.eps, y[6], y[7]);
-        cf pw[10];
-#pragma unroll
-        for (int q = 0; q < 10; ++q)
-            pw[q] = make_float2(fmaf(v[q].x, v[q].x, v[q].y * v[q].y), fmaf(v[19 - q].x, v[19 - q].x, v[19 - q].y * v[19 - q].y));
-        float* yb = yb0 + (kp & 1) * kWsYFloats;
-#pragma unroll
-        for (int i = 0; i < kMelSlots; ++i) {
-            yb[20 * i] = y[2 * i];
-            yb[kMaxMels + 20 * i] = y[2 * i + 1];
-        }
-        stage2_ws_store_normal(k1, pw, reinterpret_cast<float*>(s_p) + 2 * g + (r & 1));
-#pragma unroll
-        for (int i = 0; i < 2 * kMelSlots; ++i) {
-            sum += y[i];
-            sumsq = fmaf(y[i], y[i], sumsq);                            // only read when statistics want it
-        }
-    };
-
-    for (int k = 0; k <= n_my; ++k) {
-        const int buf = k & 1;
-        const bool have_cur = k < n_my;
-        cf v[20];
-        bool act_cur = false;
-        if (have_cur) {
-            mbar_wait_sleep(e_full + buf, (k >> 1) & 1);
-            act_cur = s_desc[k & (kWsDescRing - 1)].flags & kWsActive;
-            if (act_cur) stage2_load(e_row0 + buf * kWsECf, v);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(e_empty + buf);
-            __syncwarp();
-        }
-        const bool act_prev = k >= 1 && (s_desc[(k - 1) & (kWsDescRing - 1)].flags & kWsActive);
-        float sum = 0.f, sumsq = 0.f;
-        cf* s_p = s_p0 + buf * kWsPCf;
-        const bool full_prev = k >= 1 && (s_desc[(k - 1) & (kWsDescRing - 1)].flags & kWsFull);
-        if (act_prev && act_cur && full_prev && !mt && !special) {
-            fused_tile(k - 1, v, s_p, sum, sumsq);
-        } else {
-            if (act_prev) mel_tile(k - 1, sum, sumsq);
-            if (act_cur) stage2_tile(v, s_p);
-        }
-        if (k >= 1) {
-            if (a.partials_per_tile) {
-                double ds = (double)sum, dq = (double)sumsq;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    ds += __shfl_xor_sync(0xffffffffu, ds, o);
-                    dq += __shfl_xor_sync(0xffffffffu, dq, o);
-                }
-                const long long tile = (long long)blockIdx.x + (long long)(k - 1) * gridDim.x;
-                if (lane == 0) a.partials[tile * kWsRoleWarps + warp] = make_double2(ds, dq);
-            } else {
-                acc_s += (double)sum;
-                acc_q += (double)sumsq;
-            }
-        }
-        if (lane == 0) bulk_wait_read<0>();                             // this lane's store of tile k-3 has finished reading Y[buf^1]
-        fence_proxy_async();                                            // Y[buf^1] writes of mel(k-1) -> visible to the bulk-copy engine
-        named_bar_sync(1, kWsRoleThreads);                              // P[buf](k) and Y[buf^1](k-1) complete
-        if (k >= 1) ws_store_tile(a, s_desc + ((k - 1) & (kWsDescRing - 1)), s_y0 + (buf ^ 1) * kWsYFloats, tid);
-    }
     if (!a.partials_per_tile) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -720,11 +441,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) logmel_ws_kernel(const KernelAr
     cudaGridDependencySynchronize();
     const int n_my = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles blockIdx.x, + gridDim.x, ...
     if (tid < kWsRoleThreads) ws_producer<XT>(a, smem, s_x0, s_e0, s_desc, s_bar, tid, n_my);
-#if TALFE_WS_SWP
-    else ws_consumer_swp<XT>(a, smem, s_e0, s_p0, s_y0, s_desc, s_bar, tid - kWsRoleThreads, n_my);
-#else
     else ws_consumer<XT>(a, smem, s_e0, s_p0, s_y0, s_desc, s_bar, tid - kWsRoleThreads, n_my);
-#endif
 }
 
 constexpr size_t ws_smem_bytes(size_t table_bytes) {

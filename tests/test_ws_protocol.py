@@ -10,6 +10,10 @@ Two protocols are modelled:
     producer warps send tile k at their iteration k + 3, with y_full / y_empty / c_done.  Its first version hung on
     the GPU; this model reproduced the hang (a parity wait for the last tile passing two phases early in the drain)
     and validated the fix before more GPU time was spent, which is why it stays here.
+  * ``handoff="named"`` — another experiment measured and not adopted (102 us against 84 us): the E full /
+    E empty hand-offs on hardware named barriers (bar.arrive by one role, bar.sync by the other).  The model showed
+    it live and safe before the GPU run; the measurement showed that parking every warp of a role on one barrier
+    removes the slack the mbarrier version leaves between warps.
 (Host-side logic only; the arithmetic has its own tests.)"""
 import random
 
