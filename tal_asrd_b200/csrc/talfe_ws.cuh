@@ -5,16 +5,17 @@
 //                            warp k % 10) also the loader: tile descriptor, TMA fetch of the waveform tile one tile
 //                            ahead (double-buffered), L2 prefetch two tiles ahead
 //   warps 10..19  CONSUMERS  exchange E -> FFT-20 -> power P -> mel projection -> log -> staged feature tile Y
-//                            -> cp.async.bulk store to global memory (640 bytes per frame pair)
+//                            -> cp.async.bulk store to global memory (640 bytes per frame pair); TWO groups of 5 warps
+//                            on alternate tiles (group q owns E[q], P[q], Y[q]), two exchange rows per thread
 // (a 21st warp for the loader would cost 16 registers per thread: 6 warps on one scheduler's 16K-register file)
 // Producers keep their 20 window taps in registers; twiddles (5 LDS.128 per tile) and mel weights (7 LDS.128 per
-// tile) are re-read from shared memory, which measured faster than holding them in registers (B200, A/B in
-// profiles/r01_ab_v7_ws_vs_legacy.json: register pressure in the FFT costs more than the loads).  The roles meet
-// through mbarriers (x_full / x_empty / e_full / e_empty, two buffers each); the consumers synchronise among
-// themselves with ONE named barrier per tile (id 1; the power array is double-buffered, so "P free" needs no
-// barrier of its own); there is no CTA-wide barrier inside the tile loop.  Because the FP-heavy stage 1 and the
-// shared-memory-heavy stage 2 / mel stage now run in different warps, the SM's schedulers overlap them
-// instruction by instruction instead of phase by phase.
+// tile and mel lane) are re-read from shared memory, which measured faster than holding them in registers (B200,
+// profiles/r01_ab_v7_ws_vs_legacy.json, profiles/r01_ab_v9_variants.json: register pressure in the FFT costs more
+// than the loads).  The roles meet through mbarriers (x_full / x_empty / e_full / e_empty, two buffers each); each
+// consumer group synchronises within itself with two named barriers per tile (ids 1 / 3, 160 threads); there is no
+// CTA-wide barrier inside the tile loop.  The FP-heavy and the shared-memory-heavy phases of the three concurrent
+// streams (producers, consumer group 0, consumer group 1) drift apart, so the SM's schedulers overlap them warp by
+// warp; overlapping them INSIDE a warp (one fused instruction stream) measured slower, DESIGN.md §4.
 //
 // Shared-memory layouts and their bank-conflict properties: talfe_core.cuh ("Warp-specialised path").
 // Arithmetic is identical to the legacy kernel (same functions for the FFT, untangle, power, mel and log).
@@ -222,19 +223,20 @@ __device__ __forceinline__ void ws_producer(const KernelArgs& a, unsigned char* 
 // hardware interface, so they are spread over the warps); everything else (partial tiles, zero fill of frames
 // beyond a row's own length, [.., 80, T] layout, unaligned output) takes the cooperative element-wise path.
 // Returns whether bulk copies were issued.
+// kNT threads (kNT / 32 warps) cooperate: the whole consumer role, or one of its two groups.
+template <int kNT = kWsRoleThreads>
 __device__ __forceinline__ bool ws_store_tile(const KernelArgs& a, const WsDesc* dp, const float* s_y, int tid) {
+    constexpr int kNW = kNT / 32;
 #if defined(TALFE_ABLATE) && (TALFE_ABLATE & 8)
     return false;                                                        // timing experiment only: features never leave shared memory
 #endif
     const int flags = dp->flags;
     if (flags & kWsBulkY) {
         if ((tid & 31) == 0) {
-            const int w = tid >> 5;
             float* dst = dp->out_tile;
-            bulk_s2g(dst + 2 * w * kMaxMels, smem_u32(s_y + ws_y_off(2 * w)), 2 * kMaxMels * (unsigned)sizeof(float));
-            if (w + kWsRoleWarps < kWsGroups)
-                bulk_s2g(dst + 2 * (w + kWsRoleWarps) * kMaxMels, smem_u32(s_y + ws_y_off(2 * (w + kWsRoleWarps))),
-                         2 * kMaxMels * (unsigned)sizeof(float));
+#pragma unroll
+            for (int w = tid >> 5; w < kWsGroups; w += kNW)
+                bulk_s2g(dst + 2 * w * kMaxMels, smem_u32(s_y + ws_y_off(2 * w)), 2 * kMaxMels * (unsigned)sizeof(float));
             bulk_commit();
         }
         __syncwarp();
@@ -252,12 +254,12 @@ __device__ __forceinline__ bool ws_store_tile(const KernelArgs& a, const WsDesc*
             const int f = tid & 31;
             const float keep = (active && t.t0 + f < t.t_end) ? 1.f : 0.f;
 #pragma unroll
-            for (int q = 0; q < kMaxMels * kWsFrames / kWsRoleThreads; ++q) {
-                const int m = (tid >> 5) + q * kWsRoleWarps;
+            for (int q = 0; q < kMaxMels * kWsFrames / kNT; ++q) {
+                const int m = (tid >> 5) + q * kNW;
                 dst[(long long)m * a.n_frames + f] = keep != 0.f ? s_y[ws_yt_off(m, f)] : 0.f;
             }
         } else {
-            for (int i = tid; i < nfr * kMaxMels; i += kWsRoleThreads) {
+            for (int i = tid; i < nfr * kMaxMels; i += kNT) {
                 const int m = i / nfr, f = i - m * nfr;
                 const bool valid = active && t.t0 + f < t.t_end;
                 dst[(long long)m * a.n_frames + f] = valid ? s_y[ws_yt_off(m, f)] : 0.f;
@@ -265,7 +267,7 @@ __device__ __forceinline__ bool ws_store_tile(const KernelArgs& a, const WsDesc*
         }
         return false;
     }
-    for (int i = tid; i < nfr * kMaxMels; i += kWsRoleThreads) {
+    for (int i = tid; i < nfr * kMaxMels; i += kNT) {
         const int f = i / kMaxMels, m = i - f * kMaxMels;
         const int t_abs = t.t0 + f;
         const bool valid = active && t_abs < t.t_end;
@@ -275,110 +277,124 @@ __device__ __forceinline__ bool ws_store_tile(const KernelArgs& a, const WsDesc*
     return false;
 }
 
+// The consumer role runs as TWO groups of 5 warps on alternate tiles (group q takes
+// tiles q, q + 2, ...; buffers E[q], P[q], Y[q] are its own), every thread running two exchange rows (r0, r0 + 10) and
+// two mel lanes per tile.  The groups drift apart in phase, so that one group's shared-memory phases (exchange loads,
+// mel stage) can overlap the other's FP phase (FFT-20) across warps, which the hardware scheduler does for free and a
+// fused instruction stream inside one warp does not.  Two named barriers per tile and group (160 threads):
+//   wait E[q](k) | row r0 -> registers | A1: mel(k-2) done by all -> store of tile k-2 issued, P[q] free
+//   | FFT, power -> P[q] | row r0+10 -> registers, release E[q] | FFT, power -> P[q] | wait for the store's reads
+//   | A2: P[q](k) complete, Y[q] free | mel(k): P[q] -> Y[q] | fence
+// (measured against ONE group of 10 warps with one row per thread and one barrier per tile: 80.2 against 82.6 us;
+// the ablation switches 32 / 64 of that version went with it)
+constexpr int kCs2Threads = kWsRoleThreads / 2;                         // 160
 template <typename XT>
 __device__ __forceinline__ void ws_consumer(const KernelArgs& a, unsigned char* smem, const cf* s_e0, cf* s_p0, float* s_y0,
-                                            const WsDesc* s_desc, unsigned long long* s_bar, const int tid, const int n_my) {
-    unsigned long long* e_full = s_bar + 4;
-    unsigned long long* e_empty = s_bar + 6;
+                                                const WsDesc* s_desc, unsigned long long* s_bar, const int tid, const int n_my) {
+    const int grp = tid >= kCs2Threads ? 1 : 0;
+    const int gtid = tid - grp * kCs2Threads;
+    unsigned long long* e_full = s_bar + 4 + grp;
+    unsigned long long* e_empty = s_bar + 6 + grp;
     const int warp = tid >> 5, lane = tid & 31;
-    const int g = tid & (kWsGroups - 1), r = tid >> 4;                  // r: exchange row in stage 2, mel lane in the mel stage
-#if defined(TALFE_ABLATE) && (TALFE_ABLATE & 32)
-    const bool special = false;                                         // timing experiment only: no straggler warp at the barrier
-#else
-    const bool special = r >= 18;                                       // warp 9: the packed rows, both frames
-#endif
-    const float4* s_w4 = reinterpret_cast<const float4*>(smem + a.off_w_ws) + r * (kRefWStride / 4);
-    int lo[kMelSlots];
+    const int g = gtid & (kWsGroups - 1), r0 = gtid >> 4, r1 = r0 + 10;  // rows / mel lanes r0 (0..9) and r1 (10..19)
+    const bool special1 = r1 >= 18;                                     // the group's last warp: packed rows as its second item
+    const int bar_id = 1 + 2 * grp;                                     // 1 / 3 (2: producers' edge tiles, 4: all consumers)
+    const float4* s_w4a = reinterpret_cast<const float4*>(smem + a.off_w_ws) + r0 * (kRefWStride / 4);
+    const float4* s_w4b = reinterpret_cast<const float4*>(smem + a.off_w_ws) + r1 * (kRefWStride / 4);
+    int lo0[kMelSlots], lo1[kMelSlots];
 #pragma unroll
-    for (int i = 0; i < kMelSlots; ++i) lo[i] = reinterpret_cast<const int*>(smem + a.off_lo_ws)[i * 20 + r];
-    const cf* e_row0 = s_e0 + ws_e_base(g) + r * kWsERow;
+    for (int i = 0; i < kMelSlots; ++i) {
+        lo0[i] = reinterpret_cast<const int*>(smem + a.off_lo_ws)[i * 20 + r0];
+        lo1[i] = reinterpret_cast<const int*>(smem + a.off_lo_ws)[i * 20 + r1];
+    }
+    const cf* e_row0 = s_e0 + grp * kWsECf + ws_e_base(g) + r0 * kWsERow;
+    const cf* e_row1 = e_row0 + 10 * kWsERow;
+    cf* s_p = s_p0 + grp * kWsPCf;
+    float* s_y = s_y0 + grp * kWsYFloats;
     const bool mt = a.out_layout == TALFE_LAYOUT_MT;
-    float* yb0 = s_y0 + (mt ? ws_yt_off(r, 2 * g) : ws_y_off(2 * g) + r);
-    const int k1 = 1 + (r >> 1);
+    float* yb_a = s_y + (mt ? ws_yt_off(r0, 2 * g) : ws_y_off(2 * g) + r0);
+    float* yb_b = s_y + (mt ? ws_yt_off(r1, 2 * g) : ws_y_off(2 * g) + r1);
     double acc_s = 0.0, acc_q = 0.0;
 
-    // Per tile k (buffers b = k & 1):  E[b] -> registers -> FFT-20 -> power -> P[b]  |barrier|  store of tile k-1 from
-    // Y[b^1] issued, mel stage P[b] -> Y[b].  Hazards the single barrier covers: every warp arriving at barrier(k) has
-    // finished mel(k-1), so Y[b^1] is complete and P[b^1] is free for stage 2 of tile k+1; P[b] was last read by
-    // mel(k-2), which every warp finished before barrier(k-1); Y[b] was last read by the bulk store of tile k-2, whose
-    // issuing lanes wait for their reads before they arrive at barrier(k).
-    for (int k = 0; k < n_my; ++k) {
-        const int buf = k & 1;
-        const WsDesc* dp = s_desc + (k & (kWsDescRing - 1));
-        cf v[20];
-        mbar_wait_sleep(e_full + buf, (k >> 1) & 1);
-        const int flags = dp->flags;
-        const bool active = flags & kWsActive;
-        if (active) stage2_load(e_row0 + buf * kWsECf, v);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(e_empty + buf);
-        __syncwarp();
-        cf* s_p = s_p0 + buf * kWsPCf;
-        if (active) {
-            cf pw[10];
-            if (!special) {
-                stage2_ws_power_normal(v, pw);
-                stage2_ws_store_normal(k1, pw, reinterpret_cast<float*>(s_p) + 2 * g + (r & 1));
-            } else {
-                stage2_ws_power_special(r == 18, v, pw);
-                stage2_ws_store_special(r == 18, pw, s_p + g);
+    auto stage2_row = [&](cf (&v)[20], int r, bool special) {
+        cf pw[10];
+        if (!special) {
+            stage2_ws_power_normal(v, pw);
+            stage2_ws_store_normal(1 + (r >> 1), pw, reinterpret_cast<float*>(s_p) + 2 * g + (r & 1));
+        } else {
+            stage2_ws_power_special(r == 18, v, pw);
+            stage2_ws_store_special(r == 18, pw, s_p + g);
+        }
+    };
+    auto mel_lane = [&](const float4* s_w4, const int (&lo)[kMelSlots], float* yb, const WsDesc* dp, int flags, float& sum, float& sumsq) {
+        float w[kRefWStride];
+#pragma unroll
+        for (int q = 0; q < kRefWStride / 4; ++q) {
+            const float4 t = s_w4[q];
+            w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
+        }
+        float y[2 * kMelSlots];
+        mel_log_ws(s_p + g, w, lo, a.eps, y);
+        if (!mt) {
+#pragma unroll
+            for (int i = 0; i < kMelSlots; ++i) {
+                yb[20 * i] = y[2 * i];
+                yb[kMaxMels + 20 * i] = y[2 * i + 1];
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < kMelSlots; ++i) {
+                yb[20 * i * kWsYtStride] = y[2 * i];
+                yb[20 * i * kWsYtStride + 1] = y[2 * i + 1];
             }
         }
-        if (lane == 0) bulk_wait_read<0>();                             // this lane's store of tile k-2 has finished reading Y[buf]
-#if !(defined(TALFE_ABLATE) && (TALFE_ABLATE & 64))                     // (64: timing experiment only, racy: no consumer barrier)
-        named_bar_sync(1, kWsRoleThreads);                              // P[buf](k) and Y[buf^1](k-1) complete
-#endif
-        if (k >= 1) ws_store_tile(a, s_desc + ((k - 1) & (kWsDescRing - 1)), s_y0 + (buf ^ 1) * kWsYFloats, tid);
-        float sum = 0.f, sumsq = 0.f;
-        if (active) {
-            float w[kRefWStride];
+        if (flags & kWsFull) {
 #pragma unroll
-            for (int q = 0; q < kRefWStride / 4; ++q) {
-                const float4 t = s_w4[q];
-                w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
+            for (int i = 0; i < 2 * kMelSlots; ++i) {
+                sum += y[i];
+                if (a.want_sumsq) sumsq = fmaf(y[i], y[i], sumsq);
             }
-            float y[2 * kMelSlots];
-#if defined(TALFE_ABLATE) && (TALFE_ABLATE & 1)
+        } else {
+            const int ta = dp->t0 + 2 * g, t_end = dp->t_end;
 #pragma unroll
-            for (int i = 0; i < 2 * kMelSlots; ++i) y[i] = w[i] + s_p[g + 16 * lo[i & 3]].x;   // timing experiment only: no mel stage
-#else
-            mel_log_ws(s_p + g, w, lo, a.eps, y);
-#endif
-            float* yb = yb0 + buf * kWsYFloats;
-            if (!mt) {
+            for (int f = 0; f < 2; ++f) {
+                if (ta + f < t_end) {
 #pragma unroll
-                for (int i = 0; i < kMelSlots; ++i) {
-                    yb[20 * i] = y[2 * i];
-                    yb[kMaxMels + 20 * i] = y[2 * i + 1];
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < kMelSlots; ++i) {
-                    yb[20 * i * kWsYtStride] = y[2 * i];
-                    yb[20 * i * kWsYtStride + 1] = y[2 * i + 1];
-                }
-            }
-            if (flags & kWsFull) {
-#pragma unroll
-                for (int i = 0; i < 2 * kMelSlots; ++i) {
-                    sum += y[i];
-                    if (a.want_sumsq) sumsq = fmaf(y[i], y[i], sumsq);
-                }
-            } else {
-                const int ta = dp->t0 + 2 * g, t_end = dp->t_end;
-#pragma unroll
-                for (int f = 0; f < 2; ++f) {
-                    if (ta + f < t_end) {
-#pragma unroll
-                        for (int i = 0; i < kMelSlots; ++i) {
-                            sum += y[2 * i + f];
-                            if (a.want_sumsq) sumsq = fmaf(y[2 * i + f], y[2 * i + f], sumsq);
-                        }
+                    for (int i = 0; i < kMelSlots; ++i) {
+                        sum += y[2 * i + f];
+                        if (a.want_sumsq) sumsq = fmaf(y[2 * i + f], y[2 * i + f], sumsq);
                     }
                 }
             }
         }
-        fence_proxy_async();                                            // Y[buf] writes -> visible to the bulk-copy engine
+    };
+
+    int k_last = -1;
+    for (int k = grp; k < n_my; k += 2) {
+        const WsDesc* dp = s_desc + (k & (kWsDescRing - 1));
+        cf v[20];
+        mbar_wait_sleep(e_full, (k >> 1) & 1);
+        const int flags = dp->flags;
+        const bool active = flags & kWsActive;
+        if (active) stage2_load(e_row0, v);
+        named_bar_sync(bar_id, kCs2Threads);                            // A1: mel(k-2) finished everywhere
+        if (k >= 2) ws_store_tile<kCs2Threads>(a, s_desc + ((k - 2) & (kWsDescRing - 1)), s_y, gtid);
+        if (active) {
+            stage2_row(v, r0, false);
+            stage2_load(e_row1, v);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(e_empty);                            // both rows of E[grp] are in registers
+        __syncwarp();
+        if (active) stage2_row(v, r1, special1);
+        if (lane == 0) bulk_wait_read<0>();                             // this lane's store of tile k-2 has finished reading Y[grp]
+        named_bar_sync(bar_id, kCs2Threads);                            // A2: P[grp](k) complete, Y[grp] free
+        float sum = 0.f, sumsq = 0.f;
+        if (active) {
+            mel_lane(s_w4a, lo0, yb_a, dp, flags, sum, sumsq);
+            mel_lane(s_w4b, lo1, yb_b, dp, flags, sum, sumsq);
+        }
+        fence_proxy_async();                                            // Y[grp] writes -> visible to the bulk-copy engine
         if (a.partials_per_tile) {
             double ds = (double)sum, dq = (double)sumsq;
 #pragma unroll
@@ -387,23 +403,28 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, unsigned char* 
                 dq += __shfl_xor_sync(0xffffffffu, dq, o);
             }
             const long long tile = (long long)blockIdx.x + (long long)k * gridDim.x;
-            if (lane == 0) a.partials[tile * kWsRoleWarps + warp] = make_double2(ds, dq);
+            if (lane == 0) {                                            // 10 slots per tile: this group's 5 warps fill 5, zero the rest
+                a.partials[tile * kWsRoleWarps + (gtid >> 5)] = make_double2(ds, dq);
+                a.partials[tile * kWsRoleWarps + (gtid >> 5) + kWsRoleWarps / 2] = make_double2(0.0, 0.0);
+            }
         } else {
             acc_s += (double)sum;
             acc_q += (double)sumsq;
         }
+        k_last = k;
     }
-    named_bar_sync(1, kWsRoleThreads);
-    if (n_my >= 1) ws_store_tile(a, s_desc + ((n_my - 1) & (kWsDescRing - 1)), s_y0 + ((n_my - 1) & 1) * kWsYFloats, tid);
+    named_bar_sync(bar_id, kCs2Threads);
+    if (k_last >= 0) ws_store_tile<kCs2Threads>(a, s_desc + (k_last & (kWsDescRing - 1)), s_y, gtid);
     if (!a.partials_per_tile) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             acc_s += __shfl_xor_sync(0xffffffffu, acc_s, o);
             acc_q += __shfl_xor_sync(0xffffffffu, acc_q, o);
         }
-        double2* s_red = reinterpret_cast<double2*>(s_p0);              // the power arrays are free after the last barrier
+        named_bar_sync(4, kWsRoleThreads);                              // both groups are done with the power arrays
+        double2* s_red = reinterpret_cast<double2*>(s_p0);
         if (lane == 0) s_red[warp] = make_double2(acc_s, acc_q);
-        named_bar_sync(1, kWsRoleThreads);
+        named_bar_sync(4, kWsRoleThreads);
         if (tid == 0) {
             double ts = 0.0, tq2 = 0.0;
             for (int w2 = 0; w2 < kWsRoleWarps; ++w2) { ts += s_red[w2].x; tq2 += s_red[w2].y; }
@@ -429,7 +450,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) logmel_ws_kernel(const KernelAr
         mbar_init(s_bar + 0, 1); mbar_init(s_bar + 1, 1);                               // x_full: the loader's arrival (+ bytes)
         mbar_init(s_bar + 2, kWsRoleWarps); mbar_init(s_bar + 3, kWsRoleWarps);         // x_empty: one arrival per producer warp
         mbar_init(s_bar + 4, kWsRoleWarps); mbar_init(s_bar + 5, kWsRoleWarps);         // e_full
-        mbar_init(s_bar + 6, kWsRoleWarps); mbar_init(s_bar + 7, kWsRoleWarps);         // e_empty: one per consumer warp
+        mbar_init(s_bar + 6, kWsRoleWarps / 2); mbar_init(s_bar + 7, kWsRoleWarps / 2); // e_empty: the 5 warps of the buffer's consumer group
     }
     {
         const int4* src = reinterpret_cast<const int4*>(a.blob);

@@ -3,9 +3,12 @@ warps, mbarriers with the phase-parity semantics of mbarrier.try_wait.parity (a 
 barrier's current phase has the other parity — adjacent phases only) and the consumers' named barrier.  Random warp
 interleavings must neither deadlock nor let a buffer be read before it is complete or overwritten before it was read.
 
-Two protocols are modelled:
-  * ``stores="consumers"`` — the shipped kernel: x_full / x_empty / e_full / e_empty, the feature tile is sent by the
-    consumers after their barrier (Y hazards are then covered by program order + that barrier);
+Protocols modelled:
+  * ``run_two_groups`` — the shipped kernel: x_full / x_empty / e_full / e_empty, the consumers as two groups of five
+    warps on alternate tiles with two named barriers per tile and group;
+  * ``stores="consumers"`` — its predecessor (one consumer group of ten warps, one barrier per tile; 82.6 us against
+    80.2 us): the feature tile is sent by the consumers after their barrier (Y hazards are then covered by program
+    order + that barrier);
   * ``stores="producers"`` — an experiment measured on B200 and not adopted (87.1 us against 85.3 us):
     producer warps send tile k at their iteration k + 3, with y_full / y_empty / c_done.  Its first version hung on
     the GPU; this model reproduced the hang (a parity wait for the last tile passing two phases early in the drain)
@@ -182,6 +185,111 @@ def run(n_my, seed, stores="producers", handoff="mbar"):
 def test_pipeline_protocol_is_live_and_safe(n_my, stores):
     for seed in range(80):
         run(n_my, seed, stores)
+
+
+def run_two_groups(n_my, seed):
+    """The shipped kernel: consumers as two groups of 5 warps on alternate tiles (group q: tiles q, q + 2, ...; buffers
+    E[q], P[q], Y[q]; e_empty[q] counts the group's 5 warps), two named barriers per tile and group:
+    wait e_full | load row 0 | A1 | store of tile k-2, stage 2 -> P[q], load row 1, arrive e_empty | A2 | mel -> Y[q]."""
+    rnd = random.Random(seed)
+    G = W // 2
+    xf, xe = [MBar(1), MBar(1)], [MBar(W), MBar(W)]
+    ef, ee = [MBar(W), MBar(W)], [MBar(G), MBar(G)]
+    bars = [{"n": 0, "gen": 0}, {"n": 0, "gen": 0}]
+    x_tile, x_readers = [None, None], [0, 0]
+    e_tile, e_written, e_read = [None, None], [0, 0], [0, 0]
+    p_tile, p_written = [None, None], [0, 0]
+    mel_done, sent = {}, set()
+
+    def load_duty(kk):
+        if kk >= 2:
+            yield ("wait", xe[kk & 1], ((kk - 2) >> 1) & 1, f"x_empty({kk - 2})")
+        assert x_readers[kk & 1] == 0, "waveform tile overwritten while producers still read it"
+        x_tile[kk & 1], x_readers[kk & 1] = kk, W
+        xf[kk & 1].arrive()
+
+    def producer(w):
+        if w == 0:
+            yield from load_duty(0)
+        for k in range(n_my):
+            if k + 1 < n_my and (k + 1) % W == w:
+                yield from load_duty(k + 1)
+            yield ("wait", xf[k & 1], (k >> 1) & 1, f"x_full({k})")
+            assert x_tile[k & 1] == k
+            yield ("work",)
+            x_readers[k & 1] -= 1
+            xe[k & 1].arrive()
+            if k >= 2:
+                yield ("wait", ee[k & 1], ((k - 2) >> 1) & 1, f"e_empty({k - 2})")
+            if e_tile[k & 1] != k:
+                assert e_tile[k & 1] is None or e_read[k & 1] == G, "exchange buffer overwritten before it was read"
+                e_tile[k & 1], e_written[k & 1], e_read[k & 1] = k, 0, 0
+            yield ("work",)
+            e_written[k & 1] += 1
+            ef[k & 1].arrive()
+
+    def barrier(q):
+        b = bars[q]
+        gen = b["gen"]
+        b["n"] += 1
+        if b["n"] == G:
+            b["n"], b["gen"] = 0, b["gen"] + 1
+        return ("bar", b, gen)
+
+    def consumer(w):
+        q = w // G
+        k_last = -1
+        for k in range(q, n_my, 2):
+            yield ("wait", ef[q], (k >> 1) & 1, f"e_full({k})")
+            assert e_tile[q] == k and e_written[q] == W, "exchange buffer read before it was complete"
+            yield ("work",)                                 # row 0 -> registers
+            yield barrier(q)                                # A1
+            if k >= 2:
+                assert mel_done.get(k - 2, 0) == G, "tile sent before its mel stage finished"
+                sent.add(k - 2)
+            if p_tile[q] != k:
+                assert p_tile[q] is None or mel_done.get(p_tile[q], 0) == G, "power array overwritten while the mel stage reads it"
+                p_tile[q], p_written[q] = k, 0
+            yield ("work",)                                 # stage 2 row 0 -> P[q]; row 1 -> registers
+            e_read[q] += 1
+            ee[q].arrive()
+            yield ("work",)                                 # stage 2 row 1 -> P[q]
+            p_written[q] += 1
+            yield barrier(q)                                # A2
+            assert p_tile[q] == k and p_written[q] == G, "mel stage reads an incomplete power array"
+            if k >= 2:
+                assert (k - 2) in sent, "feature tile overwritten before it was sent"
+            yield ("work",)                                 # mel -> Y[q]
+            mel_done[k] = mel_done.get(k, 0) + 1
+            k_last = k
+        yield barrier(q)
+        if k_last >= 0:
+            assert mel_done.get(k_last, 0) == G
+            sent.add(k_last)
+
+    state = {}
+    for name, gen in [(f"P{w}", producer(w)) for w in range(W)] + [(f"C{w}", consumer(w)) for w in range(W)]:
+        try:
+            state[name] = (gen, next(gen))
+        except StopIteration:
+            pass
+    while state:
+        ready = [n for n, (_, c) in state.items()
+                 if c[0] == "work" or (c[0] == "wait" and c[1].passed(c[2])) or (c[0] == "bar" and c[1]["gen"] > c[2])]
+        assert ready, f"deadlock (n_my={n_my}, seed={seed}): " + str({n: c[-1] for n, (_, c) in state.items()})
+        name = rnd.choice(ready)
+        gen = state[name][0]
+        try:
+            state[name] = (gen, next(gen))
+        except StopIteration:
+            del state[name]
+    assert sent == set(range(n_my))
+
+
+@pytest.mark.parametrize("n_my", [1, 2, 3, 4, 5, 6, 7, 9, 10, 11, 13, 21, 41])
+def test_two_group_consumers_are_live_and_safe(n_my):
+    for seed in range(80):
+        run_two_groups(n_my, seed)
 
 
 @pytest.mark.parametrize("n_my", [1, 2, 3, 4, 5, 6, 7, 9, 10, 11, 13, 21, 41])
