@@ -105,6 +105,9 @@ __device__ __forceinline__ void ws_advance(const KernelArgs& a, int& row, int& t
 }
 
 // ------------------------------------------------------------------------------------------ producers
+// (ONE group of 10 warps, one frame pair per thread.  Splitting the producers into two groups on alternate tiles like
+// the consumers — two pairs per thread, x[q] / E[q] per group — measured 91.7 us against 80.2 us: each group then holds
+// its exchange buffer for two pairs' worth of work and the consumers wait for it.)
 template <typename XT>
 __device__ __forceinline__ void ws_producer(const KernelArgs& a, unsigned char* smem, XT* s_x0, cf* s_e0, WsDesc* s_desc,
                                             unsigned long long* s_bar, const int tid, const int n_my) {
@@ -213,110 +216,6 @@ __device__ __forceinline__ void ws_producer(const KernelArgs& a, unsigned char* 
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(e_full + buf);
-        __syncwarp();
-    }
-}
-
-
-// TALFE_WS_PS2 (build-time experiment): the producer role as TWO groups of 5 warps on alternate tiles, like the
-// consumers (group q owns x[q] and E[q]); every thread runs two frame pairs (g1, g1 + 8) per tile.  The group's
-// warps take the loader duty in turn: after the group has read x[q] of tile k, the loader fetches tile k + 2 into it.
-#ifndef TALFE_WS_PS2
-#define TALFE_WS_PS2 0
-#endif
-template <typename XT>
-__device__ __forceinline__ void ws_producer_ps2(const KernelArgs& a, unsigned char* smem, XT* s_x0, cf* s_e0, WsDesc* s_desc,
-                                                unsigned long long* s_bar, const int tid, const int n_my) {
-    constexpr int kGT = kWsRoleThreads / 2, kGW = kWsRoleWarps / 2;      // 160 threads, 5 warps per group
-    const int grp = tid >= kGT ? 1 : 0;
-    const int gtid = tid - grp * kGT;
-    unsigned long long* x_full = s_bar + grp;
-    unsigned long long* x_empty = s_bar + 2 + grp;
-    unsigned long long* e_full = s_bar + 4 + grp;
-    unsigned long long* e_empty = s_bar + 6 + grp;
-    const int gwarp = gtid >> 5, lane = tid & 31;
-    const int g1 = gtid / kGroup, j = gtid - g1 * kGroup;               // pairs g1 and g1 + 8
-    constexpr int kXG = XLayout<XT>::kGroup;
-    constexpr int kXBufBytes = kXFloats * (int)sizeof(float);
-
-    float win[20];
-    load_window(j, a.win_global, XLayout<XT>::kScale, win);
-    const cf* s_tw = reinterpret_cast<const cf*>(smem + a.off_tw) + j * 10;
-    XT* s_x = reinterpret_cast<XT*>(reinterpret_cast<unsigned char*>(s_x0) + grp * kXBufBytes);
-    const XT* xg_a = s_x + kXG * g1 + j;
-    const XT* xg_b = xg_a + kXG * 8;
-    cf* col_a = s_e0 + grp * kWsECf + ws_e_base(g1) + j;
-    cf* col_b = s_e0 + grp * kWsECf + ws_e_base(g1 + 8) + j;
-    const int step = (int)gridDim.x;
-    // loader duty for tile kk (kk = grp mod 2): descriptor, x[grp] free (tile kk-2 read by the whole group), fetch
-    auto load_duty = [&](int kk) {
-        const int tile = (int)blockIdx.x + kk * step;
-        const int row = tile / a.tiles_per_row, tq = tile - row * a.tiles_per_row;
-        long long src_off;
-        const WsDesc d = ws_describe(a, row, tq, src_off);
-        if (lane == 0) s_desc[kk & (kWsDescRing - 1)] = d;
-        if (kk >= 2) mbar_wait_sleep(x_empty, ((kk - 2) >> 1) & 1);
-        if (d.flags & kWsBulkX) {
-            const XT* src = reinterpret_cast<const XT*>(a.wave) + src_off;
-            if (lane == 0) mbar_expect_tx(x_full, kWsTileSamples * (int)sizeof(XT));
-            __syncwarp();
-            if (lane * kXBlock < kWsTileSamples)
-                bulk_g2s_u32(smem_u32(s_x + lane * kXG), src + lane * kXBlock,
-                             (unsigned)(min(kXBlock, kWsTileSamples - lane * kXBlock) * (int)sizeof(XT)), x_full,
-                             l2_evict_first_policy());
-        } else if (lane == 0) {
-            mbar_arrive(x_full);
-        }
-        __syncwarp();
-    };
-    auto load_twiddles = [&](cf (&tw)[10]) {
-#pragma unroll
-        for (int h = 0; h < 5; ++h) {
-            const float4 tt = reinterpret_cast<const float4*>(s_tw)[h];
-            tw[2 * h] = make_float2(tt.x, tt.y);
-            tw[2 * h + 1] = make_float2(tt.z, tt.w);
-        }
-    };
-    if (gwarp == 0 && grp < n_my) load_duty(grp);
-    int m = 0;                                                          // the group's m-th tile
-    for (int k = grp; k < n_my; k += 2, ++m) {
-        mbar_wait_sleep(x_full, (k >> 1) & 1);
-        const int flags = s_desc[k & (kWsDescRing - 1)].flags;
-        const bool active = flags & kWsActive;
-        cf z[20], tw[10];
-        if (active && !(flags & kWsBulkX)) {
-            // edge tile (reflection), unaligned row or chunk boundary: element-wise staging by the group
-            const WsDesc d = s_desc[k & (kWsDescRing - 1)];
-            const int s0 = kHop * d.t0 - kHalf;
-            const XT* rowp = reinterpret_cast<const XT*>(a.wave) + (long long)d.row * a.row_stride;
-            for (int i = gtid; i < kWsTileSamples; i += kGT) {
-                int g = s0 + i;
-                if (g < 0) g = -g;
-                if (g >= d.L) g = 2 * (d.L - 1) - g;
-                const int bi = g - a.origin;
-                XT v = XT(0.f);
-                if (g >= 0 && g < d.L && bi >= 0 && bi < a.buf_len) v = __ldg(rowp + bi);
-                s_x[xskew<XT>(i)] = v;
-            }
-            named_bar_sync(5 + grp, kGT);
-        }
-        if (active) stage1_ws_fft<XT>(xg_a, win, z);
-        if (k >= 2) mbar_wait_sleep(e_empty, ((k - 2) >> 1) & 1);       // the consumer group has loaded E[grp] of tile k-2
-        if (active) {
-            load_twiddles(tw);
-            stage1_ws_store(z, tw, col_a);
-            stage1_ws_fft<XT>(xg_b, win, z);
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(x_empty);                            // this warp no longer reads x[grp]
-        __syncwarp();
-        if (k + 2 < n_my && (m + 1) % kGW == gwarp) load_duty(k + 2);
-        if (active) {
-            load_twiddles(tw);
-            stage1_ws_store(z, tw, col_b);
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(e_full);
         __syncwarp();
     }
 }
@@ -552,13 +451,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) logmel_ws_kernel(const KernelAr
     const int tid = threadIdx.x;
     if (tid == 0) {
         mbar_init(s_bar + 0, 1); mbar_init(s_bar + 1, 1);                               // x_full: the loader's arrival (+ bytes)
-#if TALFE_WS_PS2
-        mbar_init(s_bar + 2, kWsRoleWarps / 2); mbar_init(s_bar + 3, kWsRoleWarps / 2); // x_empty: the 5 warps of the buffer's producer group
-        mbar_init(s_bar + 4, kWsRoleWarps / 2); mbar_init(s_bar + 5, kWsRoleWarps / 2); // e_full
-#else
         mbar_init(s_bar + 2, kWsRoleWarps); mbar_init(s_bar + 3, kWsRoleWarps);         // x_empty: one arrival per producer warp
         mbar_init(s_bar + 4, kWsRoleWarps); mbar_init(s_bar + 5, kWsRoleWarps);         // e_full
-#endif
         mbar_init(s_bar + 6, kWsRoleWarps / 2); mbar_init(s_bar + 7, kWsRoleWarps / 2); // e_empty: the 5 warps of the buffer's consumer group
     }
     {
@@ -570,11 +464,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) logmel_ws_kernel(const KernelAr
     __syncthreads();
     cudaGridDependencySynchronize();
     const int n_my = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles blockIdx.x, + gridDim.x, ...
-#if TALFE_WS_PS2
-    if (tid < kWsRoleThreads) ws_producer_ps2<XT>(a, smem, s_x0, s_e0, s_desc, s_bar, tid, n_my);
-#else
     if (tid < kWsRoleThreads) ws_producer<XT>(a, smem, s_x0, s_e0, s_desc, s_bar, tid, n_my);
-#endif
     else ws_consumer<XT>(a, smem, s_e0, s_p0, s_y0, s_desc, s_bar, tid - kWsRoleThreads, n_my);
 }
 
