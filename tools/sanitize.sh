@@ -19,7 +19,7 @@ s = stream_episode(mod, x[0].cpu().pin_memory(), chunk_seconds=1.7, device=dev)
 torch.cuda.synchronize()
 print('ok', float(y.abs().max()), float(z.abs().max()), float((s - mod(x[:1])).abs().max()))
 PY
-for tool in memcheck racecheck synccheck; do
-  timeout 900 compute-sanitizer --tool $tool python /tmp/san.py > gpurun_out/sanitizer_$tool.log 2>&1
+for tool in ${SAN_TOOLS:-memcheck racecheck synccheck}; do
+  timeout ${SAN_TIMEOUT:-900} compute-sanitizer --tool $tool python /tmp/san.py > gpurun_out/sanitizer_$tool.log 2>&1
   tail -4 gpurun_out/sanitizer_$tool.log
 done
