@@ -190,7 +190,7 @@ def test_pipeline_protocol_is_live_and_safe(n_my, stores):
 def run_two_groups(n_my, seed):
     """The shipped kernel: consumers as two groups of 5 warps on alternate tiles (group q: tiles q, q + 2, ...; buffers
     E[q], P[q], Y[q]; e_empty[q] counts the group's 5 warps), two named barriers per tile and group:
-    wait e_full | load row 0 | A1 | store of tile k-2, stage 2 -> P[q], load row 1, arrive e_empty | A2 | mel -> Y[q]."""
+    A1 | store of tile k-2 | wait e_full | load row 0, stage 2 -> P[q], load row 1, arrive e_empty | A2 | mel -> Y[q]."""
     rnd = random.Random(seed)
     G = W // 2
     xf, xe = [MBar(1), MBar(1)], [MBar(W), MBar(W)]
@@ -240,13 +240,13 @@ def run_two_groups(n_my, seed):
         q = w // G
         k_last = -1
         for k in range(q, n_my, 2):
-            yield ("wait", ef[q], (k >> 1) & 1, f"e_full({k})")
-            assert e_tile[q] == k and e_written[q] == W, "exchange buffer read before it was complete"
-            yield ("work",)                                 # row 0 -> registers
             yield barrier(q)                                # A1
             if k >= 2:
                 assert mel_done.get(k - 2, 0) == G, "tile sent before its mel stage finished"
                 sent.add(k - 2)
+            yield ("wait", ef[q], (k >> 1) & 1, f"e_full({k})")
+            assert e_tile[q] == k and e_written[q] == W, "exchange buffer read before it was complete"
+            yield ("work",)                                 # row 0 -> registers
             if p_tile[q] != k:
                 assert p_tile[q] is None or mel_done.get(p_tile[q], 0) == G, "power array overwritten while the mel stage reads it"
                 p_tile[q], p_written[q] = k, 0

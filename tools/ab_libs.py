@@ -45,12 +45,15 @@ def pick_candidate():
     best = min(ok, key=ok.get)
     res["_candidate"] = {"name": best, "kernel_us": ok[best], "default_kernel_us": ok[first]}
     with open(os.path.join(os.path.dirname(out_path) or ".", "cand.txt"), "w") as f:
-        f.write("" if best == first else [p for p in libs if os.path.basename(p) == best][0])
+        f.write("" if best == first else [p for p in libs if os.path.basename(p) == best][0].partition("@")[0])
 
 
 for rep in range(2):                                                    # two rounds: run-to-run spread per build
-    for path in libs:
-        name = os.path.basename(path)
+    for spec in libs:
+        path, _, env = spec.partition("@")                                # "lib.so@VAR=VALUE": plan-time environment switch
+        name = os.path.basename(spec)
+        for kv in (env.split(",") if env else []):
+            os.environ[kv.split("=")[0]] = kv.split("=")[1]
         _lib._LIB = None
         _build.LIB_PATH = os.path.abspath(path)
         lib = _lib.load()
@@ -72,6 +75,8 @@ for rep in range(2):                                                    # two ro
         r["max_abs_diff_vs_first"] = float((y - base).abs().max())
         r["kernel_us"].append(timeit(mod, "none"))
         r["forward_us"].append(timeit(mod, "batch"))
+        for kv in (env.split(",") if env else []):
+            os.environ.pop(kv.split("=")[0], None)
         pick_candidate()
         with open(out_path, "w") as f:
             json.dump(res, f, indent=1)
