@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TALFE_VERSION 101 /* major * 100 + minor */
+#define TALFE_VERSION 102 /* major * 100 + minor */
 
 typedef enum talfe_status {
     TALFE_OK = 0,
@@ -66,7 +66,9 @@ typedef struct talfe_plan talfe_plan; /* opaque: device-resident tables for one 
 
 /* Statistics block layout (doubles): [0] = element count, [1] = sum, [2] = sum of squares,
  * then per-mel sums [3 .. 3+M) and per-mel sums of squares [3+M .. 3+2M).  One block per row for
- * the ROW_* modes, one block in total for NONE / BATCH_MEAN. */
+ * the ROW_* modes, one block in total for NONE / BATCH_MEAN.
+ * The per-mel entries are WRITTEN ONLY by the ROW_MEL_* modes (they cost one extra pass over the features);
+ * NONE, BATCH_MEAN and ROW_MEAN fill entries [0..2] and leave the rest untouched. */
 #define TALFE_STATS_DOUBLES(n_mels) (3 + 2 * (n_mels))
 
 /* One unit of work: `batch` rows, frames [frame0, frame0 + n_frames) of each row. */
@@ -105,6 +107,9 @@ typedef struct talfe_job {
 } talfe_job;
 
 int talfe_version(void);
+/* sizeof(talfe_job) as compiled into the library: a binding checks it against its own struct definition at load
+ * time, so that a stale binary or a drifted field list fails loudly instead of passing wrong pointers. */
+size_t talfe_job_size(void);
 const char* talfe_strerror(int status);
 int talfe_last_cuda_error(void); /* cudaError_t of the most recent TALFE_ERR_CUDA on this thread */
 
@@ -150,7 +155,11 @@ int talfe_apply_stats(const talfe_plan* plan, float* feats, int64_t batch, int64
  * out: DEVICE [T, M] with T = 1 + total_len/160.  stats: DEVICE, TALFE_STATS_DOUBLES(M) doubles.
  * staging: DEVICE, talfe_stream_staging_bytes() bytes.  workspace: talfe_workspace_bytes(plan, 1, chunk_frames).
  * defer_normalise != 0 leaves `out` un-normalised and `stats` holding the sums (dataset-level statistics).
- * One episode at a time per plan (the side stream and its events belong to the plan). */
+ * One episode at a time per plan (the side stream and its events belong to the plan).
+ * Buffer lifetime: when the call returns, every copy out of `wave_host` has COMPLETED (the call waits for its side
+ * stream; the transforms may still be running on `stream`), so the caller may reuse or free the host buffer at once.
+ * `wave_host` may also be a DEVICE pointer: the episode is then transformed where it lies, chunk by chunk, and
+ * `staging` may be NULL. */
 size_t talfe_stream_staging_bytes(int wave_dtype, int64_t chunk_frames);
 int talfe_stream_episode(const talfe_plan* plan, const void* wave_host, int wave_dtype, int64_t total_len,
                          int64_t chunk_frames, float* out, int norm, int defer_normalise, double* stats, float eps,
@@ -160,6 +169,11 @@ int talfe_stream_episode(const talfe_plan* plan, const void* wave_host, int wave
  * nccl_comm is an ncclComm_t created by the caller; NCCL is resolved at run time with dlopen
  * ("libnccl.so.2"), so the library itself has no link-time dependency on it. */
 int talfe_allreduce_stats(double* stats_dev, int64_t count, void* nccl_comm, void* stream);
+
+/* Diagnostic: measured FP32 FMA rate of `device` (lane-FMAs per second, packed FFMA2 chains on every SM), the
+ * compute-side denominator of the roofline bench.py reports ("must be measured on the box").
+ * Allocates, launches and synchronises: never call it on a hot path. */
+int talfe_probe_fp32_fma_rate(int device, double* fma_per_second);
 
 /* Deterministic synthetic audio (bench / tests): fills wave[rows, n_samples] with episode
  * (first_episode + r), samples [start, start + n_samples); bit-identical to tal_asrd_b200/synth.py. */

@@ -43,3 +43,17 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if verbose:
         print(proc.stderr)
     return LIB_PATH
+
+
+def build_if_possible() -> str:
+    """What _lib.load() calls: rebuild when a source is newer than the binary and nvcc exists; use the binary as it
+    is on machines without a toolchain; fail loudly when there is neither."""
+    if not is_stale():
+        return LIB_PATH
+    try:
+        nvcc_path()
+    except RuntimeError:
+        if os.path.isfile(LIB_PATH):
+            return LIB_PATH                  # no toolchain here: _lib.load() still checks version and struct size
+        raise
+    return build()

@@ -13,8 +13,11 @@ NORM_NONE, NORM_BATCH_MEAN, NORM_ROW_MEAN, NORM_ROW_MEL_MEAN, NORM_ROW_MEL_MEANV
 LAYOUT_TM, LAYOUT_MT = 0, 1
 ERR_TOO_SHORT = -2
 
+EXPECTED_VERSION = 102     # TALFE_VERSION of include/talfe.h this binding was written against
+
 EXPORTED = [
-    "talfe_version", "talfe_strerror", "talfe_last_cuda_error", "talfe_num_frames", "talfe_plan_create",
+    "talfe_version", "talfe_job_size", "talfe_probe_fp32_fma_rate",
+    "talfe_strerror", "talfe_last_cuda_error", "talfe_num_frames", "talfe_plan_create",
     "talfe_plan_destroy", "talfe_plan_n_mels", "talfe_workspace_bytes", "talfe_run", "talfe_logmel_forward",
     "talfe_apply_stats", "talfe_allreduce_stats", "talfe_synth_fill", "talfe_stream_staging_bytes",
     "talfe_stream_episode",
@@ -45,13 +48,32 @@ def load() -> ctypes.CDLL:
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = os.environ.get("TALFE_LIB") or _build.LIB_PATH              # TALFE_LIB: an experiment build (tools/_abl/)
-    if not os.path.isfile(path):
-        if os.environ.get("TALFE_LIB"):
+    path = os.environ.get("TALFE_LIB")                                  # TALFE_LIB: an experiment build (tools/_abl/)
+    if path:
+        if not os.path.isfile(path):
             raise FileNotFoundError(f"TALFE_LIB={path} does not exist")
-        # build on first use where a toolchain exists (the GPU box receives the prebuilt .so)
-        path = _build.build()
+    else:
+        # (re)build where a toolchain exists and a source is newer than the binary; the GPU box receives the prebuilt
+        # .so together with its sources (same mtimes), so nothing is compiled there
+        path = _build.build_if_possible()
     lib = ctypes.CDLL(path)
+    lib.talfe_version.restype = c_int
+    if os.environ.get("TALFE_ABI_CHECK") == "0":                        # A/B against an older build (tools/ab_libs.py)
+        return _finish_binding(lib, optional=True)
+    # a stale or foreign binary must fail here, not pass wrong pointers later
+    if not hasattr(lib, "talfe_job_size"):
+        raise RuntimeError(f"{path} predates this binding (no talfe_job_size): rebuild with tal_asrd_b200._build.build(force=True)")
+    lib.talfe_job_size.restype = c_size_t
+    if lib.talfe_version() != EXPECTED_VERSION or lib.talfe_job_size() != ctypes.sizeof(Job):
+        raise RuntimeError(f"{path}: TALFE_VERSION {lib.talfe_version()} / sizeof(talfe_job) {lib.talfe_job_size()} do not match "
+                           f"this binding ({EXPECTED_VERSION} / {ctypes.sizeof(Job)}): rebuild the library")
+    lib.talfe_probe_fp32_fma_rate.restype = c_int
+    lib.talfe_probe_fp32_fma_rate.argtypes = [c_int, POINTER(c_double)]
+    return _finish_binding(lib)
+
+
+def _finish_binding(lib, optional: bool = False):
+    global _LIB
     lib.talfe_version.restype = c_int
     lib.talfe_strerror.restype = c_char_p
     lib.talfe_strerror.argtypes = [c_int]

@@ -34,8 +34,11 @@ class CorpusStats:
     """Accumulates statistics blocks (layout of include/talfe.h: count, sum, sumsq, per-mel sums,
     per-mel sumsq) and reduces them across ranks."""
 
-    def __init__(self, n_mels: int = 80, device: Optional[torch.device] = None):
+    def __init__(self, n_mels: int = 80, device: Optional[torch.device] = None, per_mel: bool = True):
         self.n_mels = n_mels
+        # the kernels fill the per-mel entries only in the ROW_MEL_* modes (include/talfe.h); with any other
+        # normalisation they stay zero, and mel_mean / mel_var refuse to hand out zeros as statistics
+        self.per_mel = per_mel
         self.block = torch.zeros(1, 3 + 2 * n_mels, dtype=torch.float64, device=device)
 
     def add(self, block: torch.Tensor) -> None:
@@ -61,28 +64,36 @@ class CorpusStats:
         m = self.block[0, 1] / self.block[0, 0]
         return float(self.block[0, 2] / self.block[0, 0] - m * m)
 
+    def _need_per_mel(self):
+        if not self.per_mel:
+            raise RuntimeError("per-mel statistics are only accumulated with norm='row_mel' / 'row_mel_var'")
+
     @property
     def mel_mean(self) -> torch.Tensor:
+        self._need_per_mel()
         n = self.block[0, 0] / self.n_mels
         return self.block[0, 3:3 + self.n_mels] / n
 
     @property
     def mel_var(self) -> torch.Tensor:
+        self._need_per_mel()
         n = self.block[0, 0] / self.n_mels
         mu = self.mel_mean
         return self.block[0, 3 + self.n_mels:3 + 2 * self.n_mels] / n - mu * mu
 
 
 def corpus_pass(frontend, episodes: Iterable[torch.Tensor], norm: str = "row_mel_var", group=None,
-                keep_features: bool = True, chunk_seconds: float = 30.0):
+                keep_features: bool = True, chunk_seconds: Optional[float] = None):
     """Transforms this rank's episodes, all-reduces the statistics once, then normalises in place.
 
     episodes: iterable of 1-D waveforms owned by this rank (host or device).
     Returns (list of [1, T, M] feature tensors or [], CorpusStats with the GLOBAL sums).
     """
-    from .streaming import stream_episode
+    from .streaming import DEFAULT_CHUNK_SECONDS, stream_episode
+    if chunk_seconds is None:
+        chunk_seconds = DEFAULT_CHUNK_SECONDS
     device = torch.device("cuda", torch.cuda.current_device())
-    total = CorpusStats(frontend.n_mels, device)
+    total = CorpusStats(frontend.n_mels, device, per_mel=norm in ("row_mel", "row_mel_var"))
     feats = []
     for ep in episodes:
         block = frontend.stats_block(device)

@@ -106,9 +106,9 @@ extern "C" int talfe_emul_logmel_ws(const float* x, int64_t n_samples, const flo
             load_window(j, t.win_t.data(), 1.0f, wj);
             cf tw[10];
             for (int q = 0; q < 10; ++q) tw[q] = tw_all[j * 10 + q];
-            cf z[20];
-            stage1_ws_fft<float>(xs.data() + XLayout<float>::kGroup * g1 + j, wj, z);
-            stage1_ws_store(z, tw, e.data() + ws_e_base(g1) + j);
+            cf re[11], im[11];
+            stage1_ws_fft<float>(xs.data() + XLayout<float>::kGroup * g1 + j, wj, re, im);
+            stage1_ws_store(re, im, tw, e.data() + ws_e_base(g1) + j);
         }
         for (int tid = 0; tid < kWsGroups * kGroup; ++tid) {           // consumers, stage 2: thread (g, r)
             const int g = tid & (kWsGroups - 1), r = tid >> 4;

@@ -66,7 +66,17 @@ struct talfe_plan_impl {
     // hand the two staging buffers back and forth; created with the plan, never on the hot path
     cudaStream_t copy_stream;
     cudaEvent_t ev_ready[2], ev_free[2];
+    // fused normalisation: grid-barrier words, one pair per stream this plan has been used on (launches on one stream
+    // are ordered; two streams must not share a barrier), and what the driver accepted at the first cooperative launch
+    int fuse_norm;                 // TALFE_FUSED_NORM (default 1) and cooperative launch available
+    int coop_with_pdl;             // 1: cooperative + programmatic serialisation together, 0: cooperative only, -1: untried
+    unsigned* bar_dev;             // [kBarSlots][2], zeroed once
+    void* bar_stream[16];
+    int bar_used;
+    std::mutex* bar_mutex;
 };
+constexpr int kBarSlots = 16;
+constexpr int kFuseMaxTilesPerCta = 8;
 
 struct KernelArgs {
     const void* wave;
@@ -95,6 +105,14 @@ struct KernelArgs {
     const float* win_global;       // window taps [20][20] in global memory (read once into producer registers)
     int out_align_ok;              // every frame row of `out` starts 16-byte aligned (bulk stores allowed)
     int l2_prefetch;               // prefetch tile k+2 into L2 while tile k+1 travels to shared memory
+    // reference normalisation fused into the kernel (one launch per LogMelSpec.forward): after its last tile every CTA
+    // publishes its partial sum, the grid meets at a barrier in global memory (cooperative launch: all CTAs resident),
+    // every CTA derives the same scalar mean from the partials in a fixed order and subtracts it from ITS OWN tiles,
+    // which it wrote moments ago and which therefore sit in L2
+    int fuse_norm;
+    unsigned* grid_bar;            // [0] arrivals of the current launch, [1] generation; self-resetting
+    double norm_count;             // B * T * M
+    double* stats_out;             // count, sum, sum of squares (or nullptr)
 };
 
 // ------------------------------------------------------------------------------------------ K1
@@ -416,20 +434,21 @@ __global__ void __launch_bounds__(kReduceThreads) reduce_partials_kernel(const d
     }
 }
 
-// Per-mel column sums of un-normalised features (extension modes 3/4).  grid (chunks, B).
+// Per-mel column sums of un-normalised features (extension modes 3/4).  grid (B, chunks): the batch rides on grid.x,
+// whose limit is 2^31 - 1; a row of the maximum supported length has ~52 k chunks, inside grid.y's 65 535.
 __global__ void __launch_bounds__(320) colstats_kernel(const float* __restrict__ feats, long long out_row_stride, int out_layout,
                                                        long long n_frames, int n_mels, const long long* __restrict__ lens,
                                                        long long total_len, long long frame0, double* __restrict__ colpart,
                                                        const long long* __restrict__ out_offsets) {
     __shared__ double s_sum[16][kMaxMels], s_sq[16][kMaxMels];
-    const long long row = blockIdx.y, chunk = blockIdx.x;
+    const long long row = blockIdx.x, chunk = blockIdx.y;
     const long long L = lens ? lens[row] : total_len;
     const long long T_row = L > kHalf ? 1 + L / kHop : 0;
     long long valid = min(frame0 + n_frames, T_row) - frame0;
     if (valid < 0) valid = 0;
     const long long f_lo = chunk * kColChunk, f_hi = min(f_lo + kColChunk, valid);
     const float* base = feats + (out_offsets ? out_offsets[row] * n_mels : row * out_row_stride);
-    double* o = colpart + (row * gridDim.x + chunk) * 2 * kMaxMels;
+    double* o = colpart + (row * gridDim.y + chunk) * 2 * kMaxMels;
     if (out_layout == TALFE_LAYOUT_TM && n_mels == kMaxMels && (reinterpret_cast<unsigned long long>(base) & 15ull) == 0) {
         // 20 float4 lanes x 16 frame lanes: every frame row is read as 320 contiguous bytes; fixed summation order
         const int q = threadIdx.x % 20, fl = threadIdx.x / 20;
@@ -502,7 +521,7 @@ __global__ void __launch_bounds__(256) apply_stats_kernel(float* __restrict__ fe
                                                           int n_bands) {
     __shared__ float s_mean[kMaxMels], s_rstd[kMaxMels];
     __shared__ int s_tb[2 * kMaxBands];
-    const long long row = blockIdx.y;
+    const long long row = blockIdx.x;                  // batch on grid.x (no 65 535 limit), sweep blocks on grid.y
     const double* s = stats + (norm == TALFE_NORM_BATCH_MEAN ? 0 : row * TALFE_STATS_DOUBLES(n_mels));
     long long valid = n_frames;
     if (valid_frames) valid = min(valid_frames[row], n_frames);
@@ -544,7 +563,7 @@ __global__ void __launch_bounds__(256) apply_stats_kernel(float* __restrict__ fe
     if (out_layout == TALFE_LAYOUT_TM && (n_mels & 3) == 0 && ((reinterpret_cast<unsigned long long>(base) & 15ull) == 0)) {
         float4* b4 = reinterpret_cast<float4*>(base);
         const int m4 = n_mels >> 2;
-        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total / 4; i += (long long)gridDim.x * blockDim.x) {
+        for (long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x; i < total / 4; i += (long long)gridDim.y * blockDim.x) {
             const int f = (int)(i / m4);
             const int m = (int)(i - (long long)f * m4) * 4;
             float4 v = b4[i];
@@ -556,14 +575,14 @@ __global__ void __launch_bounds__(256) apply_stats_kernel(float* __restrict__ fe
             b4[i] = v;
         }
     } else if (out_layout == TALFE_LAYOUT_TM) {
-        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        for (long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.y * blockDim.x) {
             const int f = (int)(i / n_mels);
             const int m = (int)(i - (long long)f * n_mels);
             base[i] = (n_bands && time_masked(f)) ? 0.f : (base[i] - s_mean[m]) * s_rstd[m];
         }
     } else {
-        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)n_mels * n_frames;
-             i += (long long)gridDim.x * blockDim.x) {
+        for (long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x; i < (long long)n_mels * n_frames;
+             i += (long long)gridDim.y * blockDim.x) {
             const int m = (int)(i / n_frames);
             const long long f = i - (long long)m * n_frames;
             if (f < valid) base[i] = (n_bands && time_masked((int)f)) ? 0.f : (base[i] - s_mean[m]) * s_rstd[m];
@@ -649,8 +668,9 @@ logmel_kernel_t kernel_for(bool ref_layout, int dtype) {
     return dtype == TALFE_F32 ? logmel_kernel<false, float> : dtype == TALFE_F16 ? logmel_kernel<false, __half> : logmel_kernel<false, short>;
 }
 
-logmel_kernel_t ws_kernel_for(int dtype) {
-    return dtype == TALFE_F32 ? logmel_ws_kernel<float> : dtype == TALFE_F16 ? logmel_ws_kernel<__half> : logmel_ws_kernel<short>;
+logmel_kernel_t ws_kernel_for(int dtype, bool fuse = false) {
+    if (fuse) return dtype == TALFE_F32 ? logmel_ws_kernel<float, true> : dtype == TALFE_F16 ? logmel_ws_kernel<__half, true> : logmel_ws_kernel<short, true>;
+    return dtype == TALFE_F32 ? logmel_ws_kernel<float, false> : dtype == TALFE_F16 ? logmel_ws_kernel<__half, false> : logmel_ws_kernel<short, false>;
 }
 
 // Development / profiling knobs (read once per plan): TALFE_KERNEL=legacy|ws, TALFE_L2_PREFETCH=0|1.
@@ -668,7 +688,7 @@ size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 unsigned sweep_blocks(int sm_count, long long batch, long long dense_per_row) {
     long long want = (dense_per_row / 4 + 255) / 256;
     long long cap = std::max<long long>(1, (long long)sm_count * 8 / std::max<long long>(1, batch));
-    return (unsigned)std::max<long long>(1, std::min(want, cap));
+    return (unsigned)std::max<long long>(1, std::min<long long>(std::min(want, cap), 65535));   // rides on grid.y
 }
 
 struct WorkspaceLayout { size_t partials, colpart, scratch_stats, total; long long tiles_per_row, n_tiles; int chunks; };
@@ -697,6 +717,8 @@ struct talfe_plan : talfe_plan_impl {};
 extern "C" {
 
 int talfe_version(void) { return TALFE_VERSION; }
+
+size_t talfe_job_size(void) { return sizeof(talfe_job); }
 
 const char* talfe_strerror(int status) {
     switch (status) {
@@ -759,17 +781,30 @@ int talfe_plan_create(talfe_plan** plan_out, int device, int n_mels, const float
     if (e == cudaSuccess)
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p->ctas_per_sm, kernel_for(p->ref_layout != 0, TALFE_F32), kThreads, p->smem_bytes);
     if (p->variant == 1) {
-        for (int dt = TALFE_F32; dt <= TALFE_I16 && e == cudaSuccess; ++dt)
-            e = cudaFuncSetAttribute(ws_kernel_for(dt), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->ws_smem);
+        for (int dt = TALFE_F32; dt <= TALFE_I16 && e == cudaSuccess; ++dt) {
+            e = cudaFuncSetAttribute(ws_kernel_for(dt, false), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->ws_smem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(ws_kernel_for(dt, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->ws_smem);
+        }
     }
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking);
+    {
+        int coop = 0;
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+        p->fuse_norm = (coop && p->variant == 1) ? env_int("TALFE_FUSED_NORM", 1) : 0;
+        p->coop_with_pdl = -1;
+        p->bar_used = 0;
+        p->bar_mutex = new (std::nothrow) std::mutex();
+        if (!p->bar_mutex) p->fuse_norm = 0;
+        if (e == cudaSuccess) e = cudaMalloc(&p->bar_dev, kBarSlots * 2 * sizeof(unsigned));
+        if (e == cudaSuccess) e = cudaMemset(p->bar_dev, 0, kBarSlots * 2 * sizeof(unsigned));
+    }
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
         e = cudaEventCreateWithFlags(&p->ev_ready[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_free[i], cudaEventDisableTiming);
     }
     cudaSetDevice(prev);
-    if (e != cudaSuccess) { if (p->blob_dev) cudaFree(p->blob_dev); delete p; return cuda_fail(e); }
-    if (p->ctas_per_sm < 1) { cudaFree(p->blob_dev); delete p; return TALFE_ERR_UNSUPPORTED; }
+    if (e != cudaSuccess) { talfe_plan_destroy(p); return cuda_fail(e); }
+    if (p->ctas_per_sm < 1) { talfe_plan_destroy(p); return TALFE_ERR_UNSUPPORTED; }
     *plan_out = p;
     return TALFE_OK;
 }
@@ -777,6 +812,8 @@ int talfe_plan_create(talfe_plan** plan_out, int device, int n_mels, const float
 void talfe_plan_destroy(talfe_plan* plan) {
     if (!plan) return;
     if (plan->blob_dev) cudaFree(plan->blob_dev);
+    if (plan->bar_dev) cudaFree(plan->bar_dev);
+    delete plan->bar_mutex;
     if (plan->copy_stream) cudaStreamDestroy(plan->copy_stream);
     for (int i = 0; i < 2; ++i) {
         if (plan->ev_ready[i]) cudaEventDestroy(plan->ev_ready[i]);
@@ -854,23 +891,63 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
     const bool per_row = job->norm >= TALFE_NORM_ROW_MEAN;
     a.partials_per_tile = per_row ? 1 : 0;                // batch-wide sums: one slot per CTA is enough
     a.want_sumsq = job->stats != nullptr ? 1 : 0;         // the sum of squares is only ever reported, never needed by K3
+    // The reference case — one scalar over a contiguous [B, T, M] tensor — is normalised inside the ws kernel itself
+    // (cooperative launch, grid barrier, every CTA sweeps its own tiles): ONE launch per LogMelSpec.forward.
+    const bool ref_norm = job->norm == TALFE_NORM_BATCH_MEAN && !a.lens && !(job->accumulate_stats && job->stats) &&
+                          !job->defer_normalise && ors == dense && job->n_bands == 0 &&
+                          (reinterpret_cast<uintptr_t>(job->out) & 15) == 0;
+    unsigned* bar = nullptr;
+    // ... when that pays: for a handful of tiles per CTA the second launch (its host cost and ~3 us of device latency) is
+    // a large part of the call; for big batches the separate flat sweep (8 blocks per SM, launched programmatically
+    // behind K1) measured 5 us faster than the in-kernel one (profiles/r02_ab_variants.json), so it keeps that job.
+    // TALFE_FUSED_NORM: 0 never, 1 (default) up to kFuseMaxTilesPerCta tiles per CTA, 2 always.
+    const bool fuse_pays = plan->fuse_norm >= 2 || w.n_tiles <= (long long)kFuseMaxTilesPerCta * plan->sm_count;
+    if (ref_norm && use_ws && plan->fuse_norm && fuse_pays && job->out_layout == TALFE_LAYOUT_TM && a.out_align_ok) {
+        talfe_plan* pl = const_cast<talfe_plan*>(plan);
+        std::lock_guard<std::mutex> lock(*pl->bar_mutex);
+        int slot = -1;
+        for (int i = 0; i < pl->bar_used; ++i) if (pl->bar_stream[i] == job->stream) slot = i;
+        if (slot < 0 && pl->bar_used < kBarSlots) { slot = pl->bar_used++; pl->bar_stream[slot] = job->stream; }
+        if (slot >= 0) bar = pl->bar_dev + 2 * slot;                  // more than 16 streams on one plan: two-kernel path
+    }
+    a.fuse_norm = bar ? 1 : 0;
+    a.grid_bar = bar;
+    a.norm_count = (double)dense * (double)job->batch;
+    a.stats_out = job->stats;
     {
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(use_ws ? kWsThreads : kThreads);
         cfg.dynamicSmemBytes = use_ws ? plan->ws_smem : plan->smem_bytes; cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
+        cudaLaunchAttribute attr[2];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
+        attr[1].id = cudaLaunchAttributeCooperative;
+        attr[1].val.cooperative = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        TALFE_CUDA(cudaLaunchKernelEx(&cfg, use_ws ? ws_kernel_for(a.dtype) : kernel_for(plan->ref_layout != 0, a.dtype),
-                                      (const KernelArgs)a));
+        const auto fn = use_ws ? ws_kernel_for(a.dtype, a.fuse_norm != 0) : kernel_for(plan->ref_layout != 0, a.dtype);
+        if (a.fuse_norm) {
+            talfe_plan* pl = const_cast<talfe_plan*>(plan);
+            cudaError_t e = cudaErrorUnknown;
+            if (pl->coop_with_pdl != 0) {                              // first choice: keep the prologue overlap as well
+                cfg.attrs = attr; cfg.numAttrs = 2;
+                e = cudaLaunchKernelEx(&cfg, fn, (const KernelArgs)a);
+                if (e != cudaSuccess && pl->coop_with_pdl < 0) { cudaGetLastError(); pl->coop_with_pdl = 0; }
+                else if (e == cudaSuccess) pl->coop_with_pdl = 1;
+            }
+            if (pl->coop_with_pdl == 0) {
+                cfg.attrs = attr + 1; cfg.numAttrs = 1;
+                e = cudaLaunchKernelEx(&cfg, fn, (const KernelArgs)a);
+            }
+            TALFE_CUDA(e);
+            return TALFE_OK;
+        }
+        TALFE_CUDA(cudaLaunchKernelEx(&cfg, fn, (const KernelArgs)a));
     }
 
     if (!want_stats) return TALFE_OK;
     double* stats = job->stats ? job->stats : reinterpret_cast<double*>(ws + w.scratch_stats);
     const int accumulate = (job->accumulate_stats && job->stats) ? 1 : 0;
-    if (job->norm == TALFE_NORM_BATCH_MEAN && !a.lens && !accumulate && !job->defer_normalise && ors == dense &&
-        job->n_bands == 0 && (reinterpret_cast<uintptr_t>(job->out) & 15) == 0) {
+    if (ref_norm) {
         // the reference case: one scalar over a contiguous [B, T, M] (or [B, M, T]) tensor; the sweep
         // derives the mean from the per-CTA partials itself (no separate reduction launch)
         const long long total = dense * job->batch, n4 = total / 4;
@@ -895,7 +972,7 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
     TALFE_CUDA(cudaGetLastError());
     if (job->norm == TALFE_NORM_ROW_MEL_MEAN || job->norm == TALFE_NORM_ROW_MEL_MEANVAR) {
         double* colpart = reinterpret_cast<double*>(ws + w.colpart);
-        colstats_kernel<<<dim3((unsigned)w.chunks, (unsigned)job->batch), 320, 0, stream>>>(job->out, ors, job->out_layout, job->n_frames, M,
+        colstats_kernel<<<dim3((unsigned)job->batch, (unsigned)w.chunks), 320, 0, stream>>>(job->out, ors, job->out_layout, job->n_frames, M,
                                                                                            a.lens, a.total_len, a.frame0, colpart, a.out_offsets);
         TALFE_CUDA(cudaGetLastError());
         colstats_finish_kernel<<<(unsigned)job->batch, kFinishLanes * kMaxMels, 0, stream>>>(colpart, w.chunks, M, accumulate, stats);
@@ -903,7 +980,7 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
     }
     if (job->norm == TALFE_NORM_NONE || job->defer_normalise) return TALFE_OK;
     // rows keep their zero fill beyond their own length: the sweep derives valid frames from lens
-    apply_stats_kernel<<<dim3(sweep_blocks(plan->sm_count, job->batch, dense), (unsigned)job->batch), 256, 0, stream>>>(
+    apply_stats_kernel<<<dim3((unsigned)job->batch, sweep_blocks(plan->sm_count, job->batch, dense)), 256, 0, stream>>>(
         job->out, job->batch, job->n_frames, ors, job->out_layout, M, job->norm, stats, nullptr, a.lens, a.frame0, a.out_offsets,
         job->freq_bands, job->time_bands, job->n_bands);
     TALFE_CUDA(cudaGetLastError());
@@ -927,10 +1004,13 @@ int talfe_apply_stats(const talfe_plan* plan, float* feats, int64_t batch, int64
                       int out_layout, int norm, const double* stats, const int64_t* valid_frames, void* stream) {
     if (!plan || !feats || !stats || batch < 1 || n_frames < 1) return TALFE_ERR_INVALID;
     if (norm <= TALFE_NORM_NONE || norm > TALFE_NORM_ROW_MEL_MEANVAR) return TALFE_ERR_INVALID;
+    if (out_layout != TALFE_LAYOUT_TM && out_layout != TALFE_LAYOUT_MT) return TALFE_ERR_INVALID;
+    if (batch > 0x7fffffffLL) return TALFE_ERR_UNSUPPORTED;
     const int M = plan->n_mels;
     const long long dense = n_frames * M;
     const long long ors = out_row_stride ? out_row_stride : dense;
-    apply_stats_kernel<<<dim3(sweep_blocks(plan->sm_count, batch, dense), (unsigned)batch), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+    if (ors < dense) return TALFE_ERR_INVALID;
+    apply_stats_kernel<<<dim3((unsigned)batch, sweep_blocks(plan->sm_count, batch, dense)), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         feats, batch, n_frames, ors, out_layout, M, norm, stats, reinterpret_cast<const long long*>(valid_frames), nullptr, 0,
         nullptr, nullptr, nullptr, 0);
     TALFE_CUDA(cudaGetLastError());
@@ -948,11 +1028,16 @@ size_t talfe_stream_staging_bytes(int wave_dtype, int64_t chunk_frames) {
 int talfe_stream_episode(const talfe_plan* plan, const void* wave_host, int wave_dtype, int64_t total_len,
                          int64_t chunk_frames, float* out, int norm, int defer_normalise, double* stats, float eps,
                          void* staging, size_t staging_bytes, void* workspace, size_t workspace_bytes, void* stream_v) {
-    if (!plan || !wave_host || !out || !stats || !staging || chunk_frames < 1) return TALFE_ERR_INVALID;
+    if (!plan || !wave_host || !out || !stats || chunk_frames < 1) return TALFE_ERR_INVALID;
     if (total_len <= kHalf) return TALFE_ERR_TOO_SHORT;
     if (wave_dtype < TALFE_F32 || wave_dtype > TALFE_I16) return TALFE_ERR_INVALID;
     if (norm < TALFE_NORM_NONE || norm > TALFE_NORM_ROW_MEL_MEANVAR) return TALFE_ERR_INVALID;
-    if (staging_bytes < talfe_stream_staging_bytes(wave_dtype, chunk_frames)) return TALFE_ERR_WORKSPACE;
+    // an episode that already lives in device memory is transformed in place, chunk by chunk, with no staging copies
+    cudaPointerAttributes pa{};
+    bool on_device = false;
+    if (cudaPointerGetAttributes(&pa, wave_host) == cudaSuccess) on_device = pa.type == cudaMemoryTypeDevice;
+    else cudaGetLastError();
+    if (!on_device && (!staging || staging_bytes < talfe_stream_staging_bytes(wave_dtype, chunk_frames))) return TALFE_ERR_WORKSPACE;
     const size_t elt = wave_dtype == TALFE_F32 ? 4 : 2;
     const size_t per = staging_bytes / 2 / 256 * 256;
     const int64_t T = 1 + total_len / kHop;
@@ -970,27 +1055,86 @@ int talfe_stream_episode(const talfe_plan* plan, const void* wave_host, int wave
         hi = std::min<int64_t>(total_len, need_hi);
         lo -= lo % 8;                                          // keep the chunk origin 16-byte aligned -> TMA fast path
         const int b = k & 1;
-        unsigned char* buf = reinterpret_cast<unsigned char*>(staging) + b * per;
-        if ((size_t)(hi - lo) * elt > per) return TALFE_ERR_WORKSPACE;
-        // staging buffer b is free once the transform that last read it has run (also orders against a previous episode;
-        // waiting on a never-recorded event is a no-op)
-        TALFE_CUDA(cudaStreamWaitEvent(pl->copy_stream, pl->ev_free[b], 0));
-        TALFE_CUDA(cudaMemcpyAsync(buf, reinterpret_cast<const unsigned char*>(wave_host) + lo * elt, (size_t)(hi - lo) * elt,
-                                   cudaMemcpyHostToDevice, pl->copy_stream));
-        TALFE_CUDA(cudaEventRecord(pl->ev_ready[b], pl->copy_stream));
-        TALFE_CUDA(cudaStreamWaitEvent(stream, pl->ev_ready[b], 0));
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(wave_host) + lo * elt;
+        const void* chunk = src;
+        if (!on_device) {
+            unsigned char* buf = reinterpret_cast<unsigned char*>(staging) + b * per;
+            if ((size_t)(hi - lo) * elt > per) return TALFE_ERR_WORKSPACE;
+            // staging buffer b is free once the transform that last read it has run (also orders against a previous episode;
+            // waiting on a never-recorded event is a no-op)
+            TALFE_CUDA(cudaStreamWaitEvent(pl->copy_stream, pl->ev_free[b], 0));
+            TALFE_CUDA(cudaMemcpyAsync(buf, src, (size_t)(hi - lo) * elt, cudaMemcpyHostToDevice, pl->copy_stream));
+            TALFE_CUDA(cudaEventRecord(pl->ev_ready[b], pl->copy_stream));
+            TALFE_CUDA(cudaStreamWaitEvent(stream, pl->ev_ready[b], 0));
+            chunk = buf;
+        }
         talfe_job job{};
-        job.wave = buf; job.wave_dtype = wave_dtype; job.norm = norm; job.batch = 1; job.row_stride = hi - lo;
+        job.wave = chunk; job.wave_dtype = wave_dtype; job.norm = norm; job.batch = 1; job.row_stride = hi - lo;
         job.buf_len = hi - lo; job.origin = lo; job.total_len = total_len; job.lens = nullptr;
         job.frame0 = f0; job.n_frames = f1 - f0; job.out = out + f0 * M; job.out_row_stride = 0;
         job.out_layout = TALFE_LAYOUT_TM; job.accumulate_stats = k > 0; job.eps = eps; job.defer_normalise = 1;
         job.stats = stats; job.workspace = workspace; job.workspace_bytes = workspace_bytes; job.stream = stream_v;
         const int rc = talfe_run(plan, &job);
         if (rc) return rc;
-        TALFE_CUDA(cudaEventRecord(pl->ev_free[b], stream));
+        if (!on_device) TALFE_CUDA(cudaEventRecord(pl->ev_free[b], stream));
     }
+    // every copy out of the caller's host buffer has completed when this call returns (the transforms may still be
+    // running): the caller may reuse or free `wave_host` at once — a pinned-memory allocator that only tracks copies
+    // made through its own API cannot know about ours
+    if (!on_device) TALFE_CUDA(cudaStreamSynchronize(pl->copy_stream));
     if (norm == TALFE_NORM_NONE || defer_normalise) return TALFE_OK;
     return talfe_apply_stats(plan, out, 1, T, 0, TALFE_LAYOUT_TM, norm, stats, nullptr, stream_v);
+}
+
+// ---- diagnostics: the FP32 pipe's measured FMA rate, the compute-side denominator of the roofline (SURVEY.md §8d asks
+// for a measured figure; MEASURED_PEAKS.json has none).  Dependent chains of packed FFMA2, 8 chains per thread.
+__global__ void __launch_bounds__(512) fp32_fma_probe_kernel(float2* out, int iters) {
+    float2 acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = make_float2(1.0f + threadIdx.x * 1e-6f + i, 0.5f + i);
+    const float2 m = make_float2(1.0000001f, 0.9999999f), c = make_float2(1e-7f, -1e-7f);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            asm volatile("{ .reg .b64 ra, rm, rc; mov.b64 ra, {%0,%1}; mov.b64 rm, {%2,%3}; mov.b64 rc, {%4,%5}; fma.rn.f32x2 ra, ra, rm, rc; mov.b64 {%0,%1}, ra; }"
+                         : "+f"(acc[i].x), "+f"(acc[i].y) : "f"(m.x), "f"(m.y), "f"(c.x), "f"(c.y));
+    }
+    float2 r = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { r.x += acc[i].x; r.y += acc[i].y; }
+    if (r.x == 123.456f) out[blockIdx.x * blockDim.x + threadIdx.x] = r;   // keeps the chains alive, practically never stores
+}
+
+int talfe_probe_fp32_fma_rate(int device, double* fma_per_second) {
+    if (!fma_per_second) return TALFE_ERR_INVALID;
+    int prev = 0, sms = 0;
+    TALFE_CUDA(cudaGetDevice(&prev));
+    TALFE_CUDA(cudaSetDevice(device));
+    TALFE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    float2* scratch = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    const int blocks = sms * 4, threads = 512, iters = 4096;
+    cudaError_t e = cudaMalloc(&scratch, (size_t)blocks * threads * sizeof(float2));
+    if (e == cudaSuccess) e = cudaEventCreate(&e0);
+    if (e == cudaSuccess) e = cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 5 && e == cudaSuccess; ++rep) {
+        cudaEventRecord(e0, 0);
+        fp32_fma_probe_kernel<<<blocks, threads>>>(scratch, iters);
+        cudaEventRecord(e1, 0);
+        e = cudaEventSynchronize(e1);
+        float ms = 0.f;
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+        if (e == cudaSuccess && rep > 0 && ms > 0.f)     // first repetition = warm-up
+            best = std::max(best, (double)blocks * threads * iters * 8.0 * 2.0 / (ms * 1e-3));
+    }
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (scratch) cudaFree(scratch);
+    cudaSetDevice(prev);
+    if (e != cudaSuccess) return cuda_fail(e);
+    *fma_per_second = best;
+    return TALFE_OK;
 }
 
 // ---- NCCL, resolved at run time so that the library has no link-time dependency on it

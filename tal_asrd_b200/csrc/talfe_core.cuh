@@ -12,15 +12,13 @@
 //   n = j + 20 m,  k = k1 + 20 k2                                   (j, m, k1, k2 in 0..19)
 //   X[k1 + 20 k2] = sum_j W20^(j k2) * [ W400^(j k1) * sum_m x[j + 20 m] W20^(m k1) ]
 //
-//   stage 1 (thread j):  ONE complex FFT-20 of (xa + i xb)[j + 20 m] yields, by conjugate
-//                        symmetry, the real-input FFT-20 of both frames: A_a[k1], A_b[k1],
+//   stage 1 (thread j):  the real-input FFT-20 of both frames' column j (frame a and frame b ride in the two halves
+//                        of every packed register: rfft20_pair_windowed): A_a[k1], A_b[k1],
 //                        k1 = 0..10.  Twiddle by W400^(j k1).  Exchange rows for stage 2:
 //                          row 2(k1-1)   : A_a[k1] W^(j k1)   k1 = 1..9       (frame a)
-//                          row 2(k1-1)+1 : i A_b[k1] W^(j k1) k1 = 1..9       (frame b; the unit factor i drops out of
-//                                                                              the power spectrum and makes the packed form
-//                                                                              of the ws kernel's stage 1 one instruction shorter)
-//                          row 18        : A_a[0] + i A_b[0]                  (both real -> packed)
-//                          row 19        : (A_a[10] + i A_b[10]) W^(10 j)     (both real -> packed)
+//                          row 2(k1-1)+1 : A_b[k1] W^(j k1)   k1 = 1..9       (frame b)
+//                          row 18        : (A_a[0] + i A_b[0]) / 2            (both real -> packed)
+//                          row 19        : (A_a[10] + i A_b[10]) W^(10 j) / 2 (both real -> packed)
 //   stage 2 (thread = row): complex FFT-20 over j.  Rows 0..17 give 20 spectrum bins of one frame
 //                        each (k = k1 + 20 q for output q < 10, and 400 - k by conjugate symmetry
 //                        for q >= 10); rows 18 and 19 give bins 20 q and 10 + 20 q of BOTH frames
@@ -163,6 +161,17 @@ TALFE_HD cf times_i(cf w) {
     return make_float2(-w.y, w.x);
 #endif
 }
+// -i w = (w.y, -w.x)
+TALFE_HD cf times_minus_i(cf w) {
+#ifdef __CUDA_ARCH__
+    cf r;
+    asm("{ .reg .b64 rb, rc, rr; mov.b64 rb, {%3,%2}; mov.b64 rc, {%4,%5}; mul.rn.f32x2 rr, rb, rc; mov.b64 {%0,%1}, rr; }"
+        : "=f"(r.x), "=f"(r.y) : "f"(w.x), "f"(w.y), "f"(1.0f), "f"(-1.0f));
+    return r;
+#else
+    return make_float2(w.y, -w.x);
+#endif
+}
 // s1 * u + s2 * v for real scalars s1, s2 (v's product is rounded first): FMUL2 + FFMA2 with scalar-broadcast operands.
 // With u = w, v = i w this is the complex product (s1 + i s2) w, bit-identical to cmul((s1, s2), w).
 TALFE_HD cf cfma_ss(float s1, cf u, float s2, cf v) { return cfma_s(s1, u, cmul_s(s2, v)); }
@@ -252,6 +261,68 @@ TALFE_HD void fft20_dft5s(cf (&t)[4][5], cf (&v)[20]) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Stage-1 transform: the REAL-input 20-point DFT of both frames of a pair at once.  Every cf in this function is a
+// (frame a, frame b) pair of real numbers — not a complex number — so each packed instruction advances the two
+// frames' independent real transforms in lock step.  Compared with one complex FFT-20 of xa + i xb followed by the
+// conjugate-symmetry untangle (round 1), the real-input structure needs no untangle and drops the redundant half of
+// the prime-factor butterflies: 104 packed instructions per pair column instead of 122 + 18.
+//
+// Same Good-Thomas 4 x 5 index maps as fft20 (n = 5 n1 + 4 n2, k = 5 k1 + 16 k2 mod 20) and the same window folding as
+// fft20_windowed.  The 4-point stage of a real sequence yields T0, T2 real and T1 = d02 - i d13 = conj T3, so
+//   k1 = 0, 2 : real 5-point DFTs (14 instructions each)      -> bins 0, 4, 8 (12, 16 mirror) / 10, 6, 2 (14, 18 mirror)
+//   k1 = 1    : one complex 5-point DFT (36 instructions)     -> bins 5, 1, 9 and, conjugated, 17 -> 3, 13 -> 7
+//   k1 = 3    : the mirror image of k1 = 1, never computed.
+// Output: re[k], im[k] for k = 0..10 (im[0], im[10] are identically zero and not written).  To keep every output a
+// single instruction some imaginary parts come out NEGATED: im[k] holds -Im V[k] where rfft20_im_negated(k); the
+// twiddle step that follows absorbs the sign by multiplying with -i w instead of i w (no extra instruction).
+TALFE_HD constexpr bool rfft20_im_negated(int k) { return k == 1 || k == 2 || k == 5 || k == 6; }
+
+TALFE_HD void rfft20_pair_windowed(const cf (&x)[20], const float (&win)[20], cf (&re)[11], cf (&im)[11]) {
+    cf t0[5], t2[5], p[5], e[5];                       // T0, T2 (real), T1 = (p, -e)
+#pragma unroll
+    for (int n2 = 0; n2 < 5; ++n2) {
+        const int i0 = (4 * n2) % 20, i1 = (5 + 4 * n2) % 20, i2 = (10 + 4 * n2) % 20, i3 = (15 + 4 * n2) % 20;
+        const cf a2 = cmul_s(win[i2], x[i2]), a3 = cmul_s(win[i3], x[i3]);
+        const cf s02 = cfma_s(win[i0], x[i0], a2), s13 = cfma_s(win[i1], x[i1], a3);
+        p[n2] = cfms_s(win[i0], x[i0], a2);            // d02
+        e[n2] = cfms_s(win[i1], x[i1], a3);            // d13
+        t0[n2] = cadd(s02, s13);
+        t2[n2] = csub(s02, s13);
+    }
+    {   // k1 = 0: real DFT-5 of T0 -> V[0] = y0, V[4] = y4 = (m1, s1), V[8] = y3 = (m2, s2)
+        const cf u1 = cadd(t0[1], t0[4]), u2 = cadd(t0[2], t0[3]), u3 = csub(t0[1], t0[4]), u4 = csub(t0[2], t0[3]);
+        re[0] = cadd(cadd(t0[0], u1), u2);
+        re[4] = cfma_s(TALFE_C2, u2, cfma_s(TALFE_C1, u1, t0[0]));
+        re[8] = cfma_s(TALFE_C1, u2, cfma_s(TALFE_C2, u1, t0[0]));
+        im[4] = cfma_s(TALFE_S2, u4, cmul_s(TALFE_S1, u3));
+        im[8] = cfma_s(-TALFE_S1, u4, cmul_s(TALFE_S2, u3));
+    }
+    {   // k1 = 2: real DFT-5 of T2 -> V[10] = y0, V[6] = y1 = (m1, -s1), V[2] = y2 = (m2, -s2)   (im held negated)
+        const cf u1 = cadd(t2[1], t2[4]), u2 = cadd(t2[2], t2[3]), u3 = csub(t2[1], t2[4]), u4 = csub(t2[2], t2[3]);
+        re[10] = cadd(cadd(t2[0], u1), u2);
+        re[6] = cfma_s(TALFE_C2, u2, cfma_s(TALFE_C1, u1, t2[0]));
+        re[2] = cfma_s(TALFE_C1, u2, cfma_s(TALFE_C2, u1, t2[0]));
+        im[6] = cfma_s(TALFE_S2, u4, cmul_s(TALFE_S1, u3));
+        im[2] = cfma_s(-TALFE_S1, u4, cmul_s(TALFE_S2, u3));
+    }
+    {   // k1 = 1: complex DFT-5 of T1[n2] = p[n2] - i e[n2]; the "n" quantities below carry MINUS the imaginary part
+        const cf u1r = cadd(p[1], p[4]), u2r = cadd(p[2], p[3]), u3r = csub(p[1], p[4]), u4r = csub(p[2], p[3]);
+        const cf u1n = cadd(e[1], e[4]), u2n = cadd(e[2], e[3]), u3n = csub(e[1], e[4]), u4n = csub(e[2], e[3]);
+        re[5] = cadd(cadd(p[0], u1r), u2r);            // V[5] = y0
+        im[5] = cadd(cadd(e[0], u1n), u2n);            //        (negated)
+        const cf m1r = cfma_s(TALFE_C2, u2r, cfma_s(TALFE_C1, u1r, p[0])), m1n = cfma_s(TALFE_C2, u2n, cfma_s(TALFE_C1, u1n, e[0]));
+        const cf m2r = cfma_s(TALFE_C1, u2r, cfma_s(TALFE_C2, u1r, p[0])), m2n = cfma_s(TALFE_C1, u2n, cfma_s(TALFE_C2, u1n, e[0]));
+        const cf s1r = cfma_s(TALFE_S2, u4r, cmul_s(TALFE_S1, u3r)), s1n = cfma_s(TALFE_S2, u4n, cmul_s(TALFE_S1, u3n));
+        const cf s2r = cfma_s(-TALFE_S1, u4r, cmul_s(TALFE_S2, u3r)), s2n = cfma_s(-TALFE_S1, u4n, cmul_s(TALFE_S2, u3n));
+        // y1 = m1 - i s1, y4 = m1 + i s1, y2 = m2 - i s2, y3 = m2 + i s2 with Im m = -m.n, Im s = -s.n
+        re[1] = csub(m1r, s1n); im[1] = cadd(m1n, s1r);            // V[1] = y1          (negated: Im y1 = -m1n - s1r)
+        re[9] = cadd(m1r, s1n); im[9] = csub(s1r, m1n);            // V[9] = y4
+        re[3] = csub(m2r, s2n); im[3] = cadd(m2n, s2r);            // V[3] = conj y2     (Im y2 = -m2n - s2r)
+        re[7] = cadd(m2r, s2n); im[7] = csub(m2n, s2r);            // V[7] = conj y3     (Im y3 = s2r - m2n)
+    }
+}
+
 // Exchange rows are stored in permuted slots: stage-2 lane `row` (thread 18 g + row reads with LDS.128,
 // 8 lanes per wavefront) fetches slot row_slot(row).  The permutation makes every 8-lane window of the
 // thread order 18 g + row hit 8 distinct 16-byte bank groups ((11 slot + 226 g) mod 8); found by search,
@@ -267,9 +338,9 @@ template <typename XT> TALFE_HD int xskew(int i) { return i + XLayout<XT>::kSkew
 // ---------------------------------------------------------------------------------------------
 // Stage 1.  xg points at this pair's first sample inside the skewed tile (s_x + XLayout<XT>::kGroup * g);
 // frame a = samples 0..399 of the pair, frame b = samples 160..559.
-// win_t[j*20 + m] = 0.5 * hann[j + 20 m]  (the 0.5 makes A_a = C[k] + conj C[20-k] exact scale);
-// tw_t[j*10 + (k1-1)] = W400^(j k1) for k1 = 1..10.  Rows 18 / 19 (the packed k1 = 0 / 10 rows) are left
-// at half scale, which the power computation of stage 2 absorbs ((X/2 + X/2)^2 = |X|^2).
+// win_t[j*20 + m] = 0.5 * hann[j + 20 m]: the transform runs at half scale;
+// tw_t[j*10 + (k1-1)] = 2 W400^(j k1) for k1 = 1..9 restores it for rows 0..17, tw_t[j*10 + 9] = W400^(10 j).  Rows 18 / 19
+// (the packed k1 = 0 / 10 rows) stay at half scale, which the power computation of stage 2 absorbs ((X/2 + X/2)^2 = |X|^2).
 // Writes this thread's column j of the 20 exchange rows.
 TALFE_HD void load_window(int j, const float* __restrict__ win_t, float scale, float (&win)[20]) {
     const float4* w4 = reinterpret_cast<const float4*>(win_t + j * 20);
@@ -283,7 +354,7 @@ TALFE_HD void load_window(int j, const float* __restrict__ win_t, float scale, f
 template <typename XT>
 TALFE_HD void stage1(int j, const XT* __restrict__ xg, const float (&win)[20],
                      const cf* __restrict__ tw_t, cf* __restrict__ e_group) {
-    cf xin[20], z[20];
+    cf xin[20], re[11], im[11];
     const XT* p = xg + j;
     constexpr int kSkew = XLayout<XT>::kSkew;
 #pragma unroll
@@ -293,10 +364,10 @@ TALFE_HD void stage1(int j, const XT* __restrict__ xg, const float (&win)[20],
         const int ib = 20 * m + kHop + (20 * m + kHop >= kXBlock ? kSkew : 0);
         xin[m] = make_float2(x_to_float(p[ia]), x_to_float(p[ib]));
     }
-    fft20_windowed(xin, win, z);
+    rfft20_pair_windowed(xin, win, re, im);
     const float4* t4 = reinterpret_cast<const float4*>(tw_t + j * 10);
     cf* col = e_group + j;
-    col[row_slot(18) * kERow] = z[0];                                             // row 18: (A_a[0] + i A_b[0]) / 2
+    col[row_slot(18) * kERow] = re[0];                                            // row 18: (A_a[0] + i A_b[0]) / 2
 #pragma unroll
     for (int h = 0; h < 5; ++h) {
         const float4 tt = t4[h];                                        // twiddles k1 = 2h+1, 2h+2
@@ -305,14 +376,11 @@ TALFE_HD void stage1(int j, const XT* __restrict__ xg, const float (&win)[20],
             const int k1 = 2 * h + 1 + u;
             const cf w = u == 0 ? make_float2(tt.x, tt.y) : make_float2(tt.z, tt.w);
             if (k1 < 10) {
-                const cf sm = cadd(z[k1], z[20 - k1]), df = csub(z[k1], z[20 - k1]);
-                const cf aa = make_float2(sm.x, df.y);                  // A_a[k1] = C[k1] + conj C[20-k1]
-                const cf ab = make_float2(sm.y, -df.x);                 // A_b[k1] = (C[k1] - conj C[20-k1]) / i
-                col[row_slot(2 * (k1 - 1)) * kERow] = cmul(aa, w);
-                const cf cb = cmul(ab, w);
-                col[row_slot(2 * (k1 - 1) + 1) * kERow] = make_float2(-cb.y, cb.x);   // i A_b W: see the row table above
+                const float sg = rfft20_im_negated(k1) ? -1.f : 1.f;
+                col[row_slot(2 * (k1 - 1)) * kERow] = cmul(make_float2(re[k1].x, sg * im[k1].x), w);        // A_a[k1] W
+                col[row_slot(2 * (k1 - 1) + 1) * kERow] = cmul(make_float2(re[k1].y, sg * im[k1].y), w);    // A_b[k1] W
             } else {
-                col[row_slot(19) * kERow] = cmul(z[10], w);                       // row 19: (A_a[10] + i A_b[10]) W^(10 j) / 2
+                col[row_slot(19) * kERow] = cmul(re[10], w);                      // row 19: (A_a[10] + i A_b[10]) W^(10 j) / 2
             }
         }
     }
@@ -490,9 +558,10 @@ TALFE_HD constexpr int ws_y_off(int fr) { return fr * kMaxMels + 4 * (fr >> 1); 
 // pairs x 2 adjacent mels -> words 2 g + f + 33 r) and the store loop's reads (lane = frame) are both conflict-free
 TALFE_HD constexpr int ws_yt_off(int mel, int fr) { return mel * kWsYtStride + fr; }
 
-// Stage 1, first half: 28 waveform samples -> window -> complex FFT-20 of (frame a + i frame b), in registers.
+// Stage 1, first half: 28 waveform samples -> window -> real-input FFT-20 of frame a and frame b (one in each half of
+// every packed register), in registers.
 template <typename XT>
-TALFE_HD void stage1_ws_fft(const XT* __restrict__ p /* xg + j */, const float (&win)[20], cf (&z)[20]) {
+TALFE_HD void stage1_ws_fft(const XT* __restrict__ p /* xg + j */, const float (&win)[20], cf (&re)[11], cf (&im)[11]) {
     constexpr int kSkew = XLayout<XT>::kSkew;
     cf xin[20];
 #pragma unroll
@@ -501,25 +570,23 @@ TALFE_HD void stage1_ws_fft(const XT* __restrict__ p /* xg + j */, const float (
         const int ib = 20 * m + kHop + (20 * m + kHop >= kXBlock ? kSkew : 0);
         xin[m] = make_float2(x_to_float(p[ia]), x_to_float(p[ib]));
     }
-    fft20_windowed<true>(xin, win, z);                  // window taps as scalar-broadcast operands of FMUL2 / FFMA2
+    rfft20_pair_windowed(xin, win, re, im);             // window taps as scalar-broadcast operands of FMUL2 / FFMA2
 }
 
-// Stage 1, second half: untangle the two real-input transforms, twiddle by tw[k1-1] = W400^(j k1), write
-// column j of the pair's 20 exchange rows (same row meaning as the legacy stage1; rows in natural order).
-TALFE_HD void stage1_ws_store(const cf (&z)[20], const cf (&tw)[10], cf* __restrict__ col /* E + ws_e_base(g1) + j */) {
-    // With A_a = (sm.x, df.y), A_b = (sm.y, -df.x), w = tw[k1-1] and iw = i w:
-    //   A_a w   = sm.x w  + df.y iw        i A_b w = sm.y iw + df.x w
-    // each an FMUL2 + FFMA2 with scalar-broadcast operands (7 instructions per k1 against 10 for two scalar complex
-    // products), with the same fused/unfused roundings as cmul(): bit-identical to the legacy stage1().
-    col[18 * kWsERow] = z[0];
+// Stage 1, second half: twiddle by tw[k1-1] = W400^(j k1) and write column j of the pair's 20 exchange rows (same row
+// meaning as the legacy stage1; rows in natural order).  With A = re + i im (one frame's half of the packed registers),
+// w = tw[k1-1] and iw = i w:   A w = re w + im iw   — an FMUL2 + FFMA2 with scalar-broadcast operands per frame, with the
+// same fused / unfused roundings as cmul(): bit-identical to the legacy stage1().  Where the transform left -im, the
+// product uses -i w instead (rfft20_im_negated).  5 instructions per k1 for both frames.
+TALFE_HD void stage1_ws_store(const cf (&re)[11], const cf (&im)[11], const cf (&tw)[10], cf* __restrict__ col /* E + ws_e_base(g1) + j */) {
+    col[18 * kWsERow] = re[0];
 #pragma unroll
     for (int k1 = 1; k1 < 10; ++k1) {
-        const cf sm = cadd(z[k1], z[20 - k1]), df = csub(z[k1], z[20 - k1]);
-        const cf w = tw[k1 - 1], iw = times_i(w);
-        col[(2 * (k1 - 1)) * kWsERow] = cfma_ss(sm.x, w, df.y, iw);
-        col[(2 * (k1 - 1) + 1) * kWsERow] = cfma_ss(sm.y, iw, df.x, w);
+        const cf w = tw[k1 - 1], iw = rfft20_im_negated(k1) ? times_minus_i(w) : times_i(w);
+        col[(2 * (k1 - 1)) * kWsERow] = cfma_ss(re[k1].x, w, im[k1].x, iw);
+        col[(2 * (k1 - 1) + 1) * kWsERow] = cfma_ss(re[k1].y, w, im[k1].y, iw);
     }
-    col[19 * kWsERow] = cfma_ss(z[10].x, tw[9], z[10].y, times_i(tw[9]));
+    col[19 * kWsERow] = cfma_ss(re[10].x, tw[9], re[10].y, times_i(tw[9]));
 }
 
 // Stage 2 (consumer thread (g, r)): |FFT-20(row r)|^2 kept in registers until the power array is free.

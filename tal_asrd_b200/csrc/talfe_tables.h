@@ -41,7 +41,7 @@ struct HostTables {
     MelLayout layout;
     int pstride;                    // float2 entries per pair in the power array
     std::vector<float> win_t;       // [20][20]  0.5 * window[j + 20 m]
-    std::vector<float> tw_t;        // [20][10] complex: W400^(j k1), k1 = 1..10
+    std::vector<float> tw_t;        // [20][10] complex: 2 W400^(j k1), k1 = 1..9, and W400^(10 j)
     std::vector<float> w_t;         // [20][wstride]
     std::vector<int> mel_lo;        // [4][20] slot-major: first bin of the mel owned by (slot i, lane c)
     std::vector<int> mel_id;        // [4][20] slot-major: which mel (slot i, lane c) owns, -1 = none
@@ -67,7 +67,7 @@ inline int build_tables(int n_mels, const float* window, const float* fb, HostTa
     for (int j = 0; j < 20; ++j)
         for (int k1 = 1; k1 <= 10; ++k1) {
             const double ang = -2.0 * M_PI * (double)((j * k1) % kNfft) / kNfft;
-            const double s = 1.0;
+            const double s = k1 < 10 ? 2.0 : 1.0;              // the transform runs on 0.5 * window: rows 0..17 get their factor 2 here
             t.tw_t[(j * 10 + k1 - 1) * 2 + 0] = (float)(s * std::cos(ang));
             t.tw_t[(j * 10 + k1 - 1) * 2 + 1] = (float)(s * std::sin(ang));
         }

@@ -69,6 +69,8 @@ struct __align__(16) WsDesc {
     int flags;                     // bit 0 active, bit 1 full, bit 2 x tile fetched by the copy engine, bit 3 bulk store allowed
     int pad;
     float* out_tile;               // &out[row][t0 - frame0][0] for [.., T, 80] outputs
+    const void* src;               // first sample of the tile in global memory (bulk tiles)
+    long long pad2;
 };
 constexpr int kWsDescRing = 8;
 enum { kWsActive = 1, kWsFull = 2, kWsBulkX = 4, kWsBulkY = 8 };
@@ -96,6 +98,8 @@ __device__ __forceinline__ WsDesc ws_describe(const KernelArgs& a, int row, int 
     d.out_tile = a.out + (a.out_offsets ? a.out_offsets[row] * kMaxMels : (long long)row * a.out_row_stride) +
                  (long long)(d.t0 - a.frame0) * kMaxMels;
     src_off = (long long)row * a.row_stride + b0;
+    d.src = nullptr;
+    d.pad2 = 0;
     return d;
 }
 
@@ -129,21 +133,29 @@ __device__ __forceinline__ void ws_producer(const KernelArgs& a, unsigned char* 
     // Loader duty, taken in turn by the producer warps (tile kk by warp kk % 10, one tile ahead of the FFTs): all 32
     // lanes run it (no divergent waiting): descriptor, wait for x[kk & 1] to be free, byte count, the 17 pieces of the
     // tile fetch (lane i = piece i, one per 320-sample skew block), then an L2 prefetch of the tile after next.
+    // (Measured and rejected in round 2, profiles/r02_ab_variants.json: issuing the fetch of tile k+2 from whichever
+    // producer warp is the last to have read tile k — almost two tile times of lead instead of one — needs the pair's 28
+    // samples or its transform live across the issue and spills: 85 us / 120 us against 76 us.)
     const int step = (int)gridDim.x;
-    auto load_duty = [&](int kk) {
+    auto describe = [&](int kk) {
         const int tile = (int)blockIdx.x + kk * step;
         const int row = tile / a.tiles_per_row, tq = tile - row * a.tiles_per_row;
-        const int lbuf = kk & 1;
         long long src_off;
-        const WsDesc d = ws_describe(a, row, tq, src_off);
+        WsDesc d = ws_describe(a, row, tq, src_off);
+        d.src = reinterpret_cast<const XT*>(a.wave) + src_off;
         if (lane == 0) s_desc[kk & (kWsDescRing - 1)] = d;
-        if (kk >= 2) mbar_wait_sleep(x_empty + lbuf, ((kk - 2) >> 1) & 1);               // tile kk-2 has left x[lbuf]
+        __syncwarp();
+    };
+    auto issue = [&](int kk) {
+        const int lbuf = kk & 1;
+        const WsDesc* dp = s_desc + (kk & (kWsDescRing - 1));
+        const int flags = dp->flags;
 #if defined(TALFE_ABLATE) && (TALFE_ABLATE & 16)
         if (false) {                                                     // timing experiment only: no waveform fetch
 #else
-        if (d.flags & kWsBulkX) {
+        if (flags & kWsBulkX) {
 #endif
-            const XT* src = reinterpret_cast<const XT*>(a.wave) + src_off;
+            const XT* src = reinterpret_cast<const XT*>(dp->src);
             if (lane == 0) mbar_expect_tx(x_full + lbuf, kWsTileSamples * (int)sizeof(XT));   // release: publishes the descriptor too
             __syncwarp();
             if (lane * kXBlock < kWsTileSamples)
@@ -154,6 +166,13 @@ __device__ __forceinline__ void ws_producer(const KernelArgs& a, unsigned char* 
             mbar_arrive(x_full + lbuf);                                                  // nothing in flight: descriptor only
         }
         __syncwarp();
+    };
+    auto load_duty = [&](int kk) {
+        const int tile = (int)blockIdx.x + kk * step;
+        const int row = tile / a.tiles_per_row, tq = tile - row * a.tiles_per_row;
+        describe(kk);
+        if (kk >= 2) mbar_wait_sleep(x_empty + (kk & 1), ((kk - 2) >> 1) & 1);           // tile kk-2 has left x[kk & 1]
+        issue(kk);
         if (a.l2_prefetch && lane == 0 && tile + 2 * step < a.n_tiles) {                 // tile kk+2: HBM -> L2
             int r2 = row, q2 = tq;
             ws_advance(a, r2, q2, 2 * step);
@@ -170,7 +189,7 @@ __device__ __forceinline__ void ws_producer(const KernelArgs& a, unsigned char* 
         mbar_wait_sleep(x_full + buf, (k >> 1) & 1);                    // descriptor published, bulk tile landed
         const int flags = s_desc[k & (kWsDescRing - 1)].flags;
         const bool active = flags & kWsActive;
-        cf z[20];
+        cf re[11], im[11];
         if (active) {
             if (!(flags & kWsBulkX)) {
                 // edge tile (reflection), unaligned row or chunk boundary: element-wise staging by all producers
@@ -190,15 +209,7 @@ __device__ __forceinline__ void ws_producer(const KernelArgs& a, unsigned char* 
                 }
                 named_bar_sync(2, kWsRoleThreads);
             }
-#if defined(TALFE_ABLATE) && (TALFE_ABLATE & 2)
-            {   // timing experiment only: window multiply without the FFT-20
-                const XT* p = reinterpret_cast<const XT*>(reinterpret_cast<const unsigned char*>(xg) + buf * kXBufBytes);
-#pragma unroll
-                for (int m = 0; m < 20; ++m) z[m] = make_float2(win[m] * x_to_float(p[20 * m]), win[m] * x_to_float(p[20 * m + 8]));
-            }
-#else
-            stage1_ws_fft<XT>(reinterpret_cast<const XT*>(reinterpret_cast<const unsigned char*>(xg) + buf * kXBufBytes), win, z);
-#endif
+            stage1_ws_fft<XT>(reinterpret_cast<const XT*>(reinterpret_cast<const unsigned char*>(xg) + buf * kXBufBytes), win, re, im);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(x_empty + buf);                      // this warp no longer reads x[buf]
@@ -212,7 +223,7 @@ __device__ __forceinline__ void ws_producer(const KernelArgs& a, unsigned char* 
                 tw[2 * h] = make_float2(tt.x, tt.y);
                 tw[2 * h + 1] = make_float2(tt.z, tt.w);
             }
-            stage1_ws_store(z, tw, col0 + buf * kWsECf);
+            stage1_ws_store(re, im, tw, col0 + buf * kWsECf);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(e_full + buf);
@@ -439,7 +450,99 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, unsigned char* 
     if (lane == 0) bulk_wait_all<0>();                                  // shared memory must outlive the copies that read it
 }
 
-template <typename XT>
+// ------------------------------------------------------------------------------------------ fused normalisation
+// Grid-wide barrier in global memory (one thread per CTA calls it; the launch is cooperative, so every CTA is resident).
+// bar[0] counts arrivals and is reset by the last arriver, bar[1] is the generation the others wait on: nothing needs
+// zeroing between launches, and the grid size may change from one launch to the next.
+__device__ __forceinline__ void ws_grid_barrier(unsigned* bar, unsigned n_ctas) {
+    unsigned gen, old;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(bar + 1) : "memory");
+    asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(bar) : "memory");
+    if (old == n_ctas - 1) {
+        asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(bar), "r"(0u) : "memory");
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar + 1) : "memory");
+    } else {
+        unsigned now;
+        do {
+            __nanosleep(64);
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(now) : "l"(bar + 1) : "memory");
+        } while (now == gen);
+    }
+}
+
+// mel -= mel.mean() (tal/asr/models.py:52) without a second launch.  Called by all 640 threads after both roles have
+// left their tile loops.  The reduction order is the one sub_scalar_flat_kernel uses (256 strided sums, binary tree),
+// so the fused and the two-kernel paths produce bit-identical features.
+struct WsNormArgs {            // passed by value (registers): a reference to the kernel parameters would force a stack copy
+    const double2* partials; unsigned* grid_bar; double norm_count; double* stats_out;
+    float* out; long long out_row_stride; int tiles_per_row, n_frames, n_tiles;
+};
+__device__ __noinline__ void ws_fused_batch_mean(const WsNormArgs a, unsigned char* smem_scratch) {
+    // thread and tile counts are re-derived here: nothing of this epilogue stays live in registers across the tile loops
+    const int tid = (int)threadIdx.x;
+    const int n_my = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    double* s_a = reinterpret_cast<double*>(smem_scratch);             // [256] sums, [256] sums of squares, then the mean
+    double* s_b = s_a + 256;
+    // every bulk store of this CTA has completed (its issuing lane waited for the whole group); make the copy engine's
+    // writes and the generic-proxy reads below agree, then meet: the partial of this CTA was written by consumer thread 0
+    asm volatile("fence.proxy.async;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        ws_grid_barrier(a.grid_bar, gridDim.x);
+        __threadfence();
+    }
+    __syncthreads();
+    if (tid < 256) {
+        double ra = 0.0, rb = 0.0;
+        for (int i = tid; i < (int)gridDim.x; i += 256) {
+            const double2 v = __ldcg(a.partials + i);
+            ra += v.x; rb += v.y;
+        }
+        s_a[tid] = ra; s_b[tid] = rb;
+    }
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (tid < o) { s_a[tid] += s_a[tid + o]; s_b[tid] += s_b[tid + o]; }
+        __syncthreads();
+    }
+    const float mean = a.norm_count > 0.0 ? (float)(s_a[0] / a.norm_count) : 0.f;
+    if (a.stats_out && blockIdx.x == 0 && tid == 0) { a.stats_out[0] = a.norm_count; a.stats_out[1] = s_a[0]; a.stats_out[2] = s_b[0]; }
+    // own tiles, in the order they were written (a 61 MB result sits in the 126 MB L2 entirely): one float4 per thread
+    // and tile (32 frames x 80 mels = 640 float4), kNormUnroll tiles in flight per thread — the sweep is bound by L2
+    // latency x bandwidth, so the loads of many tiles are issued before the first subtraction
+    constexpr int kNormUnroll = 14;
+    const int step = (int)gridDim.x;
+    const int tq0 = (int)blockIdx.x % a.tiles_per_row, row0 = (int)blockIdx.x / a.tiles_per_row;
+    const int dq = step % a.tiles_per_row, dr = step / a.tiles_per_row;      // tile k+1 from tile k without a division
+    int tq = tq0, row = row0;
+    for (int k0 = 0; k0 < n_my; k0 += kNormUnroll) {
+        float4 v[kNormUnroll];
+        float4* ptr[kNormUnroll];
+#pragma unroll
+        for (int u = 0; u < kNormUnroll; ++u) {
+            ptr[u] = nullptr;
+            if (k0 + u < n_my) {
+                const int nfr = min(kWsFrames, a.n_frames - tq * kWsFrames);
+                if (tid < nfr * (kMaxMels / 4)) {
+                    ptr[u] = reinterpret_cast<float4*>(a.out + (long long)row * a.out_row_stride + (long long)tq * (kWsFrames * kMaxMels)) + tid;
+                    v[u] = __ldcg(ptr[u]);
+                }
+                tq += dq; row += dr;
+                if (tq >= a.tiles_per_row) { tq -= a.tiles_per_row; ++row; }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kNormUnroll; ++u) {
+            if (ptr[u]) {
+                v[u].x -= mean; v[u].y -= mean; v[u].z -= mean; v[u].w -= mean;
+                __stcs(ptr[u], v[u]);
+            }
+        }
+    }
+}
+
+template <typename XT, bool kFuse>
 __global__ void __launch_bounds__(kWsThreads, 1) logmel_ws_kernel(const KernelArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     // carve-up: tables (twiddles | mel weights | first bins) | x[2] | E[2] | P[2] | Y[2] | descriptor ring | 8 mbarriers
@@ -468,6 +571,10 @@ __global__ void __launch_bounds__(kWsThreads, 1) logmel_ws_kernel(const KernelAr
     const int n_my = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles blockIdx.x, + gridDim.x, ...
     if (tid < kWsRoleThreads) ws_producer<XT>(a, smem, s_x0, s_e0, s_desc, s_bar, tid, n_my);
     else ws_consumer<XT>(a, smem, s_e0, s_p0, s_y0, s_desc, s_bar, tid - kWsRoleThreads, n_my);
+    if (kFuse) {                                                       // the exchange buffers are free now: scratch for the reduction
+        const WsNormArgs na{a.partials, a.grid_bar, a.norm_count, a.stats_out, a.out, a.out_row_stride, a.tiles_per_row, a.n_frames, a.n_tiles};
+        ws_fused_batch_mean(na, smem + a.blob_bytes + 2 * kXFloats * sizeof(float));
+    }
 }
 
 constexpr size_t ws_smem_bytes(size_t table_bytes) {

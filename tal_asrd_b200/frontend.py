@@ -14,7 +14,9 @@ in ``include/talfe.h``; PyTorch only provides device memory and the current stre
 """
 from __future__ import annotations
 
+import hashlib
 import math
+import os
 from typing import Optional
 
 import torch
@@ -63,7 +65,8 @@ def encoder_padding_mask(audio_lens: torch.Tensor, enc_frames: int) -> torch.Ten
 
 
 class _Plan:
-    """Owns one talfe_plan (device tables) and frees it with the object."""
+    """Owns one talfe_plan (device tables) and frees it with the object.  Also keeps the per-stream workspaces the
+    calls need (allocated once and grown on demand, not once per call)."""
 
     def __init__(self, device: torch.device, n_mels: int, window: torch.Tensor, fb: torch.Tensor):
         import ctypes
@@ -77,9 +80,27 @@ class _Plan:
             raise ValueError("window must have 400 elements and fb must be [201, n_mels]")
         _lib.check(self.lib.talfe_plan_create(ctypes.byref(self.handle), device.index, n_mels,
                                               win.data_ptr(), fbc.data_ptr()), "talfe_plan_create")
+        self._ws = {}                 # cuda_stream -> uint8 workspace tensor
+        self._ws_need = {}            # (batch, n_frames) -> bytes
+        self._run = self.lib.talfe_run
+        self._forward = self.lib.talfe_logmel_forward
 
     def workspace_bytes(self, batch: int, n_frames: int) -> int:
-        return int(self.lib.talfe_workspace_bytes(self.handle, batch, n_frames))
+        key = (batch, n_frames)
+        need = self._ws_need.get(key)
+        if need is None:
+            need = self._ws_need[key] = int(self.lib.talfe_workspace_bytes(self.handle, batch, n_frames))
+        return need
+
+    def workspace(self, stream_ptr: int, batch: int, n_frames: int) -> torch.Tensor:
+        """Workspace for a call on the given stream.  One buffer per stream (calls on one stream are ordered, so they
+        can share it); it only ever grows.  The replaced buffer goes back to the caching allocator, which keeps it
+        away from other streams until the work queued on this one has passed."""
+        need = self.workspace_bytes(batch, n_frames)
+        ws = self._ws.get(stream_ptr)
+        if ws is None or ws.numel() < need:
+            ws = self._ws[stream_ptr] = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=self.device)
+        return ws
 
     def __del__(self):
         try:
@@ -88,6 +109,24 @@ class _Plan:
                 self.handle = None
         except Exception:
             pass
+
+
+# Plans hold native handles (a ctypes CDLL and a talfe_plan*): they live HERE, outside every module's state, so that a
+# LogMelSpec can be deep-copied, pickled and torch.save'd like the reference module at any time, and so that copies of
+# a module (EMA / SWA replicas, DDP spawn) share one set of device tables.  Key: device, n_mels and the table values.
+_PLANS = {}
+
+
+def _shared_plan(device: torch.device, n_mels: int, window: torch.Tensor, fb: torch.Tensor) -> _Plan:
+    win = window.detach().to("cpu", torch.float32).contiguous()
+    fbc = fb.detach().to("cpu", torch.float32).contiguous()
+    # the library reads its development switches when a plan is created: they are part of what a plan is
+    knobs = tuple(os.environ.get(k) for k in ("TALFE_KERNEL", "TALFE_L2_PREFETCH", "TALFE_FUSED_NORM", "TALFE_LIB"))
+    key = (device.index, n_mels, hashlib.sha1(win.numpy().tobytes()).digest(), hashlib.sha1(fbc.numpy().tobytes()).digest(), knobs)
+    plan = _PLANS.get(key)
+    if plan is None:
+        plan = _PLANS[key] = _Plan(device, n_mels, win, fbc)
+    return plan
 
 
 def _require_cuda(t: torch.Tensor) -> torch.device:
@@ -103,6 +142,11 @@ def _run(plan: _Plan, audio: torch.Tensor, *, norm: int, layout: int, eps: float
          defer: bool = False, out_offsets: Optional[torch.Tensor] = None, packed_frames: int = 0,
          bands=None) -> torch.Tensor:
     device = audio.device
+    if torch.cuda.current_device() != device.index:
+        with torch.cuda.device(device):          # launches and allocations below need `device` current
+            return _run(plan, audio, norm=norm, layout=layout, eps=eps, lens=lens, origin=origin, total_len=total_len,
+                        frame0=frame0, n_frames=n_frames, out=out, stats=stats, accumulate=accumulate, defer=defer,
+                        out_offsets=out_offsets, packed_frames=packed_frames, bands=bands)
     B, buf_len = audio.shape
     if total_len is None:
         total_len = buf_len
@@ -116,8 +160,8 @@ def _run(plan: _Plan, audio: torch.Tensor, *, norm: int, layout: int, eps: float
         out = torch.empty(shape, dtype=torch.float32, device=device)
     elif tuple(out.shape) != shape or out.dtype != torch.float32 or not out.is_contiguous() or out.device != device:
         raise ValueError(f"out must be a contiguous float32 tensor of shape {shape} on {device}")
-    ws_bytes = plan.workspace_bytes(B, n_frames)
-    workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+    stream_ptr = torch.cuda.current_stream(device).cuda_stream
+    workspace = plan.workspace(stream_ptr, B, n_frames)
     job = _lib.Job()
     job.wave = audio.data_ptr()
     job.wave_dtype = _DTYPES[audio.dtype]
@@ -138,14 +182,36 @@ def _run(plan: _Plan, audio: torch.Tensor, *, norm: int, layout: int, eps: float
     job.defer_normalise = 1 if defer else 0
     job.stats = stats.data_ptr() if stats is not None else None
     job.workspace = workspace.data_ptr()
-    job.workspace_bytes = ws_bytes
+    job.workspace_bytes = workspace.numel()
     job.out_offsets = out_offsets.data_ptr() if out_offsets is not None else None
     if bands is not None:
         fb, tb = bands
         job.freq_bands, job.time_bands, job.n_bands = fb.data_ptr(), tb.data_ptr(), fb.shape[1]
-    with torch.cuda.device(device):
-        job.stream = torch.cuda.current_stream(device).cuda_stream
-        _lib.check(plan.lib.talfe_run(plan.handle, job), "talfe_run")
+    job.stream = stream_ptr
+    rc = plan._run(plan.handle, job)
+    if rc:
+        _lib.check(rc, "talfe_run")
+    return out
+
+
+def _forward_fast(plan: _Plan, audio: torch.Tensor, eps: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """LogMelSpec.forward semantics through the one-call entry point talfe_logmel_forward (no job struct to fill):
+    the shortest host path, which is what bounds small calls (one 60 s clip is ~10 us of device work)."""
+    device = audio.device
+    if torch.cuda.current_device() != device.index:
+        with torch.cuda.device(device):
+            return _forward_fast(plan, audio, eps, out)
+    B, L = audio.shape
+    T = 1 + L // HOP
+    if out is None:
+        out = torch.empty((B, T, plan.n_mels), dtype=torch.float32, device=device)
+    stream_ptr = torch.cuda.current_stream(device).cuda_stream
+    ws = plan.workspace(stream_ptr, B, T)
+    rc = plan._forward(plan.handle, audio.data_ptr(), _DTYPES[audio.dtype], B, L,
+                       audio.stride(0) if B > 1 else max(audio.stride(0), L), out.data_ptr(), eps,
+                       ws.data_ptr(), ws.numel(), stream_ptr)
+    if rc:
+        _lib.check(rc, "talfe_logmel_forward")
     return out
 
 
@@ -178,9 +244,16 @@ class _MelTransformBuffers(nn.Module):
 class LogMelSpec(nn.Module):
     """Drop-in for ``tal.asr.models.LogMelSpec`` (models.py:15-53) on a B200.
 
-    forward(audio[B, L]) -> float32 [B, 1 + L // 160, n_mels], contiguous, no grad:
+    forward(audio[B, L]) -> [B, 1 + L // 160, n_mels], contiguous, no grad:
     log(mel_power + eps) minus ONE scalar mean over the whole batch result (models.py:50-52).
     Input may be float32, float16 (what ``.half()`` callers pass, system.py:92) or int16 PCM.
+
+    Output dtype follows the reference's type promotion between the waveform and the module's buffers
+    (``window`` / ``fb``): float32 whenever either is float32 — a float32 module fed ``audio.half()`` returns
+    float32, as torchaudio does — and float16 only when the module itself has been halved (``model.half()``,
+    tal/asr/transcribe.py:255) AND the waveform is half, which is what the half-precision TDS encoder then
+    expects.  The arithmetic is float32 in every case, with the unrounded float32 tables (a halved module's
+    rounded buffers are kept for ``state_dict`` compatibility only); the cast happens once at the end.
     """
 
     def __init__(self, sr: int = DEFAULT_SR, n_mels: int = 80, eps: float = 1e-6):
@@ -195,6 +268,17 @@ class LogMelSpec(nn.Module):
         self.sr, self.n_mels, self.eps = sr, n_mels, eps
         self._plans = {}
 
+    # --- native handles never enter the module's state: deepcopy / pickle / torch.save work at any time (the
+    # reference module can be copied and pickled; Lightning's ddp spawn and EMA / SWA replicas rely on it)
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_plans"] = {}
+        return state
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._plans = {}
+
     def _load_from_state_dict(self, *args, **kwargs):
         super()._load_from_state_dict(*args, **kwargs)
         self._plans = {}                       # tables may have been replaced by checkpoint values
@@ -204,11 +288,20 @@ class LogMelSpec(nn.Module):
         return super()._apply(fn, *args, **kwargs)
 
     def plan(self, device: torch.device) -> _Plan:
-        key = (device.type, device.index)
-        if key not in self._plans:
-            self._plans[key] = _Plan(device, self.n_mels, self.mel_transform.spectrogram.window,
-                                     self.mel_transform.mel_scale.fb)
-        return self._plans[key]
+        key = device.index
+        plan = self._plans.get(key)
+        if plan is None:
+            window, fb = self.mel_transform.spectrogram.window, self.mel_transform.mel_scale.fb
+            if window.dtype != torch.float32 or fb.dtype != torch.float32:
+                # halved module: its buffers hold ROUNDED tables; the kernels run in float32 from the exact ones
+                window, fb = reference_tables(self.n_mels, self.sr)
+            plan = self._plans[key] = _shared_plan(device, self.n_mels, window, fb)
+        return plan
+
+    def _out_dtype(self, audio: torch.Tensor) -> torch.dtype:
+        if audio.dtype == torch.float16 and self.mel_transform.spectrogram.window.dtype == torch.float16:
+            return torch.float16
+        return torch.float32
 
     @torch.jit.ignore
     def forward(self, audio: torch.Tensor) -> torch.Tensor:
@@ -216,8 +309,8 @@ class LogMelSpec(nn.Module):
             audio = _prepare_audio(audio)
             device = _require_cuda(audio)
             num_frames(audio.shape[1])
-            return _run(self.plan(device), audio, norm=_lib.NORM_BATCH_MEAN, layout=_lib.LAYOUT_TM,
-                        eps=self.eps, lens=None)
+            y = _forward_fast(self.plan(device), audio, self.eps)
+            return y if self._out_dtype(audio) == torch.float32 else y.half()
 
     @torch.jit.ignore
     def features(self, audio: torch.Tensor, audio_lens: Optional[torch.Tensor] = None, norm: str = "batch",

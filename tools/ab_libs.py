@@ -11,7 +11,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from tal_asrd_b200 import _build, _lib  # noqa: E402
-from tal_asrd_b200 import LogMelSpec  # noqa: E402
+from tal_asrd_b200 import LogMelSpec, frontend  # noqa: E402
 
 out_path, libs = sys.argv[1], sys.argv[2:]
 B, L = 64, 480000
@@ -55,7 +55,9 @@ for rep in range(2):                                                    # two ro
         for kv in (env.split(",") if env else []):
             os.environ[kv.split("=")[0]] = kv.split("=")[1]
         _lib._LIB = None
-        _build.LIB_PATH = os.path.abspath(path)
+        frontend._PLANS.clear()                                           # plans are cached per table set: one per build here
+        os.environ["TALFE_LIB"] = os.path.abspath(path)
+        os.environ["TALFE_ABI_CHECK"] = "0"                               # older builds (round 1) lack the size / version exports
         lib = _lib.load()
         if waves is None:
             waves = []
