@@ -126,6 +126,9 @@ int64_t talfe_num_frames(int64_t n_samples);
 int talfe_plan_create(talfe_plan** plan, int device, int n_mels, const float* window_host, const float* fb_host);
 void talfe_plan_destroy(talfe_plan* plan);
 int talfe_plan_n_mels(const talfe_plan* plan);
+/* Kernel launches one talfe_logmel_forward of this shape makes with this plan (for honest launch accounting):
+ * 1 when the scalar-mean subtraction runs inside the transform kernel (small calls), 2 when a separate sweep follows. */
+int talfe_launches_per_forward(const talfe_plan* plan, int64_t batch, int64_t n_samples);
 
 /* Bytes of workspace talfe_run needs for `batch` rows of `n_frames` frames. */
 size_t talfe_workspace_bytes(const talfe_plan* plan, int64_t batch, int64_t n_frames);

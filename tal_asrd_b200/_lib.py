@@ -16,7 +16,7 @@ ERR_TOO_SHORT = -2
 EXPECTED_VERSION = 102     # TALFE_VERSION of include/talfe.h this binding was written against
 
 EXPORTED = [
-    "talfe_version", "talfe_job_size", "talfe_probe_fp32_fma_rate",
+    "talfe_version", "talfe_job_size", "talfe_probe_fp32_fma_rate", "talfe_launches_per_forward",
     "talfe_strerror", "talfe_last_cuda_error", "talfe_num_frames", "talfe_plan_create",
     "talfe_plan_destroy", "talfe_plan_n_mels", "talfe_workspace_bytes", "talfe_run", "talfe_logmel_forward",
     "talfe_apply_stats", "talfe_allreduce_stats", "talfe_synth_fill", "talfe_stream_staging_bytes",
@@ -69,6 +69,8 @@ def load() -> ctypes.CDLL:
                            f"this binding ({EXPECTED_VERSION} / {ctypes.sizeof(Job)}): rebuild the library")
     lib.talfe_probe_fp32_fma_rate.restype = c_int
     lib.talfe_probe_fp32_fma_rate.argtypes = [c_int, POINTER(c_double)]
+    lib.talfe_launches_per_forward.restype = c_int
+    lib.talfe_launches_per_forward.argtypes = [c_void_p, c_int64, c_int64]
     return _finish_binding(lib)
 
 

@@ -720,6 +720,14 @@ int talfe_version(void) { return TALFE_VERSION; }
 
 size_t talfe_job_size(void) { return sizeof(talfe_job); }
 
+int talfe_launches_per_forward(const talfe_plan* plan, int64_t batch, int64_t n_samples) {
+    if (!plan || batch < 1 || n_samples <= kHalf) return TALFE_ERR_INVALID;
+    const WorkspaceLayout w = workspace_layout(plan->n_mels, batch, 1 + n_samples / kHop);
+    const bool fused = plan->variant == 1 && plan->fuse_norm &&
+                       (plan->fuse_norm >= 2 || w.n_tiles <= (long long)kFuseMaxTilesPerCta * plan->sm_count);
+    return fused ? 1 : 2;
+}
+
 const char* talfe_strerror(int status) {
     switch (status) {
         case TALFE_OK: return "ok";

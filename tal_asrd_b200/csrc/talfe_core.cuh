@@ -591,6 +591,10 @@ TALFE_HD void stage1_ws_store(const cf (&re)[11], const cf (&im)[11], const cf (
 
 // Stage 2 (consumer thread (g, r)): |FFT-20(row r)|^2 kept in registers until the power array is free.
 // Normal rows r < 18: pw[q] = (bin k1 + 20 q, bin (20 - k1) + 20 q) of frame r & 1, k1 = 1 + r / 2.
+// (Measured and rejected in round 2, profiles/r02_ab_packed_power.json: leaving the last butterflies' results paired
+// across two output bins — (Re y1, Re y4), (Im y1, Im y4), one FFMA2 each with two scalar-broadcast operands — makes
+// |y|^2 of two bins one FMUL2 + one FFMA2 instead of four scalar instructions, 16 FMA-pipe slots fewer per row; the
+// extra register traffic pushed the kernel over its 96-register budget: 81.8 us against 77.6 us.)
 TALFE_HD void stage2_ws_power_normal(cf (&v)[20], cf (&pw)[10]) {
 #if !(defined(TALFE_ABLATE) && (TALFE_ABLATE & 4))
     fft20<true>(v);

@@ -35,7 +35,7 @@ def chunk_plan(total_len: int, chunk_frames: int):
     return plan
 
 
-DEFAULT_CHUNK_SECONDS = 120.0      # 12 001 frames = 376 tiles: every persistent CTA gets >= 2 tiles per chunk, and the per-chunk
+DEFAULT_CHUNK_SECONDS = 300.0      # 30 001 frames = 938 tiles: every persistent CTA gets >= 6 tiles per chunk, and the per-chunk
                                    # launch cost (two launches, ~10 us of device latency) stays below 10 % of the chunk's work
 
 
