@@ -44,6 +44,9 @@ constexpr int kColChunk = 256;                              // frames per block 
 static_assert(kNormalThreads % 32 == 0, "special rows must fill whole warps");
 
 thread_local int g_last_cuda_error = 0;
+#ifdef TALFE_TIMELINE
+unsigned* g_timeline = nullptr;
+#endif
 
 // runtime copy of talfe::row_slot() (the constexpr table would otherwise be materialised on the stack)
 __constant__ int c_row_slot[20] = {11, 16, 6, 17, 15, 4, 10, 13, 19, 8, 1, 14, 7, 12, 18, 5, 3, 0, 2, 9};
@@ -113,6 +116,7 @@ struct KernelArgs {
     unsigned* grid_bar;            // [0] arrivals of the current launch, [1] generation; self-resetting
     double norm_count;             // B * T * M
     double* stats_out;             // count, sum, sum of squares (or nullptr)
+    unsigned* timeline;            // -DTALFE_TIMELINE development builds only (nullptr otherwise)
 };
 
 // ------------------------------------------------------------------------------------------ K1
@@ -720,6 +724,15 @@ int talfe_version(void) { return TALFE_VERSION; }
 
 size_t talfe_job_size(void) { return sizeof(talfe_job); }
 
+#ifdef TALFE_TIMELINE
+int talfe_debug_timeline(unsigned* host_out /* [20][64][8] */) {     // development builds only; not declared in talfe.h
+    if (!g_timeline) return TALFE_ERR_INVALID;
+    TALFE_CUDA(cudaDeviceSynchronize());
+    TALFE_CUDA(cudaMemcpy(host_out, g_timeline, 20 * 64 * 8 * sizeof(unsigned), cudaMemcpyDeviceToHost));
+    return TALFE_OK;
+}
+#endif
+
 int talfe_launches_per_forward(const talfe_plan* plan, int64_t batch, int64_t n_samples) {
     if (!plan || batch < 1 || n_samples <= kHalf) return TALFE_ERR_INVALID;
     const WorkspaceLayout w = workspace_layout(plan->n_mels, batch, 1 + n_samples / kHop);
@@ -922,6 +935,14 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
     a.grid_bar = bar;
     a.norm_count = (double)dense * (double)job->batch;
     a.stats_out = job->stats;
+#ifdef TALFE_TIMELINE
+    {
+        static unsigned* tl = nullptr;                                  // development build: one global buffer, read back by
+        if (!tl) { cudaMalloc(&tl, 20 * 64 * 8 * sizeof(unsigned)); cudaMemset(tl, 0, 20 * 64 * 8 * sizeof(unsigned)); }
+        a.timeline = tl;                                                // talfe_debug_timeline()
+        g_timeline = tl;
+    }
+#endif
     {
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(use_ws ? kWsThreads : kThreads);

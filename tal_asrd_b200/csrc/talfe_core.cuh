@@ -540,7 +540,7 @@ TALFE_HD void mel_log_ref(int c, const cf* __restrict__ p2, const float* __restr
 //              groups for the pair-minor LDS.128 of stage 2;
 //   power      P[bin][g] (float2: frame a, frame b): stage 2 writes words 32 bin + 2 g + f (one wavefront per
 //              warp store), the mel stage reads 16 consecutive float2 per half-warp (one wavefront);
-//   features   Y[frame][80] staged per tile, row fr at float offset 80 fr + 4 (fr >> 1) (16-byte aligned rows
+//   features   Y[frame][80] staged per tile, row fr at float offset 80 fr + 4 (fr >> 2) (16-byte aligned rows
 //              for the bulk store to global memory; the pad leaves the scalar stores 2-way conflicted); for
 //              [.., 80, T] outputs the tile is staged transposed (ws_yt_off) and leaves by coalesced stores.
 constexpr int kWsGroups = 16;
@@ -553,7 +553,11 @@ constexpr int kWsPCf = kWsPBins * kWsGroups;
 constexpr int kWsYtStride = kWsFrames + 1;                              // transposed staging (layout [.., 80, T]): mel row stride 33
 constexpr int kWsYFloats = kMaxMels * kWsYtStride;                      // 2640 >= 32 * 80 + 4 * 16 (the [.., T, 80] staging)
 TALFE_HD constexpr int ws_e_base(int g) { return g * kWsEGroup + 2 * ((g >> 2) & 1); }
-TALFE_HD constexpr int ws_y_off(int fr) { return fr * kMaxMels + 4 * (fr >> 1); }
+// (16 bytes of padding after every kWsYChunk frames: a chunk leaves as ONE bulk copy.  Issuing a bulk copy costs the
+// issuing warp ~270 cycles (profiles/r02_timeline.json), so fewer and larger chunks matter; 4-frame chunks keep the
+// scalar staging stores at the 2-way conflicts that 2-frame chunks had, 8-frame chunks would make them 4-way.)
+constexpr int kWsYChunk = 4;
+TALFE_HD constexpr int ws_y_off(int fr) { return fr * kMaxMels + 4 * (fr / kWsYChunk); }
 // [.., 80, T] outputs stage the tile transposed, Yt[mel][frame] at mel * 33 + frame: the mel stage's stores (lanes = 16
 // pairs x 2 adjacent mels -> words 2 g + f + 33 r) and the store loop's reads (lane = frame) are both conflict-free
 TALFE_HD constexpr int ws_yt_off(int mel, int fr) { return mel * kWsYtStride + fr; }

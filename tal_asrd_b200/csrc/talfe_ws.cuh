@@ -46,6 +46,15 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* gmem_src, unsigned 
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
 }
 
+// -DTALFE_TIMELINE: development build that records, for CTA 0, the SM clock at every phase boundary of every warp and
+// tile into KernelArgs::timeline ([warp 20][tile 64][8] uint32): where a latency-bound pipeline loses its time cannot
+// be read off aggregate counters (tools/timeline.py).  Never defined in the product build.
+#ifdef TALFE_TIMELINE
+#define TL_MARK(warp_, k_, slot_) do { if (a.timeline && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (k_) < 64) \
+    a.timeline[(((warp_) * 64) + (k_)) * 8 + (slot_)] = (unsigned)clock64(); } while (0)
+#else
+#define TL_MARK(warp_, k_, slot_) do { } while (0)
+#endif
 #ifndef TALFE_WS_WAIT_HINT_NS
 #define TALFE_WS_WAIT_HINT_NS 1000000
 #endif
@@ -186,7 +195,9 @@ __device__ __forceinline__ void ws_producer(const KernelArgs& a, unsigned char* 
     for (int k = 0; k < n_my; ++k) {
         const int buf = k & 1;
         if (k + 1 < n_my && (k + 1) % kWsRoleWarps == warp) load_duty(k + 1);
+        TL_MARK(warp, k, 0);
         mbar_wait_sleep(x_full + buf, (k >> 1) & 1);                    // descriptor published, bulk tile landed
+        TL_MARK(warp, k, 1);
         const int flags = s_desc[k & (kWsDescRing - 1)].flags;
         const bool active = flags & kWsActive;
         cf re[11], im[11];
@@ -212,10 +223,12 @@ __device__ __forceinline__ void ws_producer(const KernelArgs& a, unsigned char* 
             stage1_ws_fft<XT>(reinterpret_cast<const XT*>(reinterpret_cast<const unsigned char*>(xg) + buf * kXBufBytes), win, re, im);
         }
         __syncwarp();
+        TL_MARK(warp, k, 2);
         if (lane == 0) mbar_arrive(x_empty + buf);                      // this warp no longer reads x[buf]
         __syncwarp();
         // every tile, active or not: a producer never runs more than one phase ahead of the consumers
         if (k >= 2) mbar_wait_sleep(e_empty + buf, ((k - 2) >> 1) & 1); // consumers have loaded E[buf] of tile k-2
+        TL_MARK(warp, k, 3);
         if (active) {
 #pragma unroll
             for (int h = 0; h < 5; ++h) {
@@ -228,12 +241,13 @@ __device__ __forceinline__ void ws_producer(const KernelArgs& a, unsigned char* 
         __syncwarp();
         if (lane == 0) mbar_arrive(e_full + buf);
         __syncwarp();
+        TL_MARK(warp, k, 4);
     }
 }
 
 // ------------------------------------------------------------------------------------------ consumers
-// Tile (k-1) leaves shared memory: full tiles of a [.., T, 80] output go out as 16 bulk copies of one 640-byte
-// frame pair each (pair w and w + 10 by lane 0 of consumer warp w: per-lane bulk copies are serialised by the
+// Tile (k-1) leaves shared memory: full tiles of a [.., T, 80] output go out as 8 bulk copies of 1 280 bytes (four
+// frames) each (chunks w and w + 5 by lane 0 of consumer warp w of the group: per-lane bulk copies are serialised by the
 // hardware interface, so they are spread over the warps); everything else (partial tiles, zero fill of frames
 // beyond a row's own length, [.., 80, T] layout, unaligned output) takes the cooperative element-wise path.
 // Returns whether bulk copies were issued.
@@ -249,8 +263,8 @@ __device__ __forceinline__ bool ws_store_tile(const KernelArgs& a, const WsDesc*
         if ((tid & 31) == 0) {
             float* dst = dp->out_tile;
 #pragma unroll
-            for (int w = tid >> 5; w < kWsGroups; w += kNW)
-                bulk_s2g(dst + 2 * w * kMaxMels, smem_u32(s_y + ws_y_off(2 * w)), 2 * kMaxMels * (unsigned)sizeof(float));
+            for (int w = tid >> 5; w < kWsFrames / kWsYChunk; w += kNW)
+                bulk_s2g(dst + kWsYChunk * w * kMaxMels, smem_u32(s_y + ws_y_off(kWsYChunk * w)), kWsYChunk * kMaxMels * (unsigned)sizeof(float));
             bulk_commit();
         }
         __syncwarp();
@@ -389,9 +403,12 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, unsigned char* 
     for (int k = grp; k < n_my; k += 2) {
         const WsDesc* dp = s_desc + (k & (kWsDescRing - 1));
         cf v[20];
+        TL_MARK(10 + warp, k, 0);
         named_bar_sync(bar_id, kCs2Threads);                            // A1: mel(k-2) finished everywhere
+        TL_MARK(10 + warp, k, 1);
         if (k >= 2) ws_store_tile<kCs2Threads>(a, s_desc + ((k - 2) & (kWsDescRing - 1)), s_y, gtid);
         mbar_wait_sleep(e_full, (k >> 1) & 1);
+        TL_MARK(10 + warp, k, 2);
         const int flags = dp->flags;
         const bool active = flags & kWsActive;
         if (active) {
@@ -402,15 +419,19 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, unsigned char* 
         __syncwarp();
         if (lane == 0) mbar_arrive(e_empty);                            // both rows of E[grp] are in registers
         __syncwarp();
+        TL_MARK(10 + warp, k, 3);
         if (active) stage2_row(v, r1, special1);
+        TL_MARK(10 + warp, k, 4);
         if (lane == 0) bulk_wait_read<0>();                             // this lane's store of tile k-2 has finished reading Y[grp]
         named_bar_sync(bar_id, kCs2Threads);                            // A2: P[grp](k) complete, Y[grp] free
+        TL_MARK(10 + warp, k, 5);
         float sum = 0.f, sumsq = 0.f;
         if (active) {
             mel_lane(s_w4a, lo0, yb_a, dp, flags, sum, sumsq);
             mel_lane(s_w4b, lo1, yb_b, dp, flags, sum, sumsq);
         }
         fence_proxy_async();                                            // Y[grp] writes -> visible to the bulk-copy engine
+        TL_MARK(10 + warp, k, 6);
         if (a.partials_per_tile) {
             double ds = (double)sum, dq = (double)sumsq;
 #pragma unroll
