@@ -10,6 +10,7 @@
 //
 // K1 work decomposition: one CTA = 16 groups of 20 threads = 16 frame pairs = 32 consecutive frames
 // of one row per tile; persistent CTAs stride over the tiles.  Math per group: talfe_core.cuh.
+#include <cuda.h>                  // CUtensorMap + the cuTensorMapEncodeTiled prototype only: the entry point is looked up at run time
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
@@ -51,6 +52,7 @@ unsigned* g_timeline = nullptr;
 // runtime copy of talfe::row_slot() (the constexpr table would otherwise be materialised on the stack)
 __constant__ int c_row_slot[20] = {11, 16, 6, 17, 15, 4, 10, 13, 19, 8, 1, 14, 7, 12, 18, 5, 3, 0, 2, 9};
 
+struct FlTables;                   // talfe_fl.cuh
 struct talfe_plan_impl {
     int device;
     int n_mels;
@@ -58,7 +60,10 @@ struct talfe_plan_impl {
     int ctas_per_sm;
     int ref_layout;                // 80-mel reference filterbank shape -> fully unrolled mel stage
     int variant;                   // 0 = legacy kernel (2 CTAs/SM, every thread runs every stage), 1 = warp-specialised
+    int fl;                        // frame-per-lane kernel for fp32 waveforms (TALFE_KERNEL=fl; needs the reference filterbank support)
+    FlTables* fl_tables;           // its uniform tables (host copy: they travel as a kernel parameter)
     int l2_prefetch;
+    int use_tma;                   // TALFE_TMA (default 1): fp32 tiles by one tensor copy instead of 17 bulk pieces
     size_t off_ws, ws_bytes, off_tw_ws, off_w_ws, off_lo_ws, ws_smem;   // table section staged by the ws kernel
     MelLayout layout;
     int pstride;
@@ -108,6 +113,8 @@ struct KernelArgs {
     const float* win_global;       // window taps [20][20] in global memory (read once into producer registers)
     int out_align_ok;              // every frame row of `out` starts 16-byte aligned (bulk stores allowed)
     int l2_prefetch;               // prefetch tile k+2 into L2 while tile k+1 travels to shared memory
+    int use_tma;                   // fp32 interior tiles arrive as one tensor copy (the kernel's CUtensorMap parameter is valid)
+    int use_tma_out;               // frame-per-lane kernel: full tiles of a [.., T, 80] output leave as one tensor store
     // reference normalisation fused into the kernel (one launch per LogMelSpec.forward): after its last tile every CTA
     // publishes its partial sum, the grid meets at a barrier in global memory (cooperative launch: all CTAs resident),
     // every CTA derives the same scalar mean from the partials in a fixed order and subtracts it from ITS OWN tiles,
@@ -224,6 +231,7 @@ __device__ __forceinline__ void load_tile(const KernelArgs& a, TileInfo& ti, XT*
 
 }  // namespace
 #include "talfe_ws.cuh"
+#include "talfe_fl.cuh"
 namespace {
 
 template <bool kRef, typename XT>
@@ -672,7 +680,8 @@ logmel_kernel_t kernel_for(bool ref_layout, int dtype) {
     return dtype == TALFE_F32 ? logmel_kernel<false, float> : dtype == TALFE_F16 ? logmel_kernel<false, __half> : logmel_kernel<false, short>;
 }
 
-logmel_kernel_t ws_kernel_for(int dtype, bool fuse = false) {
+typedef void (*logmel_ws_kernel_t)(const KernelArgs, const CUtensorMap);
+logmel_ws_kernel_t ws_kernel_for(int dtype, bool fuse = false) {
     if (fuse) return dtype == TALFE_F32 ? logmel_ws_kernel<float, true> : dtype == TALFE_F16 ? logmel_ws_kernel<__half, true> : logmel_ws_kernel<short, true>;
     return dtype == TALFE_F32 ? logmel_ws_kernel<float, false> : dtype == TALFE_F16 ? logmel_ws_kernel<__half, false> : logmel_ws_kernel<short, false>;
 }
@@ -711,6 +720,106 @@ WorkspaceLayout workspace_layout(int n_mels, long long batch, long long n_frames
     off += align_up((size_t)batch * TALFE_STATS_DOUBLES(n_mels) * sizeof(double), 256);
     w.total = off;
     return w;
+}
+
+// The waveform as the copy engine sees it (fp32 only): element (c0, c1, c2, c3) = sample 68 c1 + c0 of the 340-sample row that
+// starts 320 c2 samples after the first interior tile position of batch row c3.  Rows overlap by 20 samples on purpose: a box
+// of [68][5][17][1] written densely into shared memory IS the skewed tile (talfe_ws.cuh).  `shift` is the buffer index of
+// the sample the tile grid starts at (tile tq of a row begins at shift + 5120 tq); it is negative when the grid starts in
+// the reflected region, which only the first (edge) tile touches — that tile never uses the copy engine.
+typedef CUresult (*encode_tiled_t)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+encode_tiled_t tensor_map_encoder() {
+    static encode_tiled_t fn = []() -> encode_tiled_t {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult st;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &st) != cudaSuccess || st != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return reinterpret_cast<encode_tiled_t>(p);
+    }();
+    return fn;
+}
+
+bool encode_wave_map(CUtensorMap* tm, const float* wave, long long shift, long long buf_len, long long row_stride, long long batch) {
+    const encode_tiled_t enc = tensor_map_encoder();
+    if (!enc) return false;
+    const long long rows = (buf_len - shift - kWsTmaRowFloats) / kXBlock + 1;      // 340-sample rows that end inside the buffer
+    if (buf_len - shift < kWsTmaRowFloats || rows < kWsTmaRows) return false;
+    const cuuint64_t dims[4] = {(cuuint64_t)kWsTmaInner, (cuuint64_t)kWsTmaMid, (cuuint64_t)rows, (cuuint64_t)batch};
+    const cuuint64_t strides[3] = {kWsTmaInner * sizeof(float), kXBlock * sizeof(float), (cuuint64_t)row_stride * sizeof(float)};
+    const cuuint32_t box[4] = {kWsTmaInner, kWsTmaMid, kWsTmaRows, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(wave + shift), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// ---- frame-per-lane kernel: host side
+void fl_build_tables(const float* window, const float* fb, FlTables* t) {
+    for (int p = 0; p < 10; ++p)
+        for (int m = 0; m < 20; ++m) t->win2[p][m] = make_float2(0.5f * window[2 * p + 20 * m], 0.5f * window[2 * p + 1 + 20 * m]);
+    for (int p = 0; p < 10; ++p)
+        for (int k1 = 1; k1 <= 10; ++k1) {
+            float w[4];
+            for (int h = 0; h < 2; ++h) {
+                const int j = 2 * p + h;
+                const double ang = -2.0 * M_PI * (double)((j * k1) % kNfft) / kNfft;   // same expression as build_tables (bit-identical twiddles)
+                w[h] = (float)(2.0 * std::cos(ang));
+                w[2 + h] = (float)(2.0 * std::sin(ang));
+            }
+            t->tw4[p][k1 - 1] = make_float4(w[0], w[1], w[2], w[3]);
+        }
+    // mel classes: first bin and zero-padded weights (bins 0 and 200 carry no weight: build_tables rejects such filterbanks)
+    std::memset(t->w0, 0, sizeof(t->w0)); std::memset(t->w1, 0, sizeof(t->w1));
+    std::memset(t->w2, 0, sizeof(t->w2)); std::memset(t->w3, 0, sizeof(t->w3));
+    for (int m = 0; m < kMaxMels; ++m) {
+        int first = -1;
+        for (int f = 1; f < 200 && first < 0; ++f) if (fb[f * kMaxMels + m] != 0.f) first = f;
+        if (first < 0) first = 1;                                       // empty filter -> log(eps)
+        t->mel_lo[m] = first;
+        const int c = m / 20, i = m % 20;
+        const int width = c == 0 ? kRefW0 : c == 1 ? kRefW1 : c == 2 ? kRefW2 : kRefW3;
+        for (int r = 0; r < width; ++r) {
+            const float wv = first + r < 200 ? fb[(first + r) * kMaxMels + m] : 0.f;
+            if (c == 0) t->w0[i][r] = wv; else if (c == 1) t->w1[i][r] = wv; else if (c == 2) t->w2[i][r] = wv; else t->w3[i][r] = wv;
+        }
+    }
+}
+
+// waveform as rows of 164 samples every 160 samples (box: 34 rows); features as [B][T][80] (box: 32 frames x 84 columns, the 4 columns past
+// the 80 mels are never written)
+bool fl_encode_maps(CUtensorMap* tm_in, CUtensorMap* tm_out, bool* out_ok, const float* wave, long long shift, long long buf_len,
+                    long long row_stride, long long batch, float* out, long long n_frames, long long out_row_stride, bool want_out) {
+    const encode_tiled_t enc = tensor_map_encoder();
+    if (!enc) return false;
+    // rows of 164 samples that start every 160 samples (they overlap by 4: the tile's padding columns carry the next row's
+    // first samples, which nothing reads).  A box wider than the tensor, with the padding out of bounds, faulted for boxes
+    // that cross a multiple of 256 rows on B200 (memcheck: illegal address in UTMALDG) — the overlapping form does not.
+    const long long rows = (buf_len - shift - kFlRowPitch) / kHop + 1;  // rows that end inside the buffer
+    if (buf_len - shift < kFlRowPitch || rows < kFlRows) return false;
+    {
+        const cuuint64_t dims[3] = {(cuuint64_t)kFlRowPitch, (cuuint64_t)rows, (cuuint64_t)batch};
+        const cuuint64_t strides[2] = {kHop * sizeof(float), (cuuint64_t)row_stride * sizeof(float)};
+        const cuuint32_t box[3] = {kFlRowPitch, kFlRows, 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        if (enc(tm_in, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(wave + shift), dims, strides, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return false;
+    }
+    *out_ok = false;
+    if (want_out) {
+        const cuuint64_t dims[3] = {(cuuint64_t)kMaxMels, (cuuint64_t)n_frames, (cuuint64_t)batch};
+        const cuuint64_t strides[2] = {kMaxMels * sizeof(float), (cuuint64_t)out_row_stride * sizeof(float)};
+        const cuuint32_t box[3] = {kFlYPitch, kFlFrames, 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        *out_ok = enc(tm_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    }
+    return true;
 }
 
 }  // namespace
@@ -789,7 +898,14 @@ int talfe_plan_create(talfe_plan** plan_out, int device, int n_mels, const float
         const char* kv = std::getenv("TALFE_KERNEL");
         p->variant = p->ref_layout ? 1 : 0;                               // the warp-specialised kernel is unrolled for the reference filterbank shape
         if (kv && std::strcmp(kv, "legacy") == 0) p->variant = 0;
+        p->fl = 0;
+        p->fl_tables = nullptr;
+        if (p->variant == 1 && n_mels == kMaxMels && kv && std::strcmp(kv, "fl") == 0) {
+            p->fl_tables = new (std::nothrow) FlTables();
+            if (p->fl_tables) { fl_build_tables(win.data(), fb.data(), p->fl_tables); p->fl = 1; }
+        }
         p->l2_prefetch = env_int("TALFE_L2_PREFETCH", 0);
+        p->use_tma = env_int("TALFE_TMA", 1);
     }
     // the legacy kernel stages only its own tables (the blob's prefix up to the ws section): 2 CTAs per SM need <= 113.5 KB each
     p->smem_bytes = t.off_ws + (size_t)kXFloats * sizeof(float) +
@@ -807,6 +923,7 @@ int talfe_plan_create(talfe_plan** plan_out, int device, int n_mels, const float
             if (e == cudaSuccess) e = cudaFuncSetAttribute(ws_kernel_for(dt, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->ws_smem);
         }
     }
+    if (p->fl && e == cudaSuccess) e = cudaFuncSetAttribute(logmel_fl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFlSmemBytes);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking);
     {
         int coop = 0;
@@ -834,6 +951,7 @@ void talfe_plan_destroy(talfe_plan* plan) {
     if (!plan) return;
     if (plan->blob_dev) cudaFree(plan->blob_dev);
     if (plan->bar_dev) cudaFree(plan->bar_dev);
+    delete plan->fl_tables;
     delete plan->bar_mutex;
     if (plan->copy_stream) cudaStreamDestroy(plan->copy_stream);
     for (int i = 0; i < 2; ++i) {
@@ -908,6 +1026,24 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
     a.out_align_ok = ((reinterpret_cast<uintptr_t>(job->out) & 15) == 0 && (ors & 3) == 0) ? 1 : 0;
     long long grid = use_ws ? (long long)plan->sm_count : (long long)plan->sm_count * plan->ctas_per_sm;
     if (grid > w.n_tiles) grid = w.n_tiles;
+    CUtensorMap tmap{}, tmap_out{};
+    bool use_fl = false;
+    if (use_ws && plan->fl && a.dtype == TALFE_F32 && a.align_ok && job->row_stride < (1ll << 36)) {
+        bool out_ok = false;
+        const bool want_out = job->out_layout == TALFE_LAYOUT_TM && a.out_align_ok && !a.out_offsets;
+        use_fl = fl_encode_maps(&tmap, &tmap_out, &out_ok, reinterpret_cast<const float*>(job->wave),
+                                (long long)kHop * job->frame0 - kHalf - job->origin, job->buf_len, job->row_stride, job->batch,
+                                job->out, job->n_frames, ors, want_out);
+        static const int no_tma = env_int("TALFE_FL_NOTMA", 0);          // development: 1 = no tensor loads, 2 = no tensor stores
+        if (use_fl) { a.use_tma = (no_tma & 1) ? 0 : 1; a.use_tma_out = (out_ok && !(no_tma & 2)) ? 1 : 0; }
+    }
+    if (use_fl) {
+        grid = std::min<long long>(plan->sm_count, (w.n_tiles + kFlWarps - 1) / kFlWarps);
+        static const int grid_cap = env_int("TALFE_FL_GRID", 0);        // development: fewer CTAs -> more tiles per warp
+        if (grid_cap > 0) grid = std::min<long long>(grid, grid_cap);
+    } else if (use_ws && plan->use_tma && a.dtype == TALFE_F32 && a.align_ok && job->row_stride < (1ll << 36))
+        a.use_tma = encode_wave_map(&tmap, reinterpret_cast<const float*>(job->wave), (long long)kHop * job->frame0 - kHalf - job->origin,
+                                    job->buf_len, job->row_stride, job->batch) ? 1 : 0;
     const bool want_stats = job->stats != nullptr || job->norm != TALFE_NORM_NONE;
     const bool per_row = job->norm >= TALFE_NORM_ROW_MEAN;
     a.partials_per_tile = per_row ? 1 : 0;                // batch-wide sums: one slot per CTA is enough
@@ -923,7 +1059,7 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
     // behind K1) measured 5 us faster than the in-kernel one (profiles/r02_ab_variants.json), so it keeps that job.
     // TALFE_FUSED_NORM: 0 never, 1 (default) up to kFuseMaxTilesPerCta tiles per CTA, 2 always.
     const bool fuse_pays = plan->fuse_norm >= 2 || w.n_tiles <= (long long)kFuseMaxTilesPerCta * plan->sm_count;
-    if (ref_norm && use_ws && plan->fuse_norm && fuse_pays && job->out_layout == TALFE_LAYOUT_TM && a.out_align_ok) {
+    if (ref_norm && use_ws && !use_fl && plan->fuse_norm && fuse_pays && job->out_layout == TALFE_LAYOUT_TM && a.out_align_ok) {
         talfe_plan* pl = const_cast<talfe_plan*>(plan);
         std::lock_guard<std::mutex> lock(*pl->bar_mutex);
         int slot = -1;
@@ -953,24 +1089,31 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
         attr[1].id = cudaLaunchAttributeCooperative;
         attr[1].val.cooperative = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        const auto fn = use_ws ? ws_kernel_for(a.dtype, a.fuse_norm != 0) : kernel_for(plan->ref_layout != 0, a.dtype);
-        if (a.fuse_norm) {
+        if (use_fl) {
+            cfg.blockDim = dim3(kFlThreads); cfg.dynamicSmemBytes = kFlSmemBytes;
+            TALFE_CUDA(cudaLaunchKernelEx(&cfg, logmel_fl_kernel, (const KernelArgs)a, (const CUtensorMap)tmap, (const CUtensorMap)tmap_out,
+                                          (const FlTables)*plan->fl_tables));
+        } else if (!use_ws) {
+            TALFE_CUDA(cudaLaunchKernelEx(&cfg, kernel_for(plan->ref_layout != 0, a.dtype), (const KernelArgs)a));
+        } else if (a.fuse_norm) {
+            const auto fn = ws_kernel_for(a.dtype, true);
             talfe_plan* pl = const_cast<talfe_plan*>(plan);
             cudaError_t e = cudaErrorUnknown;
             if (pl->coop_with_pdl != 0) {                              // first choice: keep the prologue overlap as well
                 cfg.attrs = attr; cfg.numAttrs = 2;
-                e = cudaLaunchKernelEx(&cfg, fn, (const KernelArgs)a);
+                e = cudaLaunchKernelEx(&cfg, fn, (const KernelArgs)a, (const CUtensorMap)tmap);
                 if (e != cudaSuccess && pl->coop_with_pdl < 0) { cudaGetLastError(); pl->coop_with_pdl = 0; }
                 else if (e == cudaSuccess) pl->coop_with_pdl = 1;
             }
             if (pl->coop_with_pdl == 0) {
                 cfg.attrs = attr + 1; cfg.numAttrs = 1;
-                e = cudaLaunchKernelEx(&cfg, fn, (const KernelArgs)a);
+                e = cudaLaunchKernelEx(&cfg, fn, (const KernelArgs)a, (const CUtensorMap)tmap);
             }
             TALFE_CUDA(e);
             return TALFE_OK;
+        } else {
+            TALFE_CUDA(cudaLaunchKernelEx(&cfg, ws_kernel_for(a.dtype, false), (const KernelArgs)a, (const CUtensorMap)tmap));
         }
-        TALFE_CUDA(cudaLaunchKernelEx(&cfg, fn, (const KernelArgs)a));
     }
 
     if (!want_stats) return TALFE_OK;

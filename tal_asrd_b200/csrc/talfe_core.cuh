@@ -121,6 +121,32 @@ TALFE_HD cf cfma_s(float s, cf t, cf a) { return make_float2(fmaf(s, t.x, a.x), 
 TALFE_HD cf cmul_s(float s, cf t) { return make_float2(s * t.x, s * t.y); }
 TALFE_HD cf cfms_s(float s, cf t, cf a) { return make_float2(fmaf(s, t.x, -a.x), fmaf(s, t.y, -a.y)); }
 #endif
+// the same three forms with a DIFFERENT multiplier in each half (frame-per-lane kernel: the halves are two adjacent
+// columns of one frame, whose window taps differ)
+#ifdef __CUDA_ARCH__
+TALFE_HD cf cmul_s(cf s, cf t) {
+    cf r;
+    asm("{ .reg .b64 rs, rt, rr; mov.b64 rs, {%2,%3}; mov.b64 rt, {%4,%5}; mul.rn.f32x2 rr, rs, rt; mov.b64 {%0,%1}, rr; }"
+        : "=f"(r.x), "=f"(r.y) : "f"(s.x), "f"(s.y), "f"(t.x), "f"(t.y));
+    return r;
+}
+TALFE_HD cf cfma_s(cf s, cf t, cf a) {
+    cf r;
+    asm("{ .reg .b64 rs, rt, ra, rr; mov.b64 rs, {%2,%3}; mov.b64 rt, {%4,%5}; mov.b64 ra, {%6,%7}; fma.rn.f32x2 rr, rs, rt, ra; mov.b64 {%0,%1}, rr; }"
+        : "=f"(r.x), "=f"(r.y) : "f"(s.x), "f"(s.y), "f"(t.x), "f"(t.y), "f"(a.x), "f"(a.y));
+    return r;
+}
+TALFE_HD cf cfms_s(cf s, cf t, cf a) {
+    cf r;
+    asm("{ .reg .b64 rs, rt, ra, rr; .reg .f32 n0, n1; neg.f32 n0, %6; neg.f32 n1, %7; mov.b64 rs, {%2,%3}; mov.b64 rt, {%4,%5}; mov.b64 ra, {n0,n1}; fma.rn.f32x2 rr, rs, rt, ra; mov.b64 {%0,%1}, rr; }"
+        : "=f"(r.x), "=f"(r.y) : "f"(s.x), "f"(s.y), "f"(t.x), "f"(t.y), "f"(a.x), "f"(a.y));
+    return r;
+}
+#else
+TALFE_HD cf cmul_s(cf s, cf t) { return make_float2(s.x * t.x, s.y * t.y); }
+TALFE_HD cf cfma_s(cf s, cf t, cf a) { return make_float2(fmaf(s.x, t.x, a.x), fmaf(s.y, t.y, a.y)); }
+TALFE_HD cf cfms_s(cf s, cf t, cf a) { return make_float2(fmaf(s.x, t.x, -a.x), fmaf(s.y, t.y, -a.y)); }
+#endif
 // explicit fused forms: the contraction the compiler would pick for a.x*b.x - a.y*b.y may differ from one kernel
 // to the next; fixing it keeps every variant of the kernel (and the host emulator) bit-identical
 TALFE_HD cf cmul(cf a, cf b) { return make_float2(fmaf(a.x, b.x, -(a.y * b.y)), fmaf(a.x, b.y, a.y * b.x)); }
@@ -278,7 +304,8 @@ TALFE_HD void fft20_dft5s(cf (&t)[4][5], cf (&v)[20]) {
 // twiddle step that follows absorbs the sign by multiplying with -i w instead of i w (no extra instruction).
 TALFE_HD constexpr bool rfft20_im_negated(int k) { return k == 1 || k == 2 || k == 5 || k == 6; }
 
-TALFE_HD void rfft20_pair_windowed(const cf (&x)[20], const float (&win)[20], cf (&re)[11], cf (&im)[11]) {
+template <typename WT /* float: one tap for both halves; cf: one per half */>
+TALFE_HD void rfft20_pair_windowed(const cf (&x)[20], const WT (&win)[20], cf (&re)[11], cf (&im)[11]) {
     cf t0[5], t2[5], p[5], e[5];                       // T0, T2 (real), T1 = (p, -e)
 #pragma unroll
     for (int n2 = 0; n2 < 5; ++n2) {

@@ -27,6 +27,18 @@ constexpr int kWsRoleThreads = kWsGroups * kGroup;          // 320
 constexpr int kWsRoleWarps = kWsRoleThreads / 32;           // 10
 constexpr int kWsThreads = 2 * kWsRoleThreads;              // 640: 10 producer warps, 10 consumer warps (5 per scheduler: 96 registers each)
 constexpr int kWsTileSamples = kHop * kWsFrames + (kNfft - kHop);   // 5360
+// fp32 tiles travel as ONE tensor copy (cp.async.bulk.tensor, SASS UTMALDG): the waveform is described to the copy engine
+// as rows of 340 samples that start every 320 samples (a 4-D tensor map [68][5][rows][batch] with strides 272 B, 1 280 B,
+// row pitch: the rows overlap by 20 samples), so a box of 17 rows lands in shared memory with exactly the 20-float skew
+// per 320 samples that the conflict-free stage-1 reads need — what used to take 17 cp.async.bulk pieces, each of which
+// costs its issuing warp ~275 cycles (profiles/r02_timeline.json).
+constexpr int kWsTmaInner = 68, kWsTmaMid = 5, kWsTmaRows = 17;
+constexpr int kWsTmaRowFloats = kWsTmaInner * kWsTmaMid;             // 340 = kXBlock + fp32 skew
+constexpr int kWsTmaSpan = kXBlock * (kWsTmaRows - 1) + kWsTmaRowFloats;   // 5 460 samples touched in global memory
+constexpr int kWsTmaBytes = kWsTmaRows * kWsTmaRowFloats * (int)sizeof(float);   // 23 120
+constexpr int kWsXBufBytes = (kWsTmaBytes + 127) & ~127;              // 23 168: every x buffer starts 128-byte aligned
+static_assert(kWsTmaRowFloats == XLayout<float>::kGroup && kXBlock * (kWsTmaRows - 1) + 240 == kWsTileSamples, "tensor box = skewed tile");
+static_assert(kWsXBufBytes >= kXFloats * (int)sizeof(float), "x buffer holds the skewed tile of every element type");
 static_assert(kWsTileSamples == kTileSamples && kWsRoleWarps == kWarps, "tile geometry is shared with the legacy kernel");
 
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
@@ -42,6 +54,14 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 template <int N> __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_4d(unsigned smem_dst, const void* tmap, int c0, int c1, int c2, int c3,
+                                            unsigned long long* bar, unsigned long long policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4, %5}], [%6], %7;" ::"r"(
+            smem_dst),
+        "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
 __device__ __forceinline__ void bulk_prefetch_l2(const void* gmem_src, unsigned bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
 }
@@ -76,7 +96,7 @@ __device__ __forceinline__ void mbar_wait_sleep(unsigned long long* bar, unsigne
 struct __align__(16) WsDesc {
     int t0, t_end, L, row;
     int flags;                     // bit 0 active, bit 1 full, bit 2 x tile fetched by the copy engine, bit 3 bulk store allowed
-    int pad;
+    int pad;                       // tensor copy: first 320-sample row of the tile (16 * tile index in the row)
     float* out_tile;               // &out[row][t0 - frame0][0] for [.., T, 80] outputs
     const void* src;               // first sample of the tile in global memory (bulk tiles)
     long long pad2;
@@ -99,11 +119,12 @@ __device__ __forceinline__ WsDesc ws_describe(const KernelArgs& a, int row, int 
     const bool full = d.t0 + kWsFrames <= d.t_end;
     const int s0 = kHop * d.t0 - kHalf;
     const int b0 = s0 - a.origin;
-    const bool interior = s0 >= 0 && s0 + kWsTileSamples <= d.L && b0 >= 0 && b0 + kWsTileSamples <= a.buf_len;
+    // (the tensor copy reads whole 340-sample rows: up to 100 samples past the tile, which must still be inside the buffer)
+    const bool interior = s0 >= 0 && s0 + kWsTileSamples <= d.L && b0 >= 0 && b0 + (a.use_tma ? kWsTmaSpan : kWsTileSamples) <= a.buf_len;
     const bool bulk_x = active && interior && a.align_ok;
     const bool bulk_y = active && full && a.out_layout == TALFE_LAYOUT_TM && a.out_align_ok;
     d.flags = (active ? kWsActive : 0) | (full ? kWsFull : 0) | (bulk_x ? kWsBulkX : 0) | (bulk_y ? kWsBulkY : 0);
-    d.pad = 0;
+    d.pad = tq * (kWsTmaRows - 1);
     d.out_tile = a.out + (a.out_offsets ? a.out_offsets[row] * kMaxMels : (long long)row * a.out_row_stride) +
                  (long long)(d.t0 - a.frame0) * kMaxMels;
     src_off = (long long)row * a.row_stride + b0;
@@ -122,7 +143,7 @@ __device__ __forceinline__ void ws_advance(const KernelArgs& a, int& row, int& t
 // the consumers — two pairs per thread, x[q] / E[q] per group — measured 91.7 us against 80.2 us: each group then holds
 // its exchange buffer for two pairs' worth of work and the consumers wait for it.)
 template <typename XT>
-__device__ __forceinline__ void ws_producer(const KernelArgs& a, unsigned char* smem, XT* s_x0, cf* s_e0, WsDesc* s_desc,
+__device__ __forceinline__ void ws_producer(const KernelArgs& a, const void* tmap, unsigned char* smem, XT* s_x0, cf* s_e0, WsDesc* s_desc,
                                             unsigned long long* s_bar, const int tid, const int n_my) {
     unsigned long long* x_full = s_bar;            // [2]
     unsigned long long* x_empty = s_bar + 2;       // [2]
@@ -131,7 +152,7 @@ __device__ __forceinline__ void ws_producer(const KernelArgs& a, unsigned char* 
     const int warp = tid >> 5, lane = tid & 31;
     const int g1 = tid / kGroup, j = tid - g1 * kGroup;
     constexpr int kXG = XLayout<XT>::kGroup;
-    constexpr int kXBufBytes = kXFloats * (int)sizeof(float);           // both element sizes use the fp32-sized buffer
+    constexpr int kXBufBytes = kWsXBufBytes;                            // every element size uses the fp32-sized buffer
 
     float win[20];
     load_window(j, a.win_global, XLayout<XT>::kScale, win);            // once per CTA, straight from global memory
@@ -160,10 +181,16 @@ __device__ __forceinline__ void ws_producer(const KernelArgs& a, unsigned char* 
         const WsDesc* dp = s_desc + (kk & (kWsDescRing - 1));
         const int flags = dp->flags;
 #if defined(TALFE_ABLATE) && (TALFE_ABLATE & 16)
-        if (false) {                                                     // timing experiment only: no waveform fetch
+        const int fetch = 0;                                             // timing experiment only: no waveform fetch
 #else
-        if (flags & kWsBulkX) {
+        const int fetch = flags & kWsBulkX;
 #endif
+        if (fetch && sizeof(XT) == 4 && a.use_tma) {
+            if (lane == 0) {
+                mbar_expect_tx(x_full + lbuf, kWsTmaBytes);                                // release: publishes the descriptor too
+                tma_load_4d(smem_u32(s_x0) + lbuf * kXBufBytes, tmap, 0, 0, dp->pad, dp->row, x_full + lbuf, l2_evict_first_policy());
+            }
+        } else if (fetch) {
             const XT* src = reinterpret_cast<const XT*>(dp->src);
             if (lane == 0) mbar_expect_tx(x_full + lbuf, kWsTileSamples * (int)sizeof(XT));   // release: publishes the descriptor too
             __syncwarp();
@@ -563,12 +590,15 @@ __device__ __noinline__ void ws_fused_batch_mean(const WsNormArgs a, unsigned ch
     }
 }
 
+__host__ __device__ constexpr size_t ws_x_offset(size_t table_bytes) { return (table_bytes + 127) & ~(size_t)127; }
+
 template <typename XT, bool kFuse>
-__global__ void __launch_bounds__(kWsThreads, 1) logmel_ws_kernel(const KernelArgs a) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    // carve-up: tables (twiddles | mel weights | first bins) | x[2] | E[2] | P[2] | Y[2] | descriptor ring | 8 mbarriers
-    XT* s_x0 = reinterpret_cast<XT*>(smem + a.blob_bytes);
-    cf* s_e0 = reinterpret_cast<cf*>(smem + a.blob_bytes + 2 * kXFloats * sizeof(float));
+__global__ void __launch_bounds__(kWsThreads, 1) logmel_ws_kernel(const KernelArgs a, const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(16) unsigned char smem[];              // (the dynamic window itself starts 1 KB aligned: no static shared memory)
+    // carve-up: tables (twiddles | mel weights | first bins) | x[2] (128-byte aligned) | E[2] | P[2] | Y[2] | descriptor ring | 8 mbarriers
+    const unsigned x_off = (unsigned)ws_x_offset((size_t)a.blob_bytes);
+    XT* s_x0 = reinterpret_cast<XT*>(smem + x_off);
+    cf* s_e0 = reinterpret_cast<cf*>(smem + x_off + 2 * kWsXBufBytes);
     cf* s_p0 = s_e0 + 2 * kWsECf;
     float* s_y0 = reinterpret_cast<float*>(s_p0 + 2 * kWsPCf);
     WsDesc* s_desc = reinterpret_cast<WsDesc*>(s_y0 + 2 * kWsYFloats);
@@ -590,16 +620,16 @@ __global__ void __launch_bounds__(kWsThreads, 1) logmel_ws_kernel(const KernelAr
     __syncthreads();
     cudaGridDependencySynchronize();
     const int n_my = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles blockIdx.x, + gridDim.x, ...
-    if (tid < kWsRoleThreads) ws_producer<XT>(a, smem, s_x0, s_e0, s_desc, s_bar, tid, n_my);
+    if (tid < kWsRoleThreads) ws_producer<XT>(a, &tmap, smem, s_x0, s_e0, s_desc, s_bar, tid, n_my);
     else ws_consumer<XT>(a, smem, s_e0, s_p0, s_y0, s_desc, s_bar, tid - kWsRoleThreads, n_my);
     if (kFuse) {                                                       // the exchange buffers are free now: scratch for the reduction
         const WsNormArgs na{a.partials, a.grid_bar, a.norm_count, a.stats_out, a.out, a.out_row_stride, a.tiles_per_row, a.n_frames, a.n_tiles};
-        ws_fused_batch_mean(na, smem + a.blob_bytes + 2 * kXFloats * sizeof(float));
+        ws_fused_batch_mean(na, smem + x_off + 2 * kWsXBufBytes);
     }
 }
 
 constexpr size_t ws_smem_bytes(size_t table_bytes) {
-    return table_bytes + 2 * (size_t)kXFloats * sizeof(float) + 2 * (size_t)kWsECf * sizeof(cf) + 2 * (size_t)kWsPCf * sizeof(cf) +
+    return ws_x_offset(table_bytes) + 2 * (size_t)kWsXBufBytes + 2 * (size_t)kWsECf * sizeof(cf) + 2 * (size_t)kWsPCf * sizeof(cf) +
            2 * (size_t)kWsYFloats * sizeof(float) + kWsDescRing * sizeof(WsDesc) + 8 * sizeof(unsigned long long);
 }
 static_assert(kMaxMels * kWsFrames % kWsRoleThreads == 0 && kWsYFloats >= kWsFrames * kMaxMels + 4 * kWsGroups, "Y staging");

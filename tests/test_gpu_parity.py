@@ -27,7 +27,8 @@ def dev():
 
 
 def make_module(dev, kernel):
-    """kernel: 'ws' (warp-specialised, the default for the reference filterbank) or 'legacy'; the library reads
+    """kernel: 'ws' (warp-specialised, the default for the reference filterbank), 'legacy', or 'fl' (frame per lane,
+    tensor memory as transpose scratch: fp32 waveforms; everything else falls through to 'ws'); the library reads
     TALFE_KERNEL when the plan (device tables) is created, so create it here."""
     from tal_asrd_b200 import LogMelSpec
     old = os.environ.get("TALFE_KERNEL")
@@ -43,7 +44,7 @@ def make_module(dev, kernel):
     return m
 
 
-@pytest.fixture(scope="module", params=["ws", "legacy"])
+@pytest.fixture(scope="module", params=["ws", "legacy", "fl"])
 def mod(dev, request):
     return make_module(dev, request.param)
 
