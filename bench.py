@@ -421,7 +421,9 @@ def run_ours(args):
 
     corpus = None if args.no_extras else corpus_block(mod, lib, _lib, dev, world, rank, barrier, max_over_ranks)
     other = None
+    experiments = None
     if rank == 0 and world == 1 and not args.no_extras:
+        experiments = kernel_experiments(waves, outs, dev, kernel_ms)
         del waves, outs
         torch.cuda.empty_cache()
         other = other_configs(mod, lib, _lib, dev)
@@ -446,7 +448,7 @@ def run_ours(args):
                              "parallelism": f"episode-sharded x{world}, no data-path collective in the step "
                                             f"(the statistics all-reduce of configs[4] is timed in `corpus`)"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "corpus": corpus, "other_configs": other,
-            "nccl_check": nccl_check,
+            "kernel_experiments": experiments, "nccl_check": nccl_check,
             "gpu_launches": launches_per_step * args.steps, "clocks": clocks.summary(),
         }
         emit(line)
@@ -508,6 +510,49 @@ def corpus_block(mod, lib, _lib, dev, world, rank, barrier, max_over_ranks):
             "pass1_frames_per_s": frames / (t1 * 1e-3),
             "global_mean": total.mean, "global_count": total.count, "repetitions": REPS,
             "pool": f"{POOL} distinct resident episodes per rank visited in turn (inputs 0.9 GB >> L2)"}
+
+
+def kernel_experiments(waves, outs, dev, default_kernel_ms):
+    """The other formulations of K1 that live in the library, timed on the headline batch in the same run (N = 1):
+    `fl` = one thread per frame, tensor memory (tcgen05.st / tcgen05.ld) as the transpose scratch between the FFT stages,
+    uniform tables, no inter-warp synchronisation; `legacy` = the homogeneous round-1 kernel.  They are measured
+    alternatives, not the shipped path."""
+    import torch
+    from tal_asrd_b200 import LogMelSpec, frontend
+    res = {"default_kernel_ms": default_kernel_ms}
+    want = None
+    for kern in ("ws", "fl", "legacy"):
+        old = os.environ.get("TALFE_KERNEL")
+        os.environ["TALFE_KERNEL"] = kern
+        saved = dict(frontend._PLANS)
+        frontend._PLANS.clear()                                             # plans are cached per table set: a fresh one per kernel
+        try:
+            m = LogMelSpec().to(dev)
+            m.plan(dev)
+            for i in range(3):
+                m.features(waves[i % len(waves)], norm="none", out=outs[i % 2])
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(10):
+                m.features(waves[i % len(waves)], norm="none", out=outs[i % 2])
+            e1.record()
+            torch.cuda.synchronize()
+            y = m.features(waves[0], norm="none").clone()
+            if want is None:
+                want = y
+            res[kern] = {"kernel_ms": e0.elapsed_time(e1) / 10, "max_abs_diff_vs_ws": float((y - want).abs().max())}
+            del m, y
+        except Exception as exc:                                            # informational block
+            res[kern] = {"error": repr(exc)[:200]}
+        finally:
+            frontend._PLANS.clear()
+            frontend._PLANS.update(saved)
+            if old is None:
+                os.environ.pop("TALFE_KERNEL", None)
+            else:
+                os.environ["TALFE_KERNEL"] = old
+    return res
 
 
 def other_configs(mod, lib, _lib, dev):
