@@ -1038,7 +1038,7 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
         if (use_fl) { a.use_tma = (no_tma & 1) ? 0 : 1; a.use_tma_out = (out_ok && !(no_tma & 2)) ? 1 : 0; }
     }
     if (use_fl) {
-        grid = std::min<long long>(plan->sm_count, (w.n_tiles + kFlWarps - 1) / kFlWarps);
+        grid = std::min<long long>(plan->sm_count, (w.n_tiles + kFlQuads - 1) / kFlQuads);
         static const int grid_cap = env_int("TALFE_FL_GRID", 0);        // development: fewer CTAs -> more tiles per warp
         if (grid_cap > 0) grid = std::min<long long>(grid, grid_cap);
     } else if (use_ws && plan->use_tma && a.dtype == TALFE_F32 && a.align_ok && job->row_stride < (1ll << 36))
