@@ -575,16 +575,44 @@ __global__ void __launch_bounds__(256) apply_stats_kernel(float* __restrict__ fe
     if (out_layout == TALFE_LAYOUT_TM && (n_mels & 3) == 0 && ((reinterpret_cast<unsigned long long>(base) & 15ull) == 0)) {
         float4* b4 = reinterpret_cast<float4*>(base);
         const int m4 = n_mels >> 2;
-        for (long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x; i < total / 4; i += (long long)gridDim.y * blockDim.x) {
-            const int f = (int)(i / m4);
-            const int m = (int)(i - (long long)f * m4) * 4;
-            float4 v = b4[i];
-            v.x = (v.x - s_mean[m]) * s_rstd[m];
-            v.y = (v.y - s_mean[m + 1]) * s_rstd[m + 1];
-            v.z = (v.z - s_mean[m + 2]) * s_rstd[m + 2];
-            v.w = (v.w - s_mean[m + 3]) * s_rstd[m + 3];
-            if (n_bands && time_masked(f)) v = make_float4(0.f, 0.f, 0.f, 0.f);
-            b4[i] = v;
+        const long long n4 = total / 4, step = (long long)gridDim.y * blockDim.x;
+        long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x;
+        if (!n_bands) {
+            // HBM-sized sweeps (hour-long episodes, corpus passes): four independent 128-bit loads in flight per thread, and
+            // the mel index carried along instead of a 64-bit division per element
+            const int dm = (int)(step % m4);
+            int mq = (int)(i % m4);
+            auto fix = [&](float4 v, int q) {
+                const int m = 4 * q;
+                v.x = (v.x - s_mean[m]) * s_rstd[m];
+                v.y = (v.y - s_mean[m + 1]) * s_rstd[m + 1];
+                v.z = (v.z - s_mean[m + 2]) * s_rstd[m + 2];
+                v.w = (v.w - s_mean[m + 3]) * s_rstd[m + 3];
+                return v;
+            };
+            auto next = [&](int q) { q += dm; return q >= m4 ? q - m4 : q; };
+            for (; i + 3 * step < n4; i += 4 * step) {
+                const int q0 = mq, q1 = next(q0), q2 = next(q1), q3 = next(q2);
+                mq = next(q3);
+                const float4 a = b4[i], b = b4[i + step], c = b4[i + 2 * step], d = b4[i + 3 * step];
+                b4[i] = fix(a, q0); b4[i + step] = fix(b, q1); b4[i + 2 * step] = fix(c, q2); b4[i + 3 * step] = fix(d, q3);
+            }
+            for (; i < n4; i += step) {
+                b4[i] = fix(b4[i], mq);
+                mq = next(mq);
+            }
+        } else {
+            for (; i < n4; i += step) {
+                const int f = (int)(i / m4);
+                const int m = (int)(i - (long long)f * m4) * 4;
+                float4 v = b4[i];
+                v.x = (v.x - s_mean[m]) * s_rstd[m];
+                v.y = (v.y - s_mean[m + 1]) * s_rstd[m + 1];
+                v.z = (v.z - s_mean[m + 2]) * s_rstd[m + 2];
+                v.w = (v.w - s_mean[m + 3]) * s_rstd[m + 3];
+                if (time_masked(f)) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                b4[i] = v;
+            }
         }
     } else if (out_layout == TALFE_LAYOUT_TM) {
         for (long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.y * blockDim.x) {
