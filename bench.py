@@ -505,7 +505,8 @@ def corpus_block(mod, lib, _lib, dev, world, rank, barrier, max_over_ranks):
         torch.cuda.empty_cache()
         need = len(mine) * T * N_MELS * 4
         free, _ = torch.cuda.mem_get_info(dev)
-        if need * 1.15 < free:
+        cannot = max_over_ranks([0.0 if need * 1.15 < free else 1.0])[0]   # every rank takes the same branch (barriers inside)
+        if cannot == 0.0:
             feats = torch.empty(len(mine), T, N_MELS, dtype=torch.float32, device=dev)
             feats.zero_()                                                   # pages mapped before the clock starts
             blocks.zero_()

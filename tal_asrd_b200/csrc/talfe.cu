@@ -1151,7 +1151,8 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
         // the reference case: one scalar over a contiguous [B, T, M] (or [B, M, T]) tensor; the sweep
         // derives the mean from the per-CTA partials itself (no separate reduction launch)
         const long long total = dense * job->batch, n4 = total / 4;
-        const unsigned blocks = (unsigned)std::max<long long>(1, std::min<long long>((n4 + 1023) / 1024, (long long)plan->sm_count * 8));
+        static const int sweep_per_sm = env_int("TALFE_SWEEP_BLOCKS", 8);     // development knob (A/B: profiles/r02_ab_sweep.json)
+        const unsigned blocks = (unsigned)std::max<long long>(1, std::min<long long>((n4 + 1023) / 1024, (long long)plan->sm_count * sweep_per_sm));
         // programmatic dependent launch: the sweep's blocks are scheduled while K1 drains and wait at
         // cudaGridDependencySynchronize() for its memory to be visible, which hides the launch gap
         cudaLaunchConfig_t cfg{};
