@@ -622,7 +622,7 @@ def other_configs(mod, lib, _lib, dev):
     out1 = torch.empty(1, 6001, N_MELS, device=dev)
     ms = timeit(lambda: mod.features(clip, out=out1), 200, warm=10)
     c0 = {"frames": 6001, "us_per_call": ms * 1e3, "frames_per_s": 6001 / (ms * 1e-3),
-          "api": "LogMelSpec.features(out=) back to back from Python (host-bound: one launch per call)"}
+          "api": "LogMelSpec.features(out=) back to back from Python (host-bound: two launches per call)"}
     try:
         g = torch.cuda.CUDAGraph()
         side = torch.cuda.Stream(dev)
@@ -653,6 +653,11 @@ def other_configs(mod, lib, _lib, dev):
     c2["streamed_from_pinned_host_ms"] = timeit(lambda: stream_episode(mod, eph, device=dev), 3)
     pcm = (eph * 32768.0).round().to(torch.int16).pin_memory()
     c2["streamed_from_pinned_host_int16_ms"] = timeit(lambda: stream_episode(mod, pcm, device=dev), 3)
+    # "per-utterance CMVN" (BASELINE configs[2] wording; the reference itself only removes a scalar mean): per-mel mean and
+    # variance over the hour, one extra statistics pass + one in-place sweep behind the transform
+    c2["one_shot_cmvn_ms"] = timeit(lambda: mod.features(ep[None], norm="row_mel_var"), 5)
+    c2["streamed_device_resident_cmvn_ms"] = timeit(lambda: stream_episode(mod, ep, norm="row_mel_var"), 3)
+    c2["streamed_from_pinned_host_int16_cmvn_ms"] = timeit(lambda: stream_episode(mod, pcm, device=dev, norm="row_mel_var"), 3)
     c2["default_chunk_seconds"] = DEFAULT_CHUNK_SECONDS
     c2["one_shot_frames_per_s"] = T / (c2["one_shot_ms"] * 1e-3)
     c2["streamed_from_pinned_host_int16_frames_per_s"] = T / (c2["streamed_from_pinned_host_int16_ms"] * 1e-3)

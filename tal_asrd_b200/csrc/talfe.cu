@@ -84,7 +84,7 @@ struct talfe_plan_impl {
     std::mutex* bar_mutex;
 };
 constexpr int kBarSlots = 16;
-constexpr int kFuseMaxTilesPerCta = 8;
+constexpr int kFuseMaxTilesPerCta = 1;          // TALFE_FUSED_NORM=1: fuse calls of at most one tile per CTA
 
 struct KernelArgs {
     const void* wave;
@@ -956,7 +956,7 @@ int talfe_plan_create(talfe_plan** plan_out, int device, int n_mels, const float
     {
         int coop = 0;
         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
-        p->fuse_norm = (coop && p->variant == 1) ? env_int("TALFE_FUSED_NORM", 1) : 0;
+        p->fuse_norm = (coop && p->variant == 1) ? env_int("TALFE_FUSED_NORM", 0) : 0;
         p->coop_with_pdl = -1;
         p->bar_used = 0;
         p->bar_mutex = new (std::nothrow) std::mutex();
@@ -1076,16 +1076,17 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
     const bool per_row = job->norm >= TALFE_NORM_ROW_MEAN;
     a.partials_per_tile = per_row ? 1 : 0;                // batch-wide sums: one slot per CTA is enough
     a.want_sumsq = job->stats != nullptr ? 1 : 0;         // the sum of squares is only ever reported, never needed by K3
-    // The reference case — one scalar over a contiguous [B, T, M] tensor — is normalised inside the ws kernel itself
-    // (cooperative launch, grid barrier, every CTA sweeps its own tiles): ONE launch per LogMelSpec.forward.
+    // The reference case — one scalar over a contiguous [B, T, M] tensor — CAN be normalised inside the ws kernel itself
+    // (cooperative launch, grid barrier, flat sweep split evenly over the CTAs): one launch per LogMelSpec.forward.
     const bool ref_norm = job->norm == TALFE_NORM_BATCH_MEAN && !a.lens && !(job->accumulate_stats && job->stats) &&
                           !job->defer_normalise && ors == dense && job->n_bands == 0 &&
                           (reinterpret_cast<uintptr_t>(job->out) & 15) == 0;
     unsigned* bar = nullptr;
-    // ... when that pays: for a handful of tiles per CTA the second launch (its host cost and ~3 us of device latency) is
-    // a large part of the call; for big batches the separate flat sweep (8 blocks per SM, launched programmatically
-    // behind K1) measured 5 us faster than the in-kernel one (profiles/r02_ab_variants.json), so it keeps that job.
-    // TALFE_FUSED_NORM: 0 never, 1 (default) up to kFuseMaxTilesPerCta tiles per CTA, 2 always.
+    // Opt-in since round 2's measurement across call sizes (tools/latency_fused_ab.py, profiles/r02_latency_fused_ab.json):
+    // on the device the cooperative launch + grid barrier cost ~2 us more than the second, programmatically launched
+    // kernel at EVERY size (1 x 1 s: 12.5 vs 10.4 us, 1 x 60 s: 14.4 vs 12.5, 64 x 30 s: 89.0 vs 87.2), and back to back
+    // from Python the two-launch path is ahead as well once the host is warm (13.4 vs 14.5 us per call).
+    // TALFE_FUSED_NORM: 0 (default) never, 1 calls of at most kFuseMaxTilesPerCta tiles per CTA, 2 always.
     const bool fuse_pays = plan->fuse_norm >= 2 || w.n_tiles <= (long long)kFuseMaxTilesPerCta * plan->sm_count;
     if (ref_norm && use_ws && !use_fl && plan->fuse_norm && fuse_pays && job->out_layout == TALFE_LAYOUT_TM && a.out_align_ok) {
         talfe_plan* pl = const_cast<talfe_plan*>(plan);

@@ -523,12 +523,11 @@ __device__ __forceinline__ void ws_grid_barrier(unsigned* bar, unsigned n_ctas) 
 // so the fused and the two-kernel paths produce bit-identical features.
 struct WsNormArgs {            // passed by value (registers): a reference to the kernel parameters would force a stack copy
     const double2* partials; unsigned* grid_bar; double norm_count; double* stats_out;
-    float* out; long long out_row_stride; int tiles_per_row, n_frames, n_tiles;
+    float* out; long long out_row_stride; int n_rows;
 };
 __device__ __noinline__ void ws_fused_batch_mean(const WsNormArgs a, unsigned char* smem_scratch) {
-    // thread and tile counts are re-derived here: nothing of this epilogue stays live in registers across the tile loops
+    // nothing of this epilogue stays live in registers across the tile loops
     const int tid = (int)threadIdx.x;
-    const int n_my = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     double* s_a = reinterpret_cast<double*>(smem_scratch);             // [256] sums, [256] sums of squares, then the mean
     double* s_b = s_a + 256;
     // every bulk store of this CTA has completed (its issuing lane waited for the whole group); make the copy engine's
@@ -556,38 +555,30 @@ __device__ __noinline__ void ws_fused_batch_mean(const WsNormArgs a, unsigned ch
     }
     const float mean = a.norm_count > 0.0 ? (float)(s_a[0] / a.norm_count) : 0.f;
     if (a.stats_out && blockIdx.x == 0 && tid == 0) { a.stats_out[0] = a.norm_count; a.stats_out[1] = s_a[0]; a.stats_out[2] = s_b[0]; }
-    // own tiles, in the order they were written (a 61 MB result sits in the 126 MB L2 entirely): one float4 per thread
-    // and tile (32 frames x 80 mels = 640 float4), kNormUnroll tiles in flight per thread — the sweep is bound by L2
-    // latency x bandwidth, so the loads of many tiles are issued before the first subtraction
-    constexpr int kNormUnroll = 14;
-    const int step = (int)gridDim.x;
-    const int tq0 = (int)blockIdx.x % a.tiles_per_row, row0 = (int)blockIdx.x / a.tiles_per_row;
-    const int dq = step % a.tiles_per_row, dr = step / a.tiles_per_row;      // tile k+1 from tile k without a division
-    int tq = tq0, row = row0;
-    for (int k0 = 0; k0 < n_my; k0 += kNormUnroll) {
+    // flat sweep of the whole (contiguous) tensor, the same slice of it for every CTA whatever tiles it computed: a call of
+    // this size sits in L2 entirely, and an even split finishes sooner than "own tiles" when some CTAs had one tile more
+    // than others (1 x 60 s: 188 tiles on 148 CTAs).  kNormUnroll independent 128-bit loads in flight per thread.
+    constexpr int kNormUnroll = 8;
+    const long long total = (long long)a.n_rows * a.out_row_stride;
+    const long long n4 = total >> 2, step = (long long)gridDim.x * kWsThreads;
+    float4* p4 = reinterpret_cast<float4*>(a.out);
+    long long i = (long long)blockIdx.x * kWsThreads + tid;
+    for (; i + (kNormUnroll - 1) * step < n4; i += kNormUnroll * step) {
         float4 v[kNormUnroll];
-        float4* ptr[kNormUnroll];
+#pragma unroll
+        for (int u = 0; u < kNormUnroll; ++u) v[u] = __ldcg(p4 + i + u * step);
 #pragma unroll
         for (int u = 0; u < kNormUnroll; ++u) {
-            ptr[u] = nullptr;
-            if (k0 + u < n_my) {
-                const int nfr = min(kWsFrames, a.n_frames - tq * kWsFrames);
-                if (tid < nfr * (kMaxMels / 4)) {
-                    ptr[u] = reinterpret_cast<float4*>(a.out + (long long)row * a.out_row_stride + (long long)tq * (kWsFrames * kMaxMels)) + tid;
-                    v[u] = __ldcg(ptr[u]);
-                }
-                tq += dq; row += dr;
-                if (tq >= a.tiles_per_row) { tq -= a.tiles_per_row; ++row; }
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < kNormUnroll; ++u) {
-            if (ptr[u]) {
-                v[u].x -= mean; v[u].y -= mean; v[u].z -= mean; v[u].w -= mean;
-                __stcs(ptr[u], v[u]);
-            }
+            v[u].x -= mean; v[u].y -= mean; v[u].z -= mean; v[u].w -= mean;
+            __stcs(p4 + i + u * step, v[u]);
         }
     }
+    for (; i < n4; i += step) {
+        float4 v = __ldcg(p4 + i);
+        v.x -= mean; v.y -= mean; v.z -= mean; v.w -= mean;
+        __stcs(p4 + i, v);
+    }
+    if (blockIdx.x == 0 && tid < (int)(total & 3)) a.out[4 * n4 + tid] -= mean;
 }
 
 __host__ __device__ constexpr size_t ws_x_offset(size_t table_bytes) { return (table_bytes + 127) & ~(size_t)127; }
@@ -623,7 +614,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) logmel_ws_kernel(const KernelAr
     if (tid < kWsRoleThreads) ws_producer<XT>(a, &tmap, smem, s_x0, s_e0, s_desc, s_bar, tid, n_my);
     else ws_consumer<XT>(a, smem, s_e0, s_p0, s_y0, s_desc, s_bar, tid - kWsRoleThreads, n_my);
     if (kFuse) {                                                       // the exchange buffers are free now: scratch for the reduction
-        const WsNormArgs na{a.partials, a.grid_bar, a.norm_count, a.stats_out, a.out, a.out_row_stride, a.tiles_per_row, a.n_frames, a.n_tiles};
+        const WsNormArgs na{a.partials, a.grid_bar, a.norm_count, a.stats_out, a.out, a.out_row_stride, a.batch};
         ws_fused_batch_mean(na, smem + x_off + 2 * kWsXBufBytes);
     }
 }
