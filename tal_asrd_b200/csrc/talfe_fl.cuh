@@ -295,24 +295,24 @@ __device__ __forceinline__ void fl_rows(const unsigned tm, float (&ra)[40], floa
 // (0, 10, 9, 8) and rows 2, 1.  `pair_sync` separates half 1's loads of those four rows from everybody's first power store.
 template <typename Sync>
 __device__ __forceinline__ void fl_stage2(const unsigned tm, const int half, Sync pair_sync) {
-    float ra[40], rb[40];
+    float ra[40], rb[40], z[20], r10[40];
     if (half == 0) {
         fl_load_row(tm + fl_row_col(7), ra);
         fl_load_row(tm + fl_row_col(6), rb);
-        tmem_wait_ld();
-        tmem_pin(ra); tmem_pin(rb);
-        pair_sync();
-        fl_rows(tm, ra, rb, 7, 3);
     } else {
-        float z[20], r10[40];
         tmem_ld16(tm + kFlColRow0, z);
         tmem_ld4(tm + kFlColRow0 + 16, z + 16);
         fl_load_row(tm + fl_row_col(10), r10);
         fl_load_row(tm + fl_row_col(9), ra);
         fl_load_row(tm + fl_row_col(8), rb);
-        tmem_wait_ld();
-        tmem_pin(z); tmem_pin(r10); tmem_pin(ra); tmem_pin(rb);
-        pair_sync();
+    }
+    tmem_wait_ld();
+    tmem_pin(ra); tmem_pin(rb);
+    pair_sync();                                                        // (one call site for both halves: B2)
+    if (half == 0) {
+        fl_rows(tm, ra, rb, 7, 3);
+    } else {
+        tmem_pin(z); tmem_pin(r10);
         {   // row 0 (real): bins 20 q, q = 1..9 (bins 0 and 200 carry no mel weight)
             cf v[20];
 #pragma unroll

@@ -121,7 +121,7 @@ def _shared_plan(device: torch.device, n_mels: int, window: torch.Tensor, fb: to
     win = window.detach().to("cpu", torch.float32).contiguous()
     fbc = fb.detach().to("cpu", torch.float32).contiguous()
     # the library reads its development switches when a plan is created: they are part of what a plan is
-    knobs = tuple(os.environ.get(k) for k in ("TALFE_KERNEL", "TALFE_L2_PREFETCH", "TALFE_FUSED_NORM", "TALFE_LIB"))
+    knobs = tuple(os.environ.get(k) for k in ("TALFE_KERNEL", "TALFE_L2_PREFETCH", "TALFE_FUSED_NORM", "TALFE_TMA", "TALFE_LIB"))
     key = (device.index, n_mels, hashlib.sha1(win.numpy().tobytes()).digest(), hashlib.sha1(fbc.numpy().tobytes()).digest(), knobs)
     plan = _PLANS.get(key)
     if plan is None:

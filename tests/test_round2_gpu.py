@@ -51,6 +51,30 @@ def _fill(dev, rows, n, episode=0, dtype=torch.float32):
     return x
 
 
+# ------------------------------------------------------------------------------------------ tensor-copy waveform tiles
+def test_tensor_copy_tiles_are_bitwise_the_bulk_copy_path(dev):
+    """fp32 interior tiles arrive by ONE cp.async.bulk.tensor (overlapping-row tensor map) instead of 17 bulk pieces:
+    same bytes in shared memory, hence identical features — batch, one long row (tiles cross multiples of 256 tensor
+    rows), a chunk in the middle of an episode (frame0 / origin) and a strided batch."""
+    tma, bulk = _module(dev, TALFE_TMA=1), _module(dev, TALFE_TMA=0)
+    x = _fill(dev, 5, 16000 * 21 + 77, episode=3)
+    assert torch.equal(tma.features(x, norm="none"), bulk.features(x, norm="none"))
+    assert torch.equal(tma(x), bulk(x))
+    long_row = _fill(dev, 1, 16000 * 400, episode=4)
+    assert torch.equal(tma.features(long_row, norm="none"), bulk.features(long_row, norm="none"))
+    wide = _fill(dev, 3, 16000 * 9 + 4, episode=5)
+    view = wide[:, : 16000 * 9]                                           # row pitch larger than the row
+    assert torch.equal(tma.features(view, norm="none"), bulk.features(view, norm="none"))
+    from tal_asrd_b200.streaming import stream_episode
+    ep = _fill(dev, 1, 16000 * 95, episode=6)[0]
+    a = stream_episode(tma, ep, chunk_seconds=13.0)
+    b = stream_episode(bulk, ep, chunk_seconds=13.0)
+    assert torch.equal(a, b)
+    y64 = O.logmel_unnormalised_f64(ep[None].cpu().numpy())
+    y64 = y64 - y64.mean()
+    assert rel_err(a.cpu().numpy(), y64) < TOL
+
+
 # ------------------------------------------------------------------------------------------ fused normalisation
 @pytest.mark.parametrize("shape", [(1, 201), (1, 16000), (3, 24000), (5, 123457), (2, 960000), (64, 480000), (150, 5000)])
 def test_fused_normalisation_is_bitwise_the_two_kernel_path(dev, shape):
