@@ -780,9 +780,11 @@ bool encode_wave_map(CUtensorMap* tm, const float* wave, long long shift, long l
     const cuuint64_t strides[3] = {kWsTmaInner * sizeof(float), kXBlock * sizeof(float), (cuuint64_t)row_stride * sizeof(float)};
     const cuuint32_t box[4] = {kWsTmaInner, kWsTmaMid, kWsTmaRows, 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
+    static const int l2 = env_int("TALFE_TMA_L2", 2);                    // development knob: L2 promotion none / 64 / 128 / 256 bytes
+    const CUtensorMapL2promotion promo = l2 == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : l2 == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                         : l2 == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
     return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(wave + shift), dims, strides, box, estr,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // ---- frame-per-lane kernel: host side
