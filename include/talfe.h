@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TALFE_VERSION 102 /* major * 100 + minor */
+#define TALFE_VERSION 103 /* major * 100 + minor */
 
 typedef enum talfe_status {
     TALFE_OK = 0,
@@ -124,6 +124,15 @@ int64_t talfe_num_frames(int64_t n_samples);
  * n_mels in 1..80; fb rows 0 and 200 must be all zero and every filter's support contiguous,
  * otherwise TALFE_ERR_UNSUPPORTED. */
 int talfe_plan_create(talfe_plan** plan, int device, int n_mels, const float* window_host, const float* fb_host);
+/* The same for any frame geometry: LogMelSpec(sr) derives n_fft = win = int(0.025 sr) and hop = int(0.010 sr)
+ * (tal/asr/models.py:24-32).  window_host: n_fft floats, fb_host: [n_fft / 2 + 1, n_mels] row-major, both required.
+ * n_fft 400 / hop 160 is talfe_plan_create (the specialised kernels); anything else runs the generic kernel
+ * (any filterbank, n_fft <= 1280, n_mels <= 80; talfe_stream_episode is not available for such plans). */
+int talfe_plan_create_ex(talfe_plan** plan, int device, int n_fft, int hop, int n_mels, const float* window_host,
+                         const float* fb_host);
+int talfe_plan_geometry(const talfe_plan* plan, int* n_fft, int* hop);
+/* 1 + (n_samples + 2 (n_fft / 2) - n_fft) / hop for the plan's geometry, or TALFE_ERR_TOO_SHORT when n_samples <= n_fft / 2. */
+int64_t talfe_plan_num_frames(const talfe_plan* plan, int64_t n_samples);
 void talfe_plan_destroy(talfe_plan* plan);
 int talfe_plan_n_mels(const talfe_plan* plan);
 /* Kernel launches one talfe_logmel_forward of this shape makes with this plan (for honest launch accounting):

@@ -124,6 +124,63 @@ def reference_tables(n_mels: int = N_MELS):
     return _TABLES[n_mels]
 
 
+# --------------------------------------------------------------------------- other sample rates (models.py:24-32)
+def geometry(sr: int):
+    """(n_fft, hop) = (int(0.025 sr), int(0.010 sr)): what LogMelSpec.__init__ hands to MelSpectrogram."""
+    return int(25 / 1000 * sr), int(10 / 1000 * sr)
+
+
+def frame_count_general(n_samples: int, n_fft: int, hop: int) -> int:
+    """torch.stft(center=True): pad n_fft // 2 each side, frames of n_fft every hop -> 1 + (L + 2 (n_fft // 2) - n_fft) // hop
+    (= 1 + L // hop for even n_fft, 1 + (L - 1) // hop for odd)."""
+    if n_samples <= n_fft // 2:
+        raise RuntimeError(f"reflect padding of {n_fft // 2} needs more than {n_fft // 2} samples, got {n_samples}")
+    return 1 + (n_samples + 2 * (n_fft // 2) - n_fft) // hop
+
+
+_TABLES_SR = {}
+
+
+def tables_for(sr: int, n_mels: int = N_MELS):
+    """reference_tables for any sample rate: the module's fp32 buffers (window[n_fft], fb[n_fft // 2 + 1, n_mels])."""
+    key = (sr, n_mels)
+    if key not in _TABLES_SR:
+        import torch
+        n_fft, _ = geometry(sr)
+        window = torch.hann_window(n_fft, periodic=True, dtype=torch.float32)
+        freqs = torch.linspace(0, sr // 2, n_fft // 2 + 1)
+        top = 2595.0 * math.log10(1.0 + (sr // 2) / 700.0)
+        mel_pts = torch.linspace(0.0, top, n_mels + 2)
+        hz_pts = 700.0 * (10.0 ** (mel_pts / 2595.0) - 1.0)
+        width = hz_pts[1:] - hz_pts[:-1]
+        delta = hz_pts.unsqueeze(0) - freqs.unsqueeze(1)
+        fb = torch.clamp(torch.minimum((-1.0 * delta[:, :-2]) / width[:-1], delta[:, 2:] / width[1:]), min=0.0)
+        _TABLES_SR[key] = (window.numpy().copy(), fb.numpy().copy())
+    return _TABLES_SR[key]
+
+
+def logmel_unnormalised_f64_sr(audio: np.ndarray, sr: int, n_mels: int = N_MELS, eps: float = EPS) -> np.ndarray:
+    """[B, L] -> [B, T, n_mels] float64 for LogMelSpec(sr, n_mels) before the mean subtraction: explicit framing
+    (reflect, frame t = padded[hop t, hop t + n_fft)), periodic Hann, rfft, |.|^2, filterbank, log(. + eps)."""
+    audio = np.asarray(audio, dtype=np.float64)
+    n_fft, hop = geometry(sr)
+    window, fb = tables_for(sr, n_mels)
+    out = []
+    for row in audio:
+        T = frame_count_general(row.shape[-1], n_fft, hop)
+        t = np.arange(T, dtype=np.int64)[:, None]
+        j = np.arange(n_fft, dtype=np.int64)[None, :]
+        frames = row[reflect_index(hop * t - n_fft // 2 + j, row.shape[-1])] * window.astype(np.float64)[None, :]
+        spec = np.fft.rfft(frames, n=n_fft, axis=-1)
+        out.append(np.log((spec.real ** 2 + spec.imag ** 2) @ fb.astype(np.float64) + eps))
+    return np.stack(out)
+
+
+def logmel_f64_sr(audio: np.ndarray, sr: int, n_mels: int = N_MELS, eps: float = EPS) -> np.ndarray:
+    y = logmel_unnormalised_f64_sr(audio, sr, n_mels, eps)
+    return y - y.mean()
+
+
 # --------------------------------------------------------------------------- float64 twin
 def power_frames_f64(x: np.ndarray) -> np.ndarray:
     """[L] -> [T, 201] float64 power spectrum of Hann-windowed, centre/reflect frames."""

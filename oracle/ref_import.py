@@ -67,7 +67,8 @@ def load_reference_models():
     return ref_models
 
 
-def reference_logmel(double: bool = False):
-    """An instance of the reference's own LogMelSpec (fp32), or its float64 twin."""
-    mod = load_reference_models().LogMelSpec()
+def reference_logmel(double: bool = False, **ctor):
+    """An instance of the reference's own LogMelSpec (fp32), or its float64 twin; ``ctor``: sr / n_mels / eps as in
+    tal/asr/models.py:22."""
+    mod = load_reference_models().LogMelSpec(**ctor)
     return mod.double() if double else mod

@@ -13,11 +13,12 @@ NORM_NONE, NORM_BATCH_MEAN, NORM_ROW_MEAN, NORM_ROW_MEL_MEAN, NORM_ROW_MEL_MEANV
 LAYOUT_TM, LAYOUT_MT = 0, 1
 ERR_TOO_SHORT = -2
 
-EXPECTED_VERSION = 102     # TALFE_VERSION of include/talfe.h this binding was written against
+EXPECTED_VERSION = 103     # TALFE_VERSION of include/talfe.h this binding was written against
 
 EXPORTED = [
     "talfe_version", "talfe_job_size", "talfe_probe_fp32_fma_rate", "talfe_launches_per_forward",
-    "talfe_strerror", "talfe_last_cuda_error", "talfe_num_frames", "talfe_plan_create",
+    "talfe_strerror", "talfe_last_cuda_error", "talfe_num_frames", "talfe_plan_create", "talfe_plan_create_ex",
+    "talfe_plan_geometry", "talfe_plan_num_frames",
     "talfe_plan_destroy", "talfe_plan_n_mels", "talfe_workspace_bytes", "talfe_run", "talfe_logmel_forward",
     "talfe_apply_stats", "talfe_allreduce_stats", "talfe_synth_fill", "talfe_stream_staging_bytes",
     "talfe_stream_episode",
@@ -71,6 +72,12 @@ def load() -> ctypes.CDLL:
     lib.talfe_probe_fp32_fma_rate.argtypes = [c_int, POINTER(c_double)]
     lib.talfe_launches_per_forward.restype = c_int
     lib.talfe_launches_per_forward.argtypes = [c_void_p, c_int64, c_int64]
+    lib.talfe_plan_create_ex.restype = c_int
+    lib.talfe_plan_create_ex.argtypes = [POINTER(c_void_p), c_int, c_int, c_int, c_int, c_void_p, c_void_p]
+    lib.talfe_plan_geometry.restype = c_int
+    lib.talfe_plan_geometry.argtypes = [c_void_p, POINTER(c_int), POINTER(c_int)]
+    lib.talfe_plan_num_frames.restype = c_int64
+    lib.talfe_plan_num_frames.argtypes = [c_void_p, c_int64]
     return _finish_binding(lib)
 
 

@@ -44,6 +44,13 @@ constexpr int kMaxBands = 16;                               // SpecAugment bands
 constexpr int kColChunk = 256;                              // frames per block in the per-mel statistics pass
 static_assert(kNormalThreads % 32 == 0, "special rows must fill whole warps");
 
+// frames torch.stft(center=True, pad_mode='reflect') makes of L samples: 1 + (L + 2 (n_fft / 2) - n_fft) / hop, and none at
+// all unless L > n_fft / 2 (the reflection needs it).  n_fft = 400, hop = 160: 1 + L / 160.
+__host__ __device__ __forceinline__ long long frames_of(long long L, int hop, int nfft) {
+    const int half = nfft / 2;
+    return L > half ? 1 + (L + 2 * half - nfft) / hop : 0;
+}
+
 thread_local int g_last_cuda_error = 0;
 #ifdef TALFE_TIMELINE
 unsigned* g_timeline = nullptr;
@@ -60,6 +67,9 @@ struct talfe_plan_impl {
     int ctas_per_sm;
     int ref_layout;                // 80-mel reference filterbank shape -> fully unrolled mel stage
     int variant;                   // 0 = legacy kernel (2 CTAs/SM, every thread runs every stage), 1 = warp-specialised
+    int n_fft, hop;                // frame geometry: 400 / 160 for the specialised kernels, anything else -> generic kernel
+    int generic;
+    float* g_win; float2* g_tw; float* g_fb; int* g_mel_lo; int* g_mel_hi;     // generic kernel's tables (device)
     int fl;                        // frame-per-lane kernel for fp32 waveforms (TALFE_KERNEL=fl; needs the reference filterbank support)
     FlTables* fl_tables;           // its uniform tables (host copy: they travel as a kernel parameter)
     int l2_prefetch;
@@ -232,6 +242,7 @@ __device__ __forceinline__ void load_tile(const KernelArgs& a, TileInfo& ti, XT*
 }  // namespace
 #include "talfe_ws.cuh"
 #include "talfe_fl.cuh"
+#include "talfe_generic.cuh"
 namespace {
 
 template <bool kRef, typename XT>
@@ -419,7 +430,7 @@ constexpr int kReduceThreads = 1024;
 __global__ void __launch_bounds__(kReduceThreads) reduce_partials_kernel(const double2* __restrict__ partials, long long slots_per_block,
                                                               const long long* __restrict__ lens, long long total_len,
                                                               long long frame0, long long n_frames, long long rows_per_block,
-                                                              int n_mels, int accumulate, double* __restrict__ stats) {
+                                                              int n_mels, int accumulate, double* __restrict__ stats, int hop, int nfft) {
     __shared__ double s_a[kReduceThreads], s_b[kReduceThreads];
     const long long blk = blockIdx.x;
     const double2* p = partials + blk * slots_per_block;
@@ -435,7 +446,7 @@ __global__ void __launch_bounds__(kReduceThreads) reduce_partials_kernel(const d
         double count = 0.0;
         for (long long r = blk * rows_per_block; r < (blk + 1) * rows_per_block; ++r) {
             const long long L = lens ? lens[r] : total_len;
-            const long long T_row = L > kHalf ? 1 + L / kHop : 0;
+            const long long T_row = frames_of(L, hop, nfft);
             long long v = min(frame0 + n_frames, T_row) - frame0;
             if (v < 0) v = 0;
             count += (double)v * n_mels;
@@ -451,11 +462,11 @@ __global__ void __launch_bounds__(kReduceThreads) reduce_partials_kernel(const d
 __global__ void __launch_bounds__(320) colstats_kernel(const float* __restrict__ feats, long long out_row_stride, int out_layout,
                                                        long long n_frames, int n_mels, const long long* __restrict__ lens,
                                                        long long total_len, long long frame0, double* __restrict__ colpart,
-                                                       const long long* __restrict__ out_offsets) {
+                                                       const long long* __restrict__ out_offsets, int hop, int nfft) {
     __shared__ double s_sum[16][kMaxMels], s_sq[16][kMaxMels];
     const long long row = blockIdx.x, chunk = blockIdx.y;
     const long long L = lens ? lens[row] : total_len;
-    const long long T_row = L > kHalf ? 1 + L / kHop : 0;
+    const long long T_row = frames_of(L, hop, nfft);
     long long valid = min(frame0 + n_frames, T_row) - frame0;
     if (valid < 0) valid = 0;
     const long long f_lo = chunk * kColChunk, f_hi = min(f_lo + kColChunk, valid);
@@ -530,7 +541,7 @@ __global__ void __launch_bounds__(256) apply_stats_kernel(float* __restrict__ fe
                                                           const long long* __restrict__ lens, long long frame0,
                                                           const long long* __restrict__ out_offsets,
                                                           const int* __restrict__ freq_bands, const int* __restrict__ time_bands,
-                                                          int n_bands) {
+                                                          int n_bands, int hop, int nfft) {
     __shared__ float s_mean[kMaxMels], s_rstd[kMaxMels];
     __shared__ int s_tb[2 * kMaxBands];
     const long long row = blockIdx.x;                  // batch on grid.x (no 65 535 limit), sweep blocks on grid.y
@@ -539,7 +550,7 @@ __global__ void __launch_bounds__(256) apply_stats_kernel(float* __restrict__ fe
     if (valid_frames) valid = min(valid_frames[row], n_frames);
     else if (lens) {
         const long long L = lens[row];
-        valid = max(0ll, min(frame0 + n_frames, L > kHalf ? 1 + L / kHop : 0ll) - frame0);
+        valid = max(0ll, min(frame0 + n_frames, frames_of(L, hop, nfft)) - frame0);
     }
     if (threadIdx.x < n_mels) {
         float mean = 0.f, rstd = 1.f;
@@ -873,9 +884,9 @@ int talfe_debug_timeline(unsigned* host_out /* [20][64][8] */) {     // developm
 #endif
 
 int talfe_launches_per_forward(const talfe_plan* plan, int64_t batch, int64_t n_samples) {
-    if (!plan || batch < 1 || n_samples <= kHalf) return TALFE_ERR_INVALID;
-    const WorkspaceLayout w = workspace_layout(plan->n_mels, batch, 1 + n_samples / kHop);
-    const bool fused = plan->variant == 1 && plan->fuse_norm &&
+    if (!plan || batch < 1 || n_samples <= plan->n_fft / 2) return TALFE_ERR_INVALID;
+    const WorkspaceLayout w = workspace_layout(plan->n_mels, batch, frames_of(n_samples, plan->hop, plan->n_fft));
+    const bool fused = !plan->generic && plan->variant == 1 && plan->fuse_norm &&
                        (plan->fuse_norm >= 2 || w.n_tiles <= (long long)kFuseMaxTilesPerCta * plan->sm_count);
     return fused ? 1 : 2;
 }
@@ -900,6 +911,19 @@ int64_t talfe_num_frames(int64_t n_samples) {
     return 1 + n_samples / kHop;
 }
 
+int64_t talfe_plan_num_frames(const talfe_plan* plan, int64_t n_samples) {
+    if (!plan) return TALFE_ERR_INVALID;
+    if (n_samples <= plan->n_fft / 2) return TALFE_ERR_TOO_SHORT;
+    return frames_of(n_samples, plan->hop, plan->n_fft);
+}
+
+int talfe_plan_geometry(const talfe_plan* plan, int* n_fft, int* hop) {
+    if (!plan) return TALFE_ERR_INVALID;
+    if (n_fft) *n_fft = plan->n_fft;
+    if (hop) *hop = plan->hop;
+    return TALFE_OK;
+}
+
 int talfe_plan_create(talfe_plan** plan_out, int device, int n_mels, const float* window_host, const float* fb_host) {
     if (!plan_out) return TALFE_ERR_INVALID;
     *plan_out = nullptr;
@@ -918,6 +942,8 @@ int talfe_plan_create(talfe_plan** plan_out, int device, int n_mels, const float
     if (!p) return TALFE_ERR_INVALID;
     p->device = device;
     p->n_mels = n_mels;
+    p->n_fft = kNfft; p->hop = kHop; p->generic = 0;
+    p->g_win = nullptr; p->g_tw = nullptr; p->g_fb = nullptr; p->g_mel_lo = nullptr; p->g_mel_hi = nullptr;
     p->layout = t.layout;
     p->pstride = t.pstride;
     p->off_tw = t.off_tw; p->off_w = t.off_w; p->off_lo = t.off_lo; p->off_id = t.off_id; p->blob_bytes = t.blob_bytes;
@@ -944,7 +970,8 @@ int talfe_plan_create(talfe_plan** plan_out, int device, int n_mels, const float
     if (e == cudaSuccess) e = cudaMemcpy(p->blob_dev, t.blob.data(), t.blob_bytes, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, device);
     for (int dt = TALFE_F32; dt <= TALFE_I16 && e == cudaSuccess; ++dt)
-        e = cudaFuncSetAttribute(kernel_for(p->ref_layout != 0, dt), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes);
+        e = cudaFuncSetAttribute(kernel_for(p->ref_layout != 0, dt), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 std::max<int>((int)p->smem_bytes, 113 * 1024));   // the attribute is per kernel, plans of several table sizes coexist
     if (e == cudaSuccess)
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p->ctas_per_sm, kernel_for(p->ref_layout != 0, TALFE_F32), kThreads, p->smem_bytes);
     if (p->variant == 1) {
@@ -977,8 +1004,59 @@ int talfe_plan_create(talfe_plan** plan_out, int device, int n_mels, const float
     return TALFE_OK;
 }
 
+// Any other frame geometry (LogMelSpec(sr != 16000): n_fft = win = int(0.025 sr), hop = int(0.010 sr), tal/asr/models.py:24-32)
+// gets a plan for the generic kernel (csrc/talfe_generic.cuh); n_fft 400 / hop 160 delegates to talfe_plan_create.
+int talfe_plan_create_ex(talfe_plan** plan_out, int device, int n_fft, int hop, int n_mels, const float* window_host,
+                         const float* fb_host) {
+    if (!plan_out) return TALFE_ERR_INVALID;
+    *plan_out = nullptr;
+    if (n_fft == kNfft && hop == kHop) return talfe_plan_create(plan_out, device, n_mels, window_host, fb_host);
+    if (!window_host || !fb_host || n_fft < 2 || hop < 1) return TALFE_ERR_INVALID;
+    if (n_mels < 1 || n_mels > kMaxMels || n_fft > kGenMaxNfft || generic_smem_bytes(n_fft, hop) > 232448 - 1024) return TALFE_ERR_UNSUPPORTED;
+    const int bins = n_fft / 2 + 1;
+    std::vector<float2> tw(n_fft);
+    for (int i = 0; i < n_fft; ++i) {
+        const double ang = -2.0 * M_PI * (double)i / (double)n_fft;
+        tw[i] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+    }
+    std::vector<int> lo(n_mels, 1), hi(n_mels, 0);
+    for (int m = 0; m < n_mels; ++m) {
+        int first = -1, last = -1;
+        for (int f = 0; f < bins; ++f)
+            if (fb_host[(size_t)f * n_mels + m] != 0.f) { if (first < 0) first = f; last = f; }
+        if (first >= 0) { lo[m] = first; hi[m] = last; }
+    }
+    int prev = 0;
+    TALFE_CUDA(cudaGetDevice(&prev));
+    TALFE_CUDA(cudaSetDevice(device));
+    talfe_plan* p = new (std::nothrow) talfe_plan();
+    if (!p) return TALFE_ERR_INVALID;
+    p->device = device; p->n_mels = n_mels; p->n_fft = n_fft; p->hop = hop; p->generic = 1;
+    p->variant = 0; p->fl = 0; p->fuse_norm = 0; p->use_tma = 0; p->ref_layout = 0; p->ctas_per_sm = 1;
+    cudaError_t e = cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, device);
+    auto upload = [&](auto** dst, const void* src, size_t bytes) {
+        if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(dst), bytes);
+        if (e == cudaSuccess) e = cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+    };
+    upload(&p->g_win, window_host, sizeof(float) * n_fft);
+    upload(&p->g_tw, tw.data(), sizeof(float2) * n_fft);
+    upload(&p->g_fb, fb_host, sizeof(float) * (size_t)bins * n_mels);
+    upload(&p->g_mel_lo, lo.data(), sizeof(int) * n_mels);
+    upload(&p->g_mel_hi, hi.data(), sizeof(int) * n_mels);
+    // (the attribute belongs to the kernel, not to the plan: plans of different geometries coexist, so ask for the most any of them may need)
+    const int smem = 232448 - 1024;
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_generic_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_generic_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_generic_kernel<short>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaSetDevice(prev);
+    if (e != cudaSuccess) { talfe_plan_destroy(p); return cuda_fail(e); }
+    *plan_out = p;
+    return TALFE_OK;
+}
+
 void talfe_plan_destroy(talfe_plan* plan) {
     if (!plan) return;
+    cudaFree(plan->g_win); cudaFree(plan->g_tw); cudaFree(plan->g_fb); cudaFree(plan->g_mel_lo); cudaFree(plan->g_mel_hi);
     if (plan->blob_dev) cudaFree(plan->blob_dev);
     if (plan->bar_dev) cudaFree(plan->bar_dev);
     delete plan->fl_tables;
@@ -1006,9 +1084,10 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
     if (job->out_layout != TALFE_LAYOUT_TM && job->out_layout != TALFE_LAYOUT_MT) return TALFE_ERR_INVALID;
     if (job->row_stride < job->buf_len) return TALFE_ERR_INVALID;
     if (!(job->eps >= 1.1754944e-38f)) return TALFE_ERR_UNSUPPORTED;    // the log is the bare MUFU.LG2 (subnormals flush): eps keeps its argument normal
+    const int hop = plan->hop, nfft = plan->n_fft, half = nfft / 2;    // 160 / 400 / 200 unless the plan is a generic one
     if (!job->lens) {
-        if (job->total_len <= kHalf) return TALFE_ERR_TOO_SHORT;
-        if (job->frame0 + job->n_frames > 1 + job->total_len / kHop) return TALFE_ERR_INVALID;
+        if (job->total_len <= half) return TALFE_ERR_TOO_SHORT;
+        if (job->frame0 + job->n_frames > frames_of(job->total_len, hop, nfft)) return TALFE_ERR_INVALID;
     }
     const int M = plan->n_mels;
     const long long dense = job->n_frames * M;
@@ -1027,12 +1106,12 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
     KernelArgs a{};
     a.wave = job->wave; a.dtype = job->wave_dtype;
     if (job->buf_len > kMaxSamples || job->origin > kMaxSamples || job->total_len > kMaxSamples ||
-        job->frame0 + job->n_frames > kMaxSamples / kHop || job->batch > 0x7fffffffLL)
+        job->frame0 + job->n_frames > kMaxSamples / hop || job->batch > 0x7fffffffLL)
         return TALFE_ERR_UNSUPPORTED;                         // ~37 h of 16 kHz audio per row: stream it in chunks instead
     a.batch = (int)job->batch; a.row_stride = job->row_stride; a.buf_len = (int)job->buf_len; a.origin = (int)job->origin;
     a.total_len = (int)job->total_len; a.lens = reinterpret_cast<const long long*>(job->lens);
     a.frame0 = (int)job->frame0; a.n_frames = (int)job->n_frames; a.frame_end = a.frame0 + a.n_frames;
-    a.t_end_const = (int)std::min<long long>(a.frame_end, job->total_len > kHalf ? 1 + job->total_len / kHop : 0);
+    a.t_end_const = (int)std::min<long long>(a.frame_end, frames_of(job->total_len, hop, nfft));
     {
         // 160 samples (one hop) are a multiple of 16 bytes for every element type, so whether an interior tile of
         // any row starts 16-byte aligned depends only on the base pointer, the row pitch and the chunk origin
@@ -1045,7 +1124,7 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
     if (w.n_tiles > 0x7fffffffLL) return TALFE_ERR_UNSUPPORTED;
     a.tiles_per_row = (int)w.tiles_per_row; a.n_tiles = (int)w.n_tiles;
     a.partials = reinterpret_cast<double2*>(ws + w.partials);
-    const bool use_ws = plan->variant == 1;
+    const bool use_ws = plan->variant == 1 && !plan->generic;
     a.blob = plan->blob_dev + (use_ws ? plan->off_ws : 0); a.blob_bytes = (int)(use_ws ? plan->ws_bytes : plan->off_ws);
     a.win_global = reinterpret_cast<const float*>(plan->blob_dev);
     a.off_tw = (int)(use_ws ? plan->off_tw_ws : plan->off_tw); a.off_w = (int)plan->off_w; a.off_lo = (int)plan->off_lo; a.off_id = (int)plan->off_id;
@@ -1055,7 +1134,7 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
     a.l2_prefetch = plan->l2_prefetch;
     a.out_align_ok = ((reinterpret_cast<uintptr_t>(job->out) & 15) == 0 && (ors & 3) == 0) ? 1 : 0;
     long long grid = use_ws ? (long long)plan->sm_count : (long long)plan->sm_count * plan->ctas_per_sm;
-    if (grid > w.n_tiles) grid = w.n_tiles;
+    if (grid > w.n_tiles || plan->generic) grid = w.n_tiles;           // generic kernel: one CTA per tile, one partial per CTA
     CUtensorMap tmap{}, tmap_out{};
     bool use_fl = false;
     if (use_ws && plan->fl && a.dtype == TALFE_F32 && a.align_ok && job->row_stride < (1ll << 36)) {
@@ -1120,7 +1199,13 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
         attr[1].id = cudaLaunchAttributeCooperative;
         attr[1].val.cooperative = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        if (use_fl) {
+        if (plan->generic) {
+            GenericArgs g{nfft, hop, half, nfft / 2 + 1, plan->g_win, plan->g_tw, plan->g_fb, plan->g_mel_lo, plan->g_mel_hi, M};
+            cfg.blockDim = dim3(kGenThreads); cfg.dynamicSmemBytes = generic_smem_bytes(nfft, hop);
+            if (a.dtype == TALFE_F32) TALFE_CUDA(cudaLaunchKernelEx(&cfg, logmel_generic_kernel<float>, (const KernelArgs)a, (const GenericArgs)g));
+            else if (a.dtype == TALFE_F16) TALFE_CUDA(cudaLaunchKernelEx(&cfg, logmel_generic_kernel<__half>, (const KernelArgs)a, (const GenericArgs)g));
+            else TALFE_CUDA(cudaLaunchKernelEx(&cfg, logmel_generic_kernel<short>, (const KernelArgs)a, (const GenericArgs)g));
+        } else if (use_fl) {
             cfg.blockDim = dim3(kFlThreads); cfg.dynamicSmemBytes = kFlSmemBytes;
             TALFE_CUDA(cudaLaunchKernelEx(&cfg, logmel_fl_kernel, (const KernelArgs)a, (const CUtensorMap)tmap, (const CUtensorMap)tmap_out,
                                           (const FlTables)*plan->fl_tables));
@@ -1172,12 +1257,12 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
     const long long rows_per_block = per_row ? 1 : job->batch;
     const long long slots_per_block = per_row ? w.tiles_per_row * kWarps : grid;
     reduce_partials_kernel<<<(unsigned)blocks, kReduceThreads, 0, stream>>>(a.partials, slots_per_block, a.lens, a.total_len,
-                                                                  a.frame0, a.n_frames, rows_per_block, M, accumulate, stats);
+                                                                  a.frame0, a.n_frames, rows_per_block, M, accumulate, stats, hop, nfft);
     TALFE_CUDA(cudaGetLastError());
     if (job->norm == TALFE_NORM_ROW_MEL_MEAN || job->norm == TALFE_NORM_ROW_MEL_MEANVAR) {
         double* colpart = reinterpret_cast<double*>(ws + w.colpart);
         colstats_kernel<<<dim3((unsigned)job->batch, (unsigned)w.chunks), 320, 0, stream>>>(job->out, ors, job->out_layout, job->n_frames, M,
-                                                                                           a.lens, a.total_len, a.frame0, colpart, a.out_offsets);
+                                                                                           a.lens, a.total_len, a.frame0, colpart, a.out_offsets, hop, nfft);
         TALFE_CUDA(cudaGetLastError());
         colstats_finish_kernel<<<(unsigned)job->batch, kFinishLanes * kMaxMels, 0, stream>>>(colpart, w.chunks, M, accumulate, stats);
         TALFE_CUDA(cudaGetLastError());
@@ -1186,18 +1271,19 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
     // rows keep their zero fill beyond their own length: the sweep derives valid frames from lens
     apply_stats_kernel<<<dim3((unsigned)job->batch, sweep_blocks(plan->sm_count, job->batch, dense)), 256, 0, stream>>>(
         job->out, job->batch, job->n_frames, ors, job->out_layout, M, job->norm, stats, nullptr, a.lens, a.frame0, a.out_offsets,
-        job->freq_bands, job->time_bands, job->n_bands);
+        job->freq_bands, job->time_bands, job->n_bands, hop, nfft);
     TALFE_CUDA(cudaGetLastError());
     return TALFE_OK;
 }
 
 int talfe_logmel_forward(const talfe_plan* plan, const void* wave, int wave_dtype, int64_t batch, int64_t n_samples,
                          int64_t row_stride, float* out, float eps, void* workspace, size_t workspace_bytes, void* stream) {
-    if (n_samples <= kHalf) return TALFE_ERR_TOO_SHORT;
+    if (!plan) return TALFE_ERR_INVALID;
+    if (n_samples <= plan->n_fft / 2) return TALFE_ERR_TOO_SHORT;
     talfe_job job{};
     job.wave = wave; job.wave_dtype = wave_dtype; job.norm = TALFE_NORM_BATCH_MEAN;
     job.batch = batch; job.row_stride = row_stride; job.buf_len = n_samples; job.origin = 0; job.total_len = n_samples;
-    job.lens = nullptr; job.frame0 = 0; job.n_frames = 1 + n_samples / kHop;
+    job.lens = nullptr; job.frame0 = 0; job.n_frames = frames_of(n_samples, plan->hop, plan->n_fft);
     job.out = out; job.out_row_stride = 0; job.out_layout = TALFE_LAYOUT_TM; job.accumulate_stats = 0;
     job.eps = eps; job.defer_normalise = 0; job.stats = nullptr;
     job.workspace = workspace; job.workspace_bytes = workspace_bytes; job.stream = stream;
@@ -1216,7 +1302,7 @@ int talfe_apply_stats(const talfe_plan* plan, float* feats, int64_t batch, int64
     if (ors < dense) return TALFE_ERR_INVALID;
     apply_stats_kernel<<<dim3((unsigned)batch, sweep_blocks(plan->sm_count, batch, dense)), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         feats, batch, n_frames, ors, out_layout, M, norm, stats, reinterpret_cast<const long long*>(valid_frames), nullptr, 0,
-        nullptr, nullptr, nullptr, 0);
+        nullptr, nullptr, nullptr, 0, plan->hop, plan->n_fft);
     TALFE_CUDA(cudaGetLastError());
     return TALFE_OK;
 }
@@ -1233,6 +1319,7 @@ int talfe_stream_episode(const talfe_plan* plan, const void* wave_host, int wave
                          int64_t chunk_frames, float* out, int norm, int defer_normalise, double* stats, float eps,
                          void* staging, size_t staging_bytes, void* workspace, size_t workspace_bytes, void* stream_v) {
     if (!plan || !wave_host || !out || !stats || chunk_frames < 1) return TALFE_ERR_INVALID;
+    if (plan->generic) return TALFE_ERR_UNSUPPORTED;                   // the chunk arithmetic below is the 16 kHz geometry's
     if (total_len <= kHalf) return TALFE_ERR_TOO_SHORT;
     if (wave_dtype < TALFE_F32 || wave_dtype > TALFE_I16) return TALFE_ERR_INVALID;
     if (norm < TALFE_NORM_NONE || norm > TALFE_NORM_ROW_MEL_MEANVAR) return TALFE_ERR_INVALID;

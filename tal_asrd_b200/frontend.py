@@ -33,17 +33,23 @@ _LAYOUTS = {"tm": _lib.LAYOUT_TM, "mt": _lib.LAYOUT_MT}
 _DTYPES = {torch.float32: _lib.F32, torch.float16: _lib.F16, torch.int16: _lib.I16}
 
 
-def num_frames(n_samples: int) -> int:
-    """T = 1 + L // 160; RuntimeError for L <= 200 like the reference's reflect pad."""
-    if n_samples <= N_FFT // 2:
+def num_frames(n_samples: int, n_fft: int = N_FFT, hop: int = HOP) -> int:
+    """Frames torch.stft(center=True, reflect) makes: 1 + (L + 2 (n_fft // 2) - n_fft) // hop — 1 + L // 160 for the
+    reference's geometry; RuntimeError for L <= n_fft // 2 like the reference's reflect pad."""
+    if n_samples <= n_fft // 2:
         raise RuntimeError(f"Argument #4: Padding size should be less than the corresponding input dimension, "
-                           f"but got: padding ({N_FFT // 2}, {N_FFT // 2}) at dimension 2 of input of length {n_samples}")
-    return 1 + n_samples // HOP
+                           f"but got: padding ({n_fft // 2}, {n_fft // 2}) at dimension 2 of input of length {n_samples}")
+    return 1 + (n_samples + 2 * (n_fft // 2) - n_fft) // hop
+
+
+def geometry(sr: int):
+    """(n_fft, hop) the reference derives from its sample rate (tal/asr/models.py:24-32)."""
+    return int(25 / 1000 * sr), int(10 / 1000 * sr)
 
 
 def reference_tables(n_mels: int = 80, sr: int = DEFAULT_SR):
-    """(window[400], fb[201, n_mels]) evaluated with the same fp32 torch ops as the reference's
-    buffers (torch.hann_window; torchaudio's HTK filterbank recipe), hence bit-identical to them."""
+    """(window[n_fft], fb[n_fft // 2 + 1, n_mels]) evaluated with the same fp32 torch ops as the reference's
+    buffers (torch.hann_window; torchaudio's HTK filterbank recipe with f_max = sr // 2), hence bit-identical to them."""
     n_fft = int(25 / 1000 * sr)
     window = torch.hann_window(n_fft, periodic=True, dtype=torch.float32)
     freqs = torch.linspace(0, sr // 2, n_fft // 2 + 1)
@@ -68,7 +74,7 @@ class _Plan:
     """Owns one talfe_plan (device tables) and frees it with the object.  Also keeps the per-stream workspaces the
     calls need (allocated once and grown on demand, not once per call)."""
 
-    def __init__(self, device: torch.device, n_mels: int, window: torch.Tensor, fb: torch.Tensor):
+    def __init__(self, device: torch.device, n_mels: int, window: torch.Tensor, fb: torch.Tensor, hop: int = HOP):
         import ctypes
         self.lib = _lib.load()
         self.handle = ctypes.c_void_p()
@@ -76,10 +82,12 @@ class _Plan:
         self.device = device
         win = window.detach().to("cpu", torch.float32).contiguous()
         fbc = fb.detach().to("cpu", torch.float32).contiguous()
-        if win.numel() != N_FFT or tuple(fbc.shape) != (N_FFT // 2 + 1, n_mels):
-            raise ValueError("window must have 400 elements and fb must be [201, n_mels]")
-        _lib.check(self.lib.talfe_plan_create(ctypes.byref(self.handle), device.index, n_mels,
-                                              win.data_ptr(), fbc.data_ptr()), "talfe_plan_create")
+        self.n_fft, self.hop = int(win.numel()), int(hop)
+        if tuple(fbc.shape) != (self.n_fft // 2 + 1, n_mels):
+            raise ValueError("fb must be [n_fft // 2 + 1, n_mels] for a window of n_fft elements")
+        # n_fft 400 / hop 160 -> the specialised kernels; any other geometry -> the generic kernel (talfe_generic.cuh)
+        _lib.check(self.lib.talfe_plan_create_ex(ctypes.byref(self.handle), device.index, self.n_fft, self.hop, n_mels,
+                                                 win.data_ptr(), fbc.data_ptr()), "talfe_plan_create_ex")
         self._ws = {}                 # cuda_stream -> uint8 workspace tensor
         self._ws_need = {}            # (batch, n_frames) -> bytes
         self._run = self.lib.talfe_run
@@ -117,15 +125,15 @@ class _Plan:
 _PLANS = {}
 
 
-def _shared_plan(device: torch.device, n_mels: int, window: torch.Tensor, fb: torch.Tensor) -> _Plan:
+def _shared_plan(device: torch.device, n_mels: int, window: torch.Tensor, fb: torch.Tensor, hop: int = HOP) -> _Plan:
     win = window.detach().to("cpu", torch.float32).contiguous()
     fbc = fb.detach().to("cpu", torch.float32).contiguous()
     # the library reads its development switches when a plan is created: they are part of what a plan is
     knobs = tuple(os.environ.get(k) for k in ("TALFE_KERNEL", "TALFE_L2_PREFETCH", "TALFE_FUSED_NORM", "TALFE_TMA", "TALFE_LIB"))
-    key = (device.index, n_mels, hashlib.sha1(win.numpy().tobytes()).digest(), hashlib.sha1(fbc.numpy().tobytes()).digest(), knobs)
+    key = (device.index, n_mels, hop, hashlib.sha1(win.numpy().tobytes()).digest(), hashlib.sha1(fbc.numpy().tobytes()).digest(), knobs)
     plan = _PLANS.get(key)
     if plan is None:
-        plan = _PLANS[key] = _Plan(device, n_mels, win, fbc)
+        plan = _PLANS[key] = _Plan(device, n_mels, win, fbc, hop)
     return plan
 
 
@@ -151,7 +159,7 @@ def _run(plan: _Plan, audio: torch.Tensor, *, norm: int, layout: int, eps: float
     if total_len is None:
         total_len = buf_len
     if n_frames is None:
-        n_frames = num_frames(total_len) - frame0
+        n_frames = num_frames(total_len, plan.n_fft, plan.hop) - frame0
     M = plan.n_mels
     shape = (B, n_frames, M) if layout == _lib.LAYOUT_TM else (B, M, n_frames)
     if out_offsets is not None:
@@ -202,7 +210,7 @@ def _forward_fast(plan: _Plan, audio: torch.Tensor, eps: float, out: Optional[to
         with torch.cuda.device(device):
             return _forward_fast(plan, audio, eps, out)
     B, L = audio.shape
-    T = 1 + L // HOP
+    T = num_frames(L, plan.n_fft, plan.hop)
     if out is None:
         out = torch.empty((B, T, plan.n_mels), dtype=torch.float32, device=device)
     stream_ptr = torch.cuda.current_stream(device).cuda_stream
@@ -258,9 +266,11 @@ class LogMelSpec(nn.Module):
 
     def __init__(self, sr: int = DEFAULT_SR, n_mels: int = 80, eps: float = 1e-6):
         super().__init__()
-        if int(25 / 1000 * sr) != N_FFT or int(10 / 1000 * sr) != HOP:
-            raise NotImplementedError("the sm_100a kernel is specialised for sr=16000 (n_fft=400, hop=160), "
-                                      "the only rate the reference uses (tal/asr/data/__init__.py:6)")
+        # sr = 16000 (n_fft 400, hop 160: the only rate the reference runs at, tal/asr/data/__init__.py:6) is served by the
+        # specialised kernels; any other rate by the generic kernel (same C ABI, same semantics, csrc/talfe_generic.cuh)
+        self.n_fft, self.hop = geometry(sr)
+        if self.n_fft < 2 or self.hop < 1 or self.n_fft > 1280:
+            raise NotImplementedError(f"sr={sr}: n_fft={self.n_fft} is outside what the sm_100a kernels stage in shared memory (2..1280)")
         if not 1 <= n_mels <= 80:
             raise NotImplementedError("n_mels must be in 1..80")
         window, fb = reference_tables(n_mels, sr)
@@ -295,7 +305,7 @@ class LogMelSpec(nn.Module):
             if window.dtype != torch.float32 or fb.dtype != torch.float32:
                 # halved module: its buffers hold ROUNDED tables; the kernels run in float32 from the exact ones
                 window, fb = reference_tables(self.n_mels, self.sr)
-            plan = self._plans[key] = _shared_plan(device, self.n_mels, window, fb)
+            plan = self._plans[key] = _shared_plan(device, self.n_mels, window, fb, self.hop)
         return plan
 
     def _out_dtype(self, audio: torch.Tensor) -> torch.dtype:
@@ -308,7 +318,7 @@ class LogMelSpec(nn.Module):
         with torch.no_grad():
             audio = _prepare_audio(audio)
             device = _require_cuda(audio)
-            num_frames(audio.shape[1])
+            num_frames(audio.shape[1], self.n_fft, self.hop)
             y = _forward_fast(self.plan(device), audio, self.eps)
             return y if self._out_dtype(audio) == torch.float32 else y.half()
 
@@ -332,7 +342,7 @@ class LogMelSpec(nn.Module):
         with torch.no_grad():
             audio = _prepare_audio(audio)
             device = _require_cuda(audio)
-            num_frames(audio.shape[1])
+            num_frames(audio.shape[1], self.n_fft, self.hop)
             lens = None
             if audio_lens is not None:
                 lens = audio_lens.to(device=device, dtype=torch.int64).contiguous()
@@ -361,9 +371,9 @@ class LogMelSpec(nn.Module):
             audio = _prepare_audio(audio)
             device = _require_cuda(audio)
             lens_host = audio_lens.detach().to("cpu", torch.int64)
-            if lens_host.numel() != audio.shape[0] or int(lens_host.min()) <= N_FFT // 2 or int(lens_host.max()) > audio.shape[1]:
-                raise RuntimeError("audio_lens must give every row a length in (200, L]")
-            frames = 1 + lens_host // HOP
+            if lens_host.numel() != audio.shape[0] or int(lens_host.min()) <= self.n_fft // 2 or int(lens_host.max()) > audio.shape[1]:
+                raise RuntimeError(f"audio_lens must give every row a length in ({self.n_fft // 2}, L]")
+            frames = 1 + (lens_host + 2 * (self.n_fft // 2) - self.n_fft) // self.hop
             offsets_host = torch.zeros(audio.shape[0] + 1, dtype=torch.int64)
             offsets_host[1:] = torch.cumsum(frames, 0)
             offsets = offsets_host.to(device)

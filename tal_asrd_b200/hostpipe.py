@@ -91,7 +91,7 @@ class HostPipeline:
         if audio_host.dim() != 2:
             raise ValueError(f"audio must be [batch, audio_len], got shape {tuple(audio_host.shape)}")
         B, L = audio_host.shape
-        T, M = num_frames(L), self.frontend.n_mels
+        T, M = num_frames(L, self.frontend.n_fft, self.frontend.hop), self.frontend.n_mels
         shape = (B, T, M) if self.layout == "tm" else (B, M, T)
         if tuple(out_host.shape) != shape or out_host.dtype != torch.float32 or not out_host.is_contiguous():
             raise ValueError(f"out_host must be a contiguous float32 tensor of shape {shape}")

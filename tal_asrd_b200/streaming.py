@@ -58,6 +58,9 @@ def stream_episode(frontend: LogMelSpec, episode: torch.Tensor, chunk_seconds: f
     """
     if episode.dim() != 1:
         raise ValueError("episode must be a 1-D waveform")
+    if (frontend.n_fft, frontend.hop) != (N_FFT, HOP):
+        raise NotImplementedError("chunked streaming exists for the reference's 16 kHz geometry only (n_fft 400, hop 160); "
+                                  "call the module on the whole episode for other sample rates")
     if episode.dtype not in _DTYPES:
         episode = episode.float()
     if not episode.is_contiguous():

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in talfe.h but not exported"
     assert sorted(_lib.EXPORTED) == declared
-    assert lib.talfe_version() == _lib.EXPECTED_VERSION == 102
+    assert lib.talfe_version() == _lib.EXPECTED_VERSION == 103
     assert lib.talfe_job_size() == __import__("ctypes").sizeof(_lib.Job)
     assert lib.talfe_strerror(-2).decode().startswith("waveform too short")
 
@@ -63,8 +63,14 @@ def test_module_contract_without_gpu():
         m(torch.zeros(2, 16000))                            # never silently falls back to the CPU
     with pytest.raises(ValueError):
         m(torch.zeros(16000))
+    # every sample rate the reference's constructor accepts derives its own geometry (models.py:24-32)
+    m8 = LogMelSpec(sr=8000, n_mels=40)
+    assert (m8.n_fft, m8.hop) == (200, 80) and tuple(m8.mel_transform.mel_scale.fb.shape) == (101, 40)
+    assert tuple(LogMelSpec(sr=22050).mel_transform.spectrogram.window.shape) == (551,)
     with pytest.raises(NotImplementedError):
-        LogMelSpec(sr=8000)
+        LogMelSpec(sr=96000)                                # n_fft 2400: beyond what the kernels stage in shared memory
+    with pytest.raises(NotImplementedError):
+        LogMelSpec(n_mels=81)
     # a reference checkpoint's buffers load under the same keys
     t = np.load(os.path.join(GOLDEN_DIR, "tables.npz"))
     m.load_state_dict({"mel_transform.spectrogram.window": torch.from_numpy(t["window"]),
