@@ -683,6 +683,22 @@ def other_configs(mod, lib, _lib, dev):
     c3["padded_frames_per_s"] = padded_frames / (c3["padded_reference_semantics_ms"] * 1e-3)
     c3["packed_valid_frames_per_s"] = valid / (c3["packed_ms"] * 1e-3)
     res["configs[3] ragged batch 1 s .. 10 min"] = c3
+    del x, lens_t
+    torch.cuda.empty_cache()
+
+    # the rest of the constructor's signature: LogMelSpec(sr != 16000) runs the generic-geometry kernel (a plain direct-DFT
+    # formulation, correct for any n_fft / hop; the reference itself only ever runs at 16 kHz)
+    from tal_asrd_b200 import LogMelSpec
+    rates = {}
+    for sr in (8000, 22050, 48000):
+        m = LogMelSpec(sr=sr).to(dev)
+        xs = torch.randn(16, 10 * sr, device=dev) * 0.1
+        ys = m(xs)
+        ms = timeit(lambda: m.features(xs, out=ys), 5)
+        rates[str(sr)] = {"n_fft": m.n_fft, "hop": m.hop, "batch": "16 x 10 s", "frames": int(ys.shape[0] * ys.shape[1]),
+                          "ms": ms, "frames_per_s": ys.shape[0] * ys.shape[1] / (ms * 1e-3)}
+        del m, xs, ys
+    res["other sample rates (generic kernel)"] = rates
     return res
 
 
