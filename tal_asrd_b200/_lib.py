@@ -72,12 +72,6 @@ def load() -> ctypes.CDLL:
     lib.talfe_probe_fp32_fma_rate.argtypes = [c_int, POINTER(c_double)]
     lib.talfe_launches_per_forward.restype = c_int
     lib.talfe_launches_per_forward.argtypes = [c_void_p, c_int64, c_int64]
-    lib.talfe_plan_create_ex.restype = c_int
-    lib.talfe_plan_create_ex.argtypes = [POINTER(c_void_p), c_int, c_int, c_int, c_int, c_void_p, c_void_p]
-    lib.talfe_plan_geometry.restype = c_int
-    lib.talfe_plan_geometry.argtypes = [c_void_p, POINTER(c_int), POINTER(c_int)]
-    lib.talfe_plan_num_frames.restype = c_int64
-    lib.talfe_plan_num_frames.argtypes = [c_void_p, c_int64]
     return _finish_binding(lib)
 
 
@@ -91,6 +85,13 @@ def _finish_binding(lib, optional: bool = False):
     lib.talfe_num_frames.argtypes = [c_int64]
     lib.talfe_plan_create.restype = c_int
     lib.talfe_plan_create.argtypes = [POINTER(c_void_p), c_int, c_int, c_void_p, c_void_p]
+    if hasattr(lib, "talfe_plan_create_ex"):              # (absent from pre-round-2 builds loaded for A/B runs)
+        lib.talfe_plan_create_ex.restype = c_int
+        lib.talfe_plan_create_ex.argtypes = [POINTER(c_void_p), c_int, c_int, c_int, c_int, c_void_p, c_void_p]
+        lib.talfe_plan_geometry.restype = c_int
+        lib.talfe_plan_geometry.argtypes = [c_void_p, POINTER(c_int), POINTER(c_int)]
+        lib.talfe_plan_num_frames.restype = c_int64
+        lib.talfe_plan_num_frames.argtypes = [c_void_p, c_int64]
     lib.talfe_plan_destroy.restype = None
     lib.talfe_plan_destroy.argtypes = [c_void_p]
     lib.talfe_plan_n_mels.restype = c_int

@@ -44,6 +44,26 @@ static_assert(kWsTileSamples == kTileSamples && kWsRoleWarps == kWarps, "tile ge
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Experiment (round 2, measured and NOT adopted: 80.7 us against 76.4 us, profiles/r02_ab_single_arrive.json): one mbarrier
+// arrival per PHASE instead of one per warp — the warps of a role count themselves in on a shared-memory counter (acq_rel)
+// and the last one arrives, so that the sleeping waiters (NANOSLEEP.SYNCS wakes on every arrival; ~40 warp-instructions per
+// frame go into re-checking incomplete phases) wake once.  The atomic's round trip on every hand-off costs more than the
+// re-checks it saves.  -DTALFE_WS_SINGLE_ARRIVE=1 builds it.
+#ifndef TALFE_WS_SINGLE_ARRIVE
+#define TALFE_WS_SINGLE_ARRIVE 0
+#endif
+__device__ __forceinline__ void mbar_arrive_counted(unsigned long long* bar, unsigned* counter, unsigned n_warps) {
+#if TALFE_WS_SINGLE_ARRIVE
+    unsigned old;
+    asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(counter)) : "memory");
+    if (old == n_warps - 1) {
+        asm volatile("st.relaxed.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(counter)), "r"(0u) : "memory");
+        mbar_arrive(bar);
+    }
+#else
+    mbar_arrive(bar);
+#endif
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -149,6 +169,7 @@ __device__ __forceinline__ void ws_producer(const KernelArgs& a, const void* tma
     unsigned long long* x_empty = s_bar + 2;       // [2]
     unsigned long long* e_full = s_bar + 4;        // [2]
     unsigned long long* e_empty = s_bar + 6;       // [2]
+    unsigned* s_cnt = reinterpret_cast<unsigned*>(s_bar + 8);           // [0..1] x_empty, [2..3] e_full, [4..5] e_empty
     const int warp = tid >> 5, lane = tid & 31;
     const int g1 = tid / kGroup, j = tid - g1 * kGroup;
     constexpr int kXG = XLayout<XT>::kGroup;
@@ -251,7 +272,7 @@ __device__ __forceinline__ void ws_producer(const KernelArgs& a, const void* tma
         }
         __syncwarp();
         TL_MARK(warp, k, 2);
-        if (lane == 0) mbar_arrive(x_empty + buf);                      // this warp no longer reads x[buf]
+        if (lane == 0) mbar_arrive_counted(x_empty + buf, s_cnt + buf, kWsRoleWarps);   // this warp no longer reads x[buf]
         __syncwarp();
         // every tile, active or not: a producer never runs more than one phase ahead of the consumers
         if (k >= 2) mbar_wait_sleep(e_empty + buf, ((k - 2) >> 1) & 1); // consumers have loaded E[buf] of tile k-2
@@ -266,7 +287,7 @@ __device__ __forceinline__ void ws_producer(const KernelArgs& a, const void* tma
             stage1_ws_store(re, im, tw, col0 + buf * kWsECf);
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(e_full + buf);
+        if (lane == 0) mbar_arrive_counted(e_full + buf, s_cnt + 2 + buf, kWsRoleWarps);
         __syncwarp();
         TL_MARK(warp, k, 4);
     }
@@ -352,6 +373,7 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, unsigned char* 
     const int gtid = tid - grp * kCs2Threads;
     unsigned long long* e_full = s_bar + 4 + grp;
     unsigned long long* e_empty = s_bar + 6 + grp;
+    unsigned* s_cnt_empty = reinterpret_cast<unsigned*>(s_bar + 8) + 4 + grp;
     const int warp = tid >> 5, lane = tid & 31;
     const int g = gtid & (kWsGroups - 1), r0 = gtid >> 4, r1 = r0 + 10;  // rows / mel lanes r0 (0..9) and r1 (10..19)
     const bool special1 = r1 >= 18;                                     // the group's last warp: packed rows as its second item
@@ -444,7 +466,7 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, unsigned char* 
             stage2_load(e_row1, v);
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(e_empty);                            // both rows of E[grp] are in registers
+        if (lane == 0) mbar_arrive_counted(e_empty, s_cnt_empty, kWsRoleWarps / 2);    // both rows of E[grp] are in registers
         __syncwarp();
         TL_MARK(10 + warp, k, 3);
         if (active) stage2_row(v, r1, special1);
@@ -598,9 +620,13 @@ __global__ void __launch_bounds__(kWsThreads, 1) logmel_ws_kernel(const KernelAr
     const int tid = threadIdx.x;
     if (tid == 0) {
         mbar_init(s_bar + 0, 1); mbar_init(s_bar + 1, 1);                               // x_full: the loader's arrival (+ bytes)
-        mbar_init(s_bar + 2, kWsRoleWarps); mbar_init(s_bar + 3, kWsRoleWarps);         // x_empty: one arrival per producer warp
-        mbar_init(s_bar + 4, kWsRoleWarps); mbar_init(s_bar + 5, kWsRoleWarps);         // e_full
-        mbar_init(s_bar + 6, kWsRoleWarps / 2); mbar_init(s_bar + 7, kWsRoleWarps / 2); // e_empty: the 5 warps of the buffer's consumer group
+        // x_empty / e_full: the ten producer warps; e_empty: the five warps of the buffer's consumer group — counted in
+        // shared memory, ONE mbarrier arrival per phase by the last of them (mbar_arrive_counted)
+        constexpr unsigned kP = TALFE_WS_SINGLE_ARRIVE ? 1 : kWsRoleWarps, kC = TALFE_WS_SINGLE_ARRIVE ? 1 : kWsRoleWarps / 2;
+        mbar_init(s_bar + 2, kP); mbar_init(s_bar + 3, kP);
+        mbar_init(s_bar + 4, kP); mbar_init(s_bar + 5, kP);
+        mbar_init(s_bar + 6, kC); mbar_init(s_bar + 7, kC);
+        for (int i = 0; i < 6; ++i) reinterpret_cast<unsigned*>(s_bar + 8)[i] = 0;
     }
     {
         const int4* src = reinterpret_cast<const int4*>(a.blob);
@@ -621,7 +647,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) logmel_ws_kernel(const KernelAr
 
 constexpr size_t ws_smem_bytes(size_t table_bytes) {
     return ws_x_offset(table_bytes) + 2 * (size_t)kWsXBufBytes + 2 * (size_t)kWsECf * sizeof(cf) + 2 * (size_t)kWsPCf * sizeof(cf) +
-           2 * (size_t)kWsYFloats * sizeof(float) + kWsDescRing * sizeof(WsDesc) + 8 * sizeof(unsigned long long);
+           2 * (size_t)kWsYFloats * sizeof(float) + kWsDescRing * sizeof(WsDesc) + 8 * sizeof(unsigned long long) + 8 * sizeof(unsigned);
 }
 static_assert(kMaxMels * kWsFrames % kWsRoleThreads == 0 && kWsYFloats >= kWsFrames * kMaxMels + 4 * kWsGroups, "Y staging");
 static_assert(ws_smem_bytes(4160) <= 232448, "the ws kernel's shared memory must fit one SM (227 KB)");

@@ -86,8 +86,12 @@ class _Plan:
         if tuple(fbc.shape) != (self.n_fft // 2 + 1, n_mels):
             raise ValueError("fb must be [n_fft // 2 + 1, n_mels] for a window of n_fft elements")
         # n_fft 400 / hop 160 -> the specialised kernels; any other geometry -> the generic kernel (talfe_generic.cuh)
-        _lib.check(self.lib.talfe_plan_create_ex(ctypes.byref(self.handle), device.index, self.n_fft, self.hop, n_mels,
-                                                 win.data_ptr(), fbc.data_ptr()), "talfe_plan_create_ex")
+        if (self.n_fft, self.hop) == (N_FFT, HOP):
+            _lib.check(self.lib.talfe_plan_create(ctypes.byref(self.handle), device.index, n_mels,
+                                                  win.data_ptr(), fbc.data_ptr()), "talfe_plan_create")
+        else:
+            _lib.check(self.lib.talfe_plan_create_ex(ctypes.byref(self.handle), device.index, self.n_fft, self.hop, n_mels,
+                                                     win.data_ptr(), fbc.data_ptr()), "talfe_plan_create_ex")
         self._ws = {}                 # cuda_stream -> uint8 workspace tensor
         self._ws_need = {}            # (batch, n_frames) -> bytes
         self._run = self.lib.talfe_run
