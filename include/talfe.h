@@ -139,6 +139,13 @@ int talfe_plan_n_mels(const talfe_plan* plan);
  * 1 when the scalar-mean subtraction runs inside the transform kernel (small calls), 2 when a separate sweep follows. */
 int talfe_launches_per_forward(const talfe_plan* plan, int64_t batch, int64_t n_samples);
 
+/* Loader side (tal/asr/data/util.py:44-48): torchaudio.transforms.Resample(orig_freq, 16000) for files that are not 16 kHz.
+ * orig / new_: the two rates divided by their gcd; kernel_dev: DEVICE filter table [new_][2 * width + orig] (built by the
+ * binding with torchaudio's windowed-sinc formula); wave: DEVICE [batch, n_samples] (f32 / f16, or i16 PCM scaled by 1/32768
+ * like torchaudio.load); out: DEVICE float [batch, out_len], out_len = ceil(new_ * n_samples / orig).  batch <= 65535. */
+int talfe_resample(const void* wave, int wave_dtype, int64_t batch, int64_t n_samples, int64_t row_stride, int orig, int new_,
+                   int width, const float* kernel_dev, float* out, int64_t out_len, int64_t out_row_stride, void* stream);
+
 /* Bytes of workspace talfe_run needs for `batch` rows of `n_frames` frames. */
 size_t talfe_workspace_bytes(const talfe_plan* plan, int64_t batch, int64_t n_frames);
 

@@ -18,7 +18,7 @@ EXPECTED_VERSION = 103     # TALFE_VERSION of include/talfe.h this binding was w
 EXPORTED = [
     "talfe_version", "talfe_job_size", "talfe_probe_fp32_fma_rate", "talfe_launches_per_forward",
     "talfe_strerror", "talfe_last_cuda_error", "talfe_num_frames", "talfe_plan_create", "talfe_plan_create_ex",
-    "talfe_plan_geometry", "talfe_plan_num_frames",
+    "talfe_plan_geometry", "talfe_plan_num_frames", "talfe_resample",
     "talfe_plan_destroy", "talfe_plan_n_mels", "talfe_workspace_bytes", "talfe_run", "talfe_logmel_forward",
     "talfe_apply_stats", "talfe_allreduce_stats", "talfe_synth_fill", "talfe_stream_staging_bytes",
     "talfe_stream_episode",
@@ -92,6 +92,10 @@ def _finish_binding(lib, optional: bool = False):
         lib.talfe_plan_geometry.argtypes = [c_void_p, POINTER(c_int), POINTER(c_int)]
         lib.talfe_plan_num_frames.restype = c_int64
         lib.talfe_plan_num_frames.argtypes = [c_void_p, c_int64]
+    if hasattr(lib, "talfe_resample"):
+        lib.talfe_resample.restype = c_int
+        lib.talfe_resample.argtypes = [c_void_p, c_int, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_void_p,
+                                       c_int64, c_int64, c_void_p]
     lib.talfe_plan_destroy.restype = None
     lib.talfe_plan_destroy.argtypes = [c_void_p]
     lib.talfe_plan_n_mels.restype = c_int

@@ -713,6 +713,32 @@ __global__ void synth_kernel(void* wave, int dtype, long long rows, long long n,
     }
 }
 
+// ------------------------------------------------------------------------------------------ resampling (loader side)
+// load_audio_segment resamples a file whose rate is not 16 kHz with torchaudio.transforms.Resample (tal/asr/data/util.py:44-48):
+// a polyphase windowed-sinc FIR, out[b new + j] = sum_k x[b orig - width + k] K[j][k] with zeros beyond the ends
+// (torchaudio/functional/functional.py:_apply_sinc_resample_kernel: pad (width, width + orig), conv1d with stride orig).
+// The filter table K[new][2 width + orig] is built on the host by the binding with torchaudio's own formula.
+template <typename XT>
+__global__ void __launch_bounds__(256) resample_kernel(const XT* __restrict__ x, long long row_stride, long long n, int orig, int new_,
+                                                       int width, const float* __restrict__ K, float* __restrict__ out,
+                                                       long long out_len, long long out_row_stride, float scale) {
+    const XT* xr = x + (long long)blockIdx.y * row_stride;
+    float* orow = out + (long long)blockIdx.y * out_row_stride;
+    const int taps = 2 * width + orig;
+    for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < out_len; o += (long long)gridDim.x * blockDim.x) {
+        const long long blk = o / new_;
+        const int j = (int)(o - blk * new_);
+        const long long base = blk * orig - width;
+        const float* kj = K + (long long)j * taps;
+        float acc = 0.f;
+        for (int k = 0; k < taps; ++k) {
+            const long long i = base + k;
+            if (i >= 0 && i < n) acc = fmaf(x_to_float(xr[i]) * scale, kj[k], acc);
+        }
+        orow[o] = acc;
+    }
+}
+
 typedef void (*logmel_kernel_t)(const KernelArgs);
 logmel_kernel_t kernel_for(bool ref_layout, int dtype) {
     if (ref_layout) return dtype == TALFE_F32 ? logmel_kernel<true, float> : dtype == TALFE_F16 ? logmel_kernel<true, __half> : logmel_kernel<true, short>;
@@ -1288,6 +1314,23 @@ int talfe_logmel_forward(const talfe_plan* plan, const void* wave, int wave_dtyp
     job.eps = eps; job.defer_normalise = 0; job.stats = nullptr;
     job.workspace = workspace; job.workspace_bytes = workspace_bytes; job.stream = stream;
     return talfe_run(plan, &job);
+}
+
+int talfe_resample(const void* wave, int wave_dtype, int64_t batch, int64_t n_samples, int64_t row_stride, int orig, int new_,
+                   int width, const float* kernel_dev, float* out, int64_t out_len, int64_t out_row_stride, void* stream) {
+    if (!wave || !kernel_dev || !out || batch < 1 || batch > 65535 || n_samples < 1 || orig < 1 || new_ < 1 || width < 1) return TALFE_ERR_INVALID;
+    if (wave_dtype < TALFE_F32 || wave_dtype > TALFE_I16 || row_stride < n_samples || out_row_stride < out_len) return TALFE_ERR_INVALID;
+    if (out_len != (new_ * n_samples + orig - 1) / orig) return TALFE_ERR_INVALID;          // ceil(new L / orig), as torchaudio truncates
+    const dim3 grid((unsigned)std::min<long long>((out_len + 255) / 256, 148 * 16), (unsigned)batch);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (wave_dtype == TALFE_F32)
+        resample_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(wave), row_stride, n_samples, orig, new_, width, kernel_dev, out, out_len, out_row_stride, 1.0f);
+    else if (wave_dtype == TALFE_F16)
+        resample_kernel<__half><<<grid, 256, 0, st>>>(reinterpret_cast<const __half*>(wave), row_stride, n_samples, orig, new_, width, kernel_dev, out, out_len, out_row_stride, 1.0f);
+    else
+        resample_kernel<short><<<grid, 256, 0, st>>>(reinterpret_cast<const short*>(wave), row_stride, n_samples, orig, new_, width, kernel_dev, out, out_len, out_row_stride, 1.0f / 32768.0f);
+    TALFE_CUDA(cudaGetLastError());
+    return TALFE_OK;
 }
 
 int talfe_apply_stats(const talfe_plan* plan, float* feats, int64_t batch, int64_t n_frames, int64_t out_row_stride,
