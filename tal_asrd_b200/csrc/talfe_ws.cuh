@@ -49,6 +49,13 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
 // and the last one arrives, so that the sleeping waiters (NANOSLEEP.SYNCS wakes on every arrival; ~40 warp-instructions per
 // frame go into re-checking incomplete phases) wake once.  The atomic's round trip on every hand-off costs more than the
 // re-checks it saves.  -DTALFE_WS_SINGLE_ARRIVE=1 builds it.
+// Experiment (round 2, measured and NOT adopted: 77.9 us against 76.2 us, profiles/r02_ab_loader_waits_e.json): only the
+// loader waits for "E[buf] free", before it lets the next tile's waveform travel, so that x_full implies it and no producer
+// warp pays a second completed try_wait per tile.  It makes the warp with loader duty the straggler of its tile, and the
+// slowest of the ten producer warps is what every consumer waits for.  -DTALFE_WS_LOADER_WAITS_E=1 builds it.
+#ifndef TALFE_WS_LOADER_WAITS_E
+#define TALFE_WS_LOADER_WAITS_E 0
+#endif
 #ifndef TALFE_WS_SINGLE_ARRIVE
 #define TALFE_WS_SINGLE_ARRIVE 0
 #endif
@@ -229,6 +236,13 @@ __device__ __forceinline__ void ws_producer(const KernelArgs& a, const void* tma
         const int row = tile / a.tiles_per_row, tq = tile - row * a.tiles_per_row;
         describe(kk);
         if (kk >= 2) mbar_wait_sleep(x_empty + (kk & 1), ((kk - 2) >> 1) & 1);           // tile kk-2 has left x[kk & 1]
+#if TALFE_WS_LOADER_WAITS_E
+        // ... and E[kk & 1]: the consumers have loaded tile kk-2's rows.  The loader alone waits for it, BEFORE it lets tile
+        // kk's waveform travel: "x_full(kk) complete" then implies "E[kk & 1] free" for every producer warp (release /
+        // acquire chain consumer -> e_empty -> loader -> x_full -> producers), and none of the ten warps pays the ~300
+        // cycles of a second completed try_wait per tile.
+        if (kk >= 2) mbar_wait_sleep(e_empty + (kk & 1), ((kk - 2) >> 1) & 1);
+#endif
         issue(kk);
         if (a.l2_prefetch && lane == 0 && tile + 2 * step < a.n_tiles) {                 // tile kk+2: HBM -> L2
             int r2 = row, q2 = tq;
@@ -275,7 +289,9 @@ __device__ __forceinline__ void ws_producer(const KernelArgs& a, const void* tma
         if (lane == 0) mbar_arrive_counted(x_empty + buf, s_cnt + buf, kWsRoleWarps);   // this warp no longer reads x[buf]
         __syncwarp();
         // every tile, active or not: a producer never runs more than one phase ahead of the consumers
+#if !TALFE_WS_LOADER_WAITS_E
         if (k >= 2) mbar_wait_sleep(e_empty + buf, ((k - 2) >> 1) & 1); // consumers have loaded E[buf] of tile k-2
+#endif
         TL_MARK(warp, k, 3);
         if (active) {
 #pragma unroll
