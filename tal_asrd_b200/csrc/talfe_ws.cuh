@@ -165,6 +165,55 @@ __device__ __forceinline__ void ws_advance(const KernelArgs& a, int& row, int& t
     while (tq >= a.tiles_per_row) { tq -= a.tiles_per_row; ++row; }
 }
 
+// Who fetches the waveform tiles.  0: the producer warps in turn (tile k by warp k % 10, one tile ahead, after waiting for
+// x_empty).  1: the CONSUMER group that has just seen "E[k & 1] full": every producer warp has then finished reading
+// x[k & 1] (it arrives on e_full after its last read), so the buffer is free without any further barrier, the fetch of tile
+// k + 2 gets ~4 000 cycles of lead instead of ~2 600, and the producers — the role that sets the kernel's pace — lose the
+// loader duty that made one of their ten warps the straggler of every tile (and the x_empty arrivals with it).
+// Measured and NOT adopted (profiles/r02_ab_consumer_loads.json): 78.0 us against 76.1 us, bit-identical — the consumer warp
+// with loader duty becomes the straggler of its group at barrier A2; the consumers have less slack than the timeline suggests.
+#ifndef TALFE_WS_CONSUMER_LOADS
+#define TALFE_WS_CONSUMER_LOADS 0
+#endif
+
+// Descriptor of tile kk of this CTA -> ring, then its fetch into x[kk & 1] (all 32 lanes of ONE warp run this; the caller
+// guarantees that x[kk & 1] is free).
+template <typename XT>
+__device__ __forceinline__ void ws_load_tile(const KernelArgs& a, const void* tmap, XT* s_x0, WsDesc* s_desc, unsigned long long* x_full,
+                                             const int kk, const int lane) {
+    constexpr int kXG = XLayout<XT>::kGroup;
+    const int tile = (int)blockIdx.x + kk * (int)gridDim.x;
+    const int row = tile / a.tiles_per_row, tq = tile - row * a.tiles_per_row;
+    long long src_off;
+    WsDesc d = ws_describe(a, row, tq, src_off);
+    const XT* src = reinterpret_cast<const XT*>(a.wave) + src_off;
+    d.src = src;
+    if (lane == 0) s_desc[kk & (kWsDescRing - 1)] = d;
+    __syncwarp();
+    const int lbuf = kk & 1;
+#if defined(TALFE_ABLATE) && (TALFE_ABLATE & 16)
+    const int fetch = 0;                                                 // timing experiment only: no waveform fetch
+#else
+    const int fetch = d.flags & kWsBulkX;
+#endif
+    if (fetch && sizeof(XT) == 4 && a.use_tma) {
+        if (lane == 0) {
+            mbar_expect_tx(x_full + lbuf, kWsTmaBytes);                                    // release: publishes the descriptor too
+            tma_load_4d(smem_u32(s_x0) + lbuf * kWsXBufBytes, tmap, 0, 0, d.pad, d.row, x_full + lbuf, l2_evict_first_policy());
+        }
+    } else if (fetch) {
+        if (lane == 0) mbar_expect_tx(x_full + lbuf, kWsTileSamples * (int)sizeof(XT));   // release: publishes the descriptor too
+        __syncwarp();
+        if (lane * kXBlock < kWsTileSamples)
+            bulk_g2s_u32(smem_u32(s_x0 + lane * kXG) + lbuf * kWsXBufBytes, src + lane * kXBlock,
+                         (unsigned)(min(kXBlock, kWsTileSamples - lane * kXBlock) * (int)sizeof(XT)), x_full + lbuf,
+                         l2_evict_first_policy());
+    } else if (lane == 0) {
+        mbar_arrive(x_full + lbuf);                                                      // nothing in flight: descriptor only
+    }
+    __syncwarp();
+}
+
 // ------------------------------------------------------------------------------------------ producers
 // (ONE group of 10 warps, one frame pair per thread.  Splitting the producers into two groups on alternate tiles like
 // the consumers — two pairs per thread, x[q] / E[q] per group — measured 91.7 us against 80.2 us: each group then holds
@@ -253,10 +302,14 @@ __device__ __forceinline__ void ws_producer(const KernelArgs& a, const void* tma
         }
         __syncwarp();
     };
+#if !TALFE_WS_CONSUMER_LOADS
     if (warp == 0) load_duty(0);
+#endif
     for (int k = 0; k < n_my; ++k) {
         const int buf = k & 1;
+#if !TALFE_WS_CONSUMER_LOADS
         if (k + 1 < n_my && (k + 1) % kWsRoleWarps == warp) load_duty(k + 1);
+#endif
         TL_MARK(warp, k, 0);
         mbar_wait_sleep(x_full + buf, (k >> 1) & 1);                    // descriptor published, bulk tile landed
         TL_MARK(warp, k, 1);
@@ -280,14 +333,17 @@ __device__ __forceinline__ void ws_producer(const KernelArgs& a, const void* tma
                     if (g >= 0 && g < d.L && bi >= 0 && bi < a.buf_len) v = __ldg(rowp + bi);
                     s_x[xskew<XT>(i)] = v;
                 }
+                fence_proxy_async();                                    // these generic writes before the next tensor copy into x[buf]
                 named_bar_sync(2, kWsRoleThreads);
             }
             stage1_ws_fft<XT>(reinterpret_cast<const XT*>(reinterpret_cast<const unsigned char*>(xg) + buf * kXBufBytes), win, re, im);
         }
         __syncwarp();
         TL_MARK(warp, k, 2);
+#if !TALFE_WS_CONSUMER_LOADS
         if (lane == 0) mbar_arrive_counted(x_empty + buf, s_cnt + buf, kWsRoleWarps);   // this warp no longer reads x[buf]
         __syncwarp();
+#endif
         // every tile, active or not: a producer never runs more than one phase ahead of the consumers
 #if !TALFE_WS_LOADER_WAITS_E
         if (k >= 2) mbar_wait_sleep(e_empty + buf, ((k - 2) >> 1) & 1); // consumers have loaded E[buf] of tile k-2
@@ -383,8 +439,8 @@ __device__ __forceinline__ bool ws_store_tile(const KernelArgs& a, const WsDesc*
 // the ablation switches 32 / 64 of that version went with it)
 constexpr int kCs2Threads = kWsRoleThreads / 2;                         // 160
 template <typename XT>
-__device__ __forceinline__ void ws_consumer(const KernelArgs& a, unsigned char* smem, const cf* s_e0, cf* s_p0, float* s_y0,
-                                                const WsDesc* s_desc, unsigned long long* s_bar, const int tid, const int n_my) {
+__device__ __forceinline__ void ws_consumer(const KernelArgs& a, const void* tmap, unsigned char* smem, XT* s_x0, const cf* s_e0, cf* s_p0, float* s_y0,
+                                                WsDesc* s_desc, unsigned long long* s_bar, const int tid, const int n_my) {
     const int grp = tid >= kCs2Threads ? 1 : 0;
     const int gtid = tid - grp * kCs2Threads;
     unsigned long long* e_full = s_bar + 4 + grp;
@@ -465,6 +521,11 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, unsigned char* 
     };
 
     int k_last = -1;
+#if TALFE_WS_CONSUMER_LOADS
+    // the group's first tile: nothing has touched x[grp] yet (published to the rest of the group by barrier A1 below)
+    if (gtid < 32 && grp < n_my) ws_load_tile<XT>(a, tmap, s_x0, s_desc, s_bar, grp, lane);
+    int duty = 1;                                                       // the group's warp that fetches at this tile (in turn)
+#endif
     for (int k = grp; k < n_my; k += 2) {
         const WsDesc* dp = s_desc + (k & (kWsDescRing - 1));
         cf v[20];
@@ -474,6 +535,11 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, unsigned char* 
         if (k >= 2) ws_store_tile<kCs2Threads>(a, s_desc + ((k - 2) & (kWsDescRing - 1)), s_y, gtid);
         mbar_wait_sleep(e_full, (k >> 1) & 1);
         TL_MARK(10 + warp, k, 2);
+#if TALFE_WS_CONSUMER_LOADS
+        // E[grp](k) is full: every producer warp has finished reading x[k & 1] -> tile k + 2 may travel into it
+        if (k + 2 < n_my && (gtid >> 5) == duty) ws_load_tile<XT>(a, tmap, s_x0, s_desc, s_bar, k + 2, lane);
+        duty = duty == kWsRoleWarps / 2 - 1 ? 0 : duty + 1;
+#endif
         const int flags = dp->flags;
         const bool active = flags & kWsActive;
         if (active) {
@@ -654,7 +720,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) logmel_ws_kernel(const KernelAr
     cudaGridDependencySynchronize();
     const int n_my = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles blockIdx.x, + gridDim.x, ...
     if (tid < kWsRoleThreads) ws_producer<XT>(a, &tmap, smem, s_x0, s_e0, s_desc, s_bar, tid, n_my);
-    else ws_consumer<XT>(a, smem, s_e0, s_p0, s_y0, s_desc, s_bar, tid - kWsRoleThreads, n_my);
+    else ws_consumer<XT>(a, &tmap, smem, s_x0, s_e0, s_p0, s_y0, s_desc, s_bar, tid - kWsRoleThreads, n_my);
     if (kFuse) {                                                       // the exchange buffers are free now: scratch for the reduction
         const WsNormArgs na{a.partials, a.grid_bar, a.norm_count, a.stats_out, a.out, a.out_row_stride, a.batch};
         ws_fused_batch_mean(na, smem + x_off + 2 * kWsXBufBytes);
