@@ -26,6 +26,26 @@ namespace {
 constexpr int kWsRoleThreads = kWsGroups * kGroup;          // 320
 constexpr int kWsRoleWarps = kWsRoleThreads / 32;           // 10
 constexpr int kWsThreads = 2 * kWsRoleThreads;              // 640: 10 producer warps, 10 consumer warps (5 per scheduler: 96 registers each)
+// Helper warpgroup (round 2, -DTALFE_WS_HELPER=1): four more warps, one per scheduler, launched with the rest at 80 registers
+// per thread.  `setmaxnreg` then moves registers from the helpers (40) to the twenty compute warps (88): 640 x 88 + 128 x 40
+// = 768 x 80.  Helper warp 0 is the LOADER (tile descriptors, x_empty waits, tensor copies of the waveform tiles — the duty
+// that made one of the ten producer warps the straggler of every tile), helper warp 1 the STORER (bulk copies of the staged
+// feature tiles to global memory, which cost an issuing consumer warp ~270 cycles each); helper warps 2 and 3 exit.
+// Measured and NOT adopted (profiles/r02_ab_helper_warpgroup.json, all bit-identical): against the helpers-idle build the
+// loader warp saves 2.6 us and the storer 0.4 us, but 88 instead of 96 registers for the compute warps costs 5.0 us (81.2 us
+// with idle helpers, 78.6 with the loader, 79.9 with both, 76.2 shipped).  768 x 80 registers is the whole pool a launch of
+// 24 warps can get (allocation granularity 8 per thread), so 96 + a helper warpgroup does not exist on this register file.
+#ifndef TALFE_WS_HELPER
+#define TALFE_WS_HELPER 0
+#endif
+#ifndef TALFE_WS_HELPER_MODE
+#define TALFE_WS_HELPER_MODE 3        // bit 0: the loader duty moves to the helpers, bit 1: the bulk feature stores do
+#endif
+constexpr bool kWsHelperLoads = (TALFE_WS_HELPER_MODE & 1) != 0, kWsHelperStores = (TALFE_WS_HELPER_MODE & 2) != 0;
+constexpr int kWsHelperThreads = 128;
+constexpr int kWsComputeRegs = 88, kWsHelperRegs = 40;
+static_assert(kWsThreads * kWsComputeRegs + kWsHelperThreads * kWsHelperRegs == (kWsThreads + kWsHelperThreads) * 80, "register pool");
+__host__ __device__ constexpr int ws_block_threads(bool fuse) { return (TALFE_WS_HELPER && !fuse) ? kWsThreads + kWsHelperThreads : kWsThreads; }
 constexpr int kWsTileSamples = kHop * kWsFrames + (kNfft - kHop);   // 5360
 // fp32 tiles travel as ONE tensor copy (cp.async.bulk.tensor, SASS UTMALDG): the waveform is described to the copy engine
 // as rows of 340 samples that start every 320 samples (a 4-D tensor map [68][5][rows][batch] with strides 272 B, 1 280 B,
@@ -128,7 +148,7 @@ struct __align__(16) WsDesc {
     const void* src;               // first sample of the tile in global memory (bulk tiles)
     long long pad2;
 };
-constexpr int kWsDescRing = 8;
+constexpr int kWsDescRing = 16;
 enum { kWsActive = 1, kWsFull = 2, kWsBulkX = 4, kWsBulkY = 8 };
 
 __device__ __forceinline__ WsDesc ws_describe(const KernelArgs& a, int row, int tq, long long& src_off) {
@@ -172,34 +192,43 @@ __device__ __forceinline__ void ws_advance(const KernelArgs& a, int& row, int& t
 // loader duty that made one of their ten warps the straggler of every tile (and the x_empty arrivals with it).
 // Measured and NOT adopted (profiles/r02_ab_consumer_loads.json): 78.0 us against 76.1 us, bit-identical — the consumer warp
 // with loader duty becomes the straggler of its group at barrier A2; the consumers have less slack than the timeline suggests.
+// 2: a consumer warp again, but in the group's IDLE window: at the top of its iteration for tile k — before it waits for
+// "E[k & 1] full", which the producers complete ~1 000 cycles after their last read of x[k & 1] — the duty warp (the group's
+// five warps in turn) describes tile k + 2, waits for x_empty(k) and lets the tile travel.  The producers keep their
+// x_empty arrivals and lose the loader duty; the consumers pay for it with time they would have spent waiting.
+// Measured and NOT adopted either (profiles/r02_ab_consumer_loads_idle_window.json): 78.4 us against 76.2 us.
 #ifndef TALFE_WS_CONSUMER_LOADS
 #define TALFE_WS_CONSUMER_LOADS 0
 #endif
 
-// Descriptor of tile kk of this CTA -> ring, then its fetch into x[kk & 1] (all 32 lanes of ONE warp run this; the caller
-// guarantees that x[kk & 1] is free).
+// Descriptor of tile kk of this CTA -> ring (all 32 lanes of ONE warp run this; nothing here touches an x buffer).
 template <typename XT>
-__device__ __forceinline__ void ws_load_tile(const KernelArgs& a, const void* tmap, XT* s_x0, WsDesc* s_desc, unsigned long long* x_full,
-                                             const int kk, const int lane) {
-    constexpr int kXG = XLayout<XT>::kGroup;
+__device__ __forceinline__ WsDesc ws_describe_tile(const KernelArgs& a, WsDesc* s_desc, const int kk, const int lane) {
     const int tile = (int)blockIdx.x + kk * (int)gridDim.x;
     const int row = tile / a.tiles_per_row, tq = tile - row * a.tiles_per_row;
     long long src_off;
     WsDesc d = ws_describe(a, row, tq, src_off);
-    const XT* src = reinterpret_cast<const XT*>(a.wave) + src_off;
-    d.src = src;
+    d.src = reinterpret_cast<const XT*>(a.wave) + src_off;
     if (lane == 0) s_desc[kk & (kWsDescRing - 1)] = d;
     __syncwarp();
+    return d;
+}
+// The fetch of described tile kk into x[kk & 1], which the caller guarantees to be free (same warp, all 32 lanes).
+template <typename XT>
+__device__ __forceinline__ void ws_issue_tile(const KernelArgs& a, const void* tmap, XT* s_x0, unsigned long long* x_full, const int kk,
+                                              const int flags, const int pad, const int row, const void* src_v, const int lane) {
+    constexpr int kXG = XLayout<XT>::kGroup;
+    const XT* src = reinterpret_cast<const XT*>(src_v);
     const int lbuf = kk & 1;
 #if defined(TALFE_ABLATE) && (TALFE_ABLATE & 16)
     const int fetch = 0;                                                 // timing experiment only: no waveform fetch
 #else
-    const int fetch = d.flags & kWsBulkX;
+    const int fetch = flags & kWsBulkX;
 #endif
     if (fetch && sizeof(XT) == 4 && a.use_tma) {
         if (lane == 0) {
             mbar_expect_tx(x_full + lbuf, kWsTmaBytes);                                    // release: publishes the descriptor too
-            tma_load_4d(smem_u32(s_x0) + lbuf * kWsXBufBytes, tmap, 0, 0, d.pad, d.row, x_full + lbuf, l2_evict_first_policy());
+            tma_load_4d(smem_u32(s_x0) + lbuf * kWsXBufBytes, tmap, 0, 0, pad, row, x_full + lbuf, l2_evict_first_policy());
         }
     } else if (fetch) {
         if (lane == 0) mbar_expect_tx(x_full + lbuf, kWsTileSamples * (int)sizeof(XT));   // release: publishes the descriptor too
@@ -213,12 +242,18 @@ __device__ __forceinline__ void ws_load_tile(const KernelArgs& a, const void* tm
     }
     __syncwarp();
 }
+template <typename XT>
+__device__ __forceinline__ void ws_load_tile(const KernelArgs& a, const void* tmap, XT* s_x0, WsDesc* s_desc, unsigned long long* x_full,
+                                             const int kk, const int lane) {
+    const WsDesc d = ws_describe_tile<XT>(a, s_desc, kk, lane);
+    ws_issue_tile<XT>(a, tmap, s_x0, x_full, kk, d.flags, d.pad, d.row, d.src, lane);
+}
 
 // ------------------------------------------------------------------------------------------ producers
 // (ONE group of 10 warps, one frame pair per thread.  Splitting the producers into two groups on alternate tiles like
 // the consumers — two pairs per thread, x[q] / E[q] per group — measured 91.7 us against 80.2 us: each group then holds
 // its exchange buffer for two pairs' worth of work and the consumers wait for it.)
-template <typename XT>
+template <typename XT, bool kHelper>
 __device__ __forceinline__ void ws_producer(const KernelArgs& a, const void* tmap, unsigned char* smem, XT* s_x0, cf* s_e0, WsDesc* s_desc,
                                             unsigned long long* s_bar, const int tid, const int n_my) {
     unsigned long long* x_full = s_bar;            // [2]
@@ -303,12 +338,12 @@ __device__ __forceinline__ void ws_producer(const KernelArgs& a, const void* tma
         __syncwarp();
     };
 #if !TALFE_WS_CONSUMER_LOADS
-    if (warp == 0) load_duty(0);
+    if (!(kHelper && kWsHelperLoads) && warp == 0) load_duty(0);
 #endif
     for (int k = 0; k < n_my; ++k) {
         const int buf = k & 1;
 #if !TALFE_WS_CONSUMER_LOADS
-        if (k + 1 < n_my && (k + 1) % kWsRoleWarps == warp) load_duty(k + 1);
+        if (!(kHelper && kWsHelperLoads) && k + 1 < n_my && (k + 1) % kWsRoleWarps == warp) load_duty(k + 1);
 #endif
         TL_MARK(warp, k, 0);
         mbar_wait_sleep(x_full + buf, (k >> 1) & 1);                    // descriptor published, bulk tile landed
@@ -340,7 +375,7 @@ __device__ __forceinline__ void ws_producer(const KernelArgs& a, const void* tma
         }
         __syncwarp();
         TL_MARK(warp, k, 2);
-#if !TALFE_WS_CONSUMER_LOADS
+#if TALFE_WS_CONSUMER_LOADS != 1
         if (lane == 0) mbar_arrive_counted(x_empty + buf, s_cnt + buf, kWsRoleWarps);   // this warp no longer reads x[buf]
         __syncwarp();
 #endif
@@ -438,13 +473,16 @@ __device__ __forceinline__ bool ws_store_tile(const KernelArgs& a, const WsDesc*
 // (measured against ONE group of 10 warps with one row per thread and one barrier per tile: 80.2 against 82.6 us;
 // the ablation switches 32 / 64 of that version went with it)
 constexpr int kCs2Threads = kWsRoleThreads / 2;                         // 160
-template <typename XT>
+template <typename XT, bool kHelperCta>
 __device__ __forceinline__ void ws_consumer(const KernelArgs& a, const void* tmap, unsigned char* smem, XT* s_x0, const cf* s_e0, cf* s_p0, float* s_y0,
                                                 WsDesc* s_desc, unsigned long long* s_bar, const int tid, const int n_my) {
+    constexpr bool kHelper = kHelperCta && kWsHelperStores;           // full tiles leave through the storer warp
     const int grp = tid >= kCs2Threads ? 1 : 0;
     const int gtid = tid - grp * kCs2Threads;
     unsigned long long* e_full = s_bar + 4 + grp;
     unsigned long long* e_empty = s_bar + 6 + grp;
+    unsigned long long* y_full = s_bar + 12 + grp;                      // (helper build) Y[grp] staged -> the storer
+    unsigned long long* y_empty = s_bar + 14 + grp;                     // (helper build) the storer has read Y[grp]
     unsigned* s_cnt_empty = reinterpret_cast<unsigned*>(s_bar + 8) + 4 + grp;
     const int warp = tid >> 5, lane = tid & 31;
     const int g = gtid & (kWsGroups - 1), r0 = gtid >> 4, r1 = r0 + 10;  // rows / mel lanes r0 (0..9) and r1 (10..19)
@@ -532,10 +570,22 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, const void* tma
         TL_MARK(10 + warp, k, 0);
         named_bar_sync(bar_id, kCs2Threads);                            // A1: mel(k-2) finished everywhere
         TL_MARK(10 + warp, k, 1);
-        if (k >= 2) ws_store_tile<kCs2Threads>(a, s_desc + ((k - 2) & (kWsDescRing - 1)), s_y, gtid);
+        if (k >= 2) {
+            const WsDesc* dprev = s_desc + ((k - 2) & (kWsDescRing - 1));
+            // helper build: full tiles leave through the storer warp; the group itself only handles the element-wise cases
+            if (!kHelper || !(dprev->flags & kWsBulkY)) ws_store_tile<kCs2Threads>(a, dprev, s_y, gtid);
+        }
+#if TALFE_WS_CONSUMER_LOADS == 2
+        if (k + 2 < n_my && (gtid >> 5) == duty) {
+            const WsDesc dn = ws_describe_tile<XT>(a, s_desc, k + 2, lane);
+            mbar_wait_sleep(s_bar + 2 + grp, (k >> 1) & 1);            // x_empty: every producer warp has read tile k out of x[k & 1]
+            ws_issue_tile<XT>(a, tmap, s_x0, s_bar, k + 2, dn.flags, dn.pad, dn.row, dn.src, lane);
+        }
+        duty = duty == kWsRoleWarps / 2 - 1 ? 0 : duty + 1;
+#endif
         mbar_wait_sleep(e_full, (k >> 1) & 1);
         TL_MARK(10 + warp, k, 2);
-#if TALFE_WS_CONSUMER_LOADS
+#if TALFE_WS_CONSUMER_LOADS == 1
         // E[grp](k) is full: every producer warp has finished reading x[k & 1] -> tile k + 2 may travel into it
         if (k + 2 < n_my && (gtid >> 5) == duty) ws_load_tile<XT>(a, tmap, s_x0, s_desc, s_bar, k + 2, lane);
         duty = duty == kWsRoleWarps / 2 - 1 ? 0 : duty + 1;
@@ -553,8 +603,9 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, const void* tma
         TL_MARK(10 + warp, k, 3);
         if (active) stage2_row(v, r1, special1);
         TL_MARK(10 + warp, k, 4);
-        if (lane == 0) bulk_wait_read<0>();                             // this lane's store of tile k-2 has finished reading Y[grp]
+        if (!kHelper && lane == 0) bulk_wait_read<0>();                 // this lane's store of tile k-2 has finished reading Y[grp]
         named_bar_sync(bar_id, kCs2Threads);                            // A2: P[grp](k) complete, Y[grp] free
+        if (kHelper && k >= 2) mbar_wait_sleep(y_empty, ((k - 2) >> 1) & 1);   // the storer is done with tile k-2 in Y[grp]
         TL_MARK(10 + warp, k, 5);
         float sum = 0.f, sumsq = 0.f;
         if (active) {
@@ -562,6 +613,10 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, const void* tma
             mel_lane(s_w4b, lo1, yb_b, dp, flags, sum, sumsq);
         }
         fence_proxy_async();                                            // Y[grp] writes -> visible to the bulk-copy engine
+        if (kHelper) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(y_full);                         // one arrival per warp of the group
+        }
         TL_MARK(10 + warp, k, 6);
         if (a.partials_per_tile) {
             double ds = (double)sum, dq = (double)sumsq;
@@ -582,7 +637,8 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, const void* tma
         k_last = k;
     }
     named_bar_sync(bar_id, kCs2Threads);
-    if (k_last >= 0) ws_store_tile<kCs2Threads>(a, s_desc + (k_last & (kWsDescRing - 1)), s_y, gtid);
+    if (k_last >= 0 && (!kHelper || !(s_desc[k_last & (kWsDescRing - 1)].flags & kWsBulkY)))
+        ws_store_tile<kCs2Threads>(a, s_desc + (k_last & (kWsDescRing - 1)), s_y, gtid);
     if (!a.partials_per_tile) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -599,7 +655,42 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, const void* tma
             a.partials[blockIdx.x] = make_double2(ts, tq2);
         }
     }
-    if (lane == 0) bulk_wait_all<0>();                                  // shared memory must outlive the copies that read it
+    if (!kHelper && lane == 0) bulk_wait_all<0>();                      // shared memory must outlive the copies that read it
+}
+
+// ------------------------------------------------------------------------------------------ helper warpgroup
+// Helper warp 0: every tile's descriptor and waveform fetch, as far ahead as the two x buffers allow.
+// Helper warp 1: every full tile's staged features -> global memory (eight bulk copies of four frames, one per lane), then
+// "Y[q] free" for the consumer group that owns the buffer.  Both run at kWsHelperRegs registers.
+template <typename XT>
+__device__ __forceinline__ void ws_helper(const KernelArgs& a, const void* tmap, XT* s_x0, const float* s_y0, WsDesc* s_desc,
+                                          unsigned long long* s_bar, const int htid, const int n_my) {
+    const int hwarp = htid >> 5, lane = htid & 31;
+    if (hwarp == 0 && kWsHelperLoads) {
+        unsigned long long* x_full = s_bar;
+        unsigned long long* x_empty = s_bar + 2;
+#pragma unroll 1
+        for (int kk = 0; kk < n_my; ++kk) {
+            if (kk >= 2) mbar_wait_sleep(x_empty + (kk & 1), ((kk - 2) >> 1) & 1);       // tile kk-2 has left x[kk & 1]
+            ws_load_tile<XT>(a, tmap, s_x0, s_desc, x_full, kk, lane);
+        }
+    } else if (hwarp == 1 && kWsHelperStores) {
+#pragma unroll 1
+        for (int k = 0; k < n_my; ++k) {
+            const int q = k & 1;
+            mbar_wait_sleep(s_bar + 12 + q, (k >> 1) & 1);                               // Y[q] holds tile k
+            const WsDesc* dp = s_desc + (k & (kWsDescRing - 1));
+            if ((dp->flags & kWsBulkY) && lane < kWsFrames / kWsYChunk) {
+                bulk_s2g(dp->out_tile + kWsYChunk * lane * kMaxMels, smem_u32(s_y0 + q * kWsYFloats + ws_y_off(kWsYChunk * lane)),
+                         kWsYChunk * kMaxMels * (unsigned)sizeof(float));
+                bulk_commit();
+                bulk_wait_read<0>();
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_bar + 14 + q);                                  // Y[q] may be overwritten
+        }
+        bulk_wait_all<0>();                                             // shared memory must outlive the copies that read it
+    }
 }
 
 // ------------------------------------------------------------------------------------------ fused normalisation
@@ -688,7 +779,9 @@ __device__ __noinline__ void ws_fused_batch_mean(const WsNormArgs a, unsigned ch
 __host__ __device__ constexpr size_t ws_x_offset(size_t table_bytes) { return (table_bytes + 127) & ~(size_t)127; }
 
 template <typename XT, bool kFuse>
-__global__ void __launch_bounds__(kWsThreads, 1) logmel_ws_kernel(const KernelArgs a, const __grid_constant__ CUtensorMap tmap) {
+__global__ void __launch_bounds__(ws_block_threads(kFuse), 1) logmel_ws_kernel(const KernelArgs a, const __grid_constant__ CUtensorMap tmap) {
+    constexpr bool kHelper = TALFE_WS_HELPER && !kFuse;
+    constexpr int kNT = ws_block_threads(kFuse);
     extern __shared__ __align__(16) unsigned char smem[];              // (the dynamic window itself starts 1 KB aligned: no static shared memory)
     // carve-up: tables (twiddles | mel weights | first bins) | x[2] (128-byte aligned) | E[2] | P[2] | Y[2] | descriptor ring | 8 mbarriers
     const unsigned x_off = (unsigned)ws_x_offset((size_t)a.blob_bytes);
@@ -709,18 +802,25 @@ __global__ void __launch_bounds__(kWsThreads, 1) logmel_ws_kernel(const KernelAr
         mbar_init(s_bar + 4, kP); mbar_init(s_bar + 5, kP);
         mbar_init(s_bar + 6, kC); mbar_init(s_bar + 7, kC);
         for (int i = 0; i < 6; ++i) reinterpret_cast<unsigned*>(s_bar + 8)[i] = 0;
+        mbar_init(s_bar + 12, kWsRoleWarps / 2); mbar_init(s_bar + 13, kWsRoleWarps / 2);   // y_full: the five warps of a consumer group
+        mbar_init(s_bar + 14, 1); mbar_init(s_bar + 15, 1);                                 // y_empty: the storer
     }
     {
         const int4* src = reinterpret_cast<const int4*>(a.blob);
         int4* dst = reinterpret_cast<int4*>(smem);
-        for (int i = tid; i < a.blob_bytes / 16; i += kWsThreads) dst[i] = __ldg(src + i);
-        for (int i = tid; i < 2 * kWsPCf; i += kWsThreads) s_p0[i] = make_float2(0.f, 0.f);   // incl. the never-written read padding
+        for (int i = tid; i < a.blob_bytes / 16; i += kNT) dst[i] = __ldg(src + i);
+        for (int i = tid; i < 2 * kWsPCf; i += kNT) s_p0[i] = make_float2(0.f, 0.f);   // incl. the never-written read padding
     }
     __syncthreads();
     cudaGridDependencySynchronize();
     const int n_my = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles blockIdx.x, + gridDim.x, ...
-    if (tid < kWsRoleThreads) ws_producer<XT>(a, &tmap, smem, s_x0, s_e0, s_desc, s_bar, tid, n_my);
-    else ws_consumer<XT>(a, &tmap, smem, s_x0, s_e0, s_p0, s_y0, s_desc, s_bar, tid - kWsRoleThreads, n_my);
+    if (kHelper) {                                                       // warpgroup-uniform: warps 0..19 compute, 20..23 help
+        if (tid < kWsThreads) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kWsComputeRegs));
+        else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kWsHelperRegs));
+    }
+    if (tid < kWsRoleThreads) ws_producer<XT, kHelper>(a, &tmap, smem, s_x0, s_e0, s_desc, s_bar, tid, n_my);
+    else if (tid < kWsThreads) ws_consumer<XT, kHelper>(a, &tmap, smem, s_x0, s_e0, s_p0, s_y0, s_desc, s_bar, tid - kWsRoleThreads, n_my);
+    else if (kHelper) ws_helper<XT>(a, &tmap, s_x0, s_y0, s_desc, s_bar, tid - kWsThreads, n_my);
     if (kFuse) {                                                       // the exchange buffers are free now: scratch for the reduction
         const WsNormArgs na{a.partials, a.grid_bar, a.norm_count, a.stats_out, a.out, a.out_row_stride, a.batch};
         ws_fused_batch_mean(na, smem + x_off + 2 * kWsXBufBytes);
@@ -729,7 +829,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) logmel_ws_kernel(const KernelAr
 
 constexpr size_t ws_smem_bytes(size_t table_bytes) {
     return ws_x_offset(table_bytes) + 2 * (size_t)kWsXBufBytes + 2 * (size_t)kWsECf * sizeof(cf) + 2 * (size_t)kWsPCf * sizeof(cf) +
-           2 * (size_t)kWsYFloats * sizeof(float) + kWsDescRing * sizeof(WsDesc) + 8 * sizeof(unsigned long long) + 8 * sizeof(unsigned);
+           2 * (size_t)kWsYFloats * sizeof(float) + kWsDescRing * sizeof(WsDesc) + 16 * sizeof(unsigned long long);
 }
 static_assert(kMaxMels * kWsFrames % kWsRoleThreads == 0 && kWsYFloats >= kWsFrames * kMaxMels + 4 * kWsGroups, "Y staging");
 static_assert(ws_smem_bytes(4160) <= 232448, "the ws kernel's shared memory must fit one SM (227 KB)");
