@@ -25,7 +25,16 @@ namespace {
 
 constexpr int kWsRoleThreads = kWsGroups * kGroup;          // 320
 constexpr int kWsRoleWarps = kWsRoleThreads / 32;           // 10
-constexpr int kWsThreads = 2 * kWsRoleThreads;              // 640: 10 producer warps, 10 consumer warps (5 per scheduler: 96 registers each)
+// -DTALFE_WS_P2=1 (experiment): FIVE producer warps, every producer thread running stage 1 of TWO frame pairs (g1 and g1 + 8)
+// per tile as independent instruction streams — 15 warps at 136 registers instead of 20 at 96: more registers and
+// instruction-level parallelism per warp, half the twiddle loads and barrier arrivals, against fewer warps per scheduler.
+// Measured and NOT adopted (profiles/r02_ab_p2_five_producer_warps.json): 94.5 us against 76.5 us, bit-identical.
+#ifndef TALFE_WS_P2
+#define TALFE_WS_P2 0
+#endif
+constexpr int kWsProdThreads = TALFE_WS_P2 ? kWsRoleThreads / 2 : kWsRoleThreads;   // 160 / 320
+constexpr int kWsProdWarps = kWsProdThreads / 32;                                     // 5 / 10
+constexpr int kWsThreads = kWsProdThreads + kWsRoleThreads;  // 640: 10 producer warps, 10 consumer warps (5 per scheduler: 96 registers each)
 // Helper warpgroup (round 2, -DTALFE_WS_HELPER=1): four more warps, one per scheduler, launched with the rest at 80 registers
 // per thread.  `setmaxnreg` then moves registers from the helpers (40) to the twenty compute warps (88): 640 x 88 + 128 x 40
 // = 768 x 80.  Helper warp 0 is the LOADER (tile descriptors, x_empty waits, tensor copies of the waveform tiles — the duty
@@ -44,7 +53,7 @@ constexpr int kWsThreads = 2 * kWsRoleThreads;              // 640: 10 producer 
 constexpr bool kWsHelperLoads = (TALFE_WS_HELPER_MODE & 1) != 0, kWsHelperStores = (TALFE_WS_HELPER_MODE & 2) != 0;
 constexpr int kWsHelperThreads = 128;
 constexpr int kWsComputeRegs = 88, kWsHelperRegs = 40;
-static_assert(kWsThreads * kWsComputeRegs + kWsHelperThreads * kWsHelperRegs == (kWsThreads + kWsHelperThreads) * 80, "register pool");
+static_assert(!TALFE_WS_HELPER || kWsThreads * kWsComputeRegs + kWsHelperThreads * kWsHelperRegs == (kWsThreads + kWsHelperThreads) * 80, "register pool");
 __host__ __device__ constexpr int ws_block_threads(bool fuse) { return (TALFE_WS_HELPER && !fuse) ? kWsThreads + kWsHelperThreads : kWsThreads; }
 constexpr int kWsTileSamples = kHop * kWsFrames + (kNfft - kHop);   // 5360
 // fp32 tiles travel as ONE tensor copy (cp.async.bulk.tensor, SASS UTMALDG): the waveform is described to the copy engine
@@ -343,7 +352,7 @@ __device__ __forceinline__ void ws_producer(const KernelArgs& a, const void* tma
     for (int k = 0; k < n_my; ++k) {
         const int buf = k & 1;
 #if !TALFE_WS_CONSUMER_LOADS
-        if (!(kHelper && kWsHelperLoads) && k + 1 < n_my && (k + 1) % kWsRoleWarps == warp) load_duty(k + 1);
+        if (!(kHelper && kWsHelperLoads) && k + 1 < n_my && (k + 1) % kWsProdWarps == warp) load_duty(k + 1);
 #endif
         TL_MARK(warp, k, 0);
         mbar_wait_sleep(x_full + buf, (k >> 1) & 1);                    // descriptor published, bulk tile landed
@@ -359,7 +368,7 @@ __device__ __forceinline__ void ws_producer(const KernelArgs& a, const void* tma
                 XT* s_x = reinterpret_cast<XT*>(reinterpret_cast<unsigned char*>(s_x0) + buf * kXBufBytes);
                 const int s0 = kHop * d.t0 - kHalf;
                 const XT* rowp = reinterpret_cast<const XT*>(a.wave) + (long long)d.row * a.row_stride;
-                for (int i = tid; i < kWsTileSamples; i += kWsRoleThreads) {
+                for (int i = tid; i < kWsTileSamples; i += kWsProdThreads) {
                     int g = s0 + i;
                     if (g < 0) g = -g;                                  // reflect, no edge repeat
                     if (g >= d.L) g = 2 * (d.L - 1) - g;
@@ -369,14 +378,35 @@ __device__ __forceinline__ void ws_producer(const KernelArgs& a, const void* tma
                     s_x[xskew<XT>(i)] = v;
                 }
                 fence_proxy_async();                                    // these generic writes before the next tensor copy into x[buf]
-                named_bar_sync(2, kWsRoleThreads);
+                named_bar_sync(2, kWsProdThreads);
             }
             stage1_ws_fft<XT>(reinterpret_cast<const XT*>(reinterpret_cast<const unsigned char*>(xg) + buf * kXBufBytes), win, re, im);
         }
+#if TALFE_WS_P2
+        // second pair of this thread (g1 + 8): pair A's exchange stores and pair B's transform are independent streams
+        if (k >= 2) mbar_wait_sleep(e_empty + buf, ((k - 2) >> 1) & 1); // consumers have loaded E[buf] of tile k-2
+        TL_MARK(warp, k, 3);
+        cf re2[11], im2[11];
+        if (active) {
+#pragma unroll
+            for (int h = 0; h < 5; ++h) {
+                const float4 tt = reinterpret_cast<const float4*>(s_tw)[h];
+                tw[2 * h] = make_float2(tt.x, tt.y);
+                tw[2 * h + 1] = make_float2(tt.z, tt.w);
+            }
+            stage1_ws_store(re, im, tw, col0 + buf * kWsECf);
+            stage1_ws_fft<XT>(reinterpret_cast<const XT*>(reinterpret_cast<const unsigned char*>(xg + (kWsGroups / 2) * kXG) + buf * kXBufBytes), win, re2, im2);
+        }
+        __syncwarp();
+        TL_MARK(warp, k, 2);
+        if (lane == 0) mbar_arrive_counted(x_empty + buf, s_cnt + buf, kWsProdWarps);   // this warp no longer reads x[buf]
+        __syncwarp();
+        if (active) stage1_ws_store(re2, im2, tw, col0 + (ws_e_base(g1 + kWsGroups / 2) - ws_e_base(g1)) + buf * kWsECf);
+#else
         __syncwarp();
         TL_MARK(warp, k, 2);
 #if TALFE_WS_CONSUMER_LOADS != 1
-        if (lane == 0) mbar_arrive_counted(x_empty + buf, s_cnt + buf, kWsRoleWarps);   // this warp no longer reads x[buf]
+        if (lane == 0) mbar_arrive_counted(x_empty + buf, s_cnt + buf, kWsProdWarps);   // this warp no longer reads x[buf]
         __syncwarp();
 #endif
         // every tile, active or not: a producer never runs more than one phase ahead of the consumers
@@ -393,8 +423,9 @@ __device__ __forceinline__ void ws_producer(const KernelArgs& a, const void* tma
             }
             stage1_ws_store(re, im, tw, col0 + buf * kWsECf);
         }
+#endif
         __syncwarp();
-        if (lane == 0) mbar_arrive_counted(e_full + buf, s_cnt + 2 + buf, kWsRoleWarps);
+        if (lane == 0) mbar_arrive_counted(e_full + buf, s_cnt + 2 + buf, kWsProdWarps);
         __syncwarp();
         TL_MARK(warp, k, 4);
     }
@@ -797,7 +828,7 @@ __global__ void __launch_bounds__(ws_block_threads(kFuse), 1) logmel_ws_kernel(c
         mbar_init(s_bar + 0, 1); mbar_init(s_bar + 1, 1);                               // x_full: the loader's arrival (+ bytes)
         // x_empty / e_full: the ten producer warps; e_empty: the five warps of the buffer's consumer group — counted in
         // shared memory, ONE mbarrier arrival per phase by the last of them (mbar_arrive_counted)
-        constexpr unsigned kP = TALFE_WS_SINGLE_ARRIVE ? 1 : kWsRoleWarps, kC = TALFE_WS_SINGLE_ARRIVE ? 1 : kWsRoleWarps / 2;
+        constexpr unsigned kP = TALFE_WS_SINGLE_ARRIVE ? 1 : kWsProdWarps, kC = TALFE_WS_SINGLE_ARRIVE ? 1 : kWsRoleWarps / 2;
         mbar_init(s_bar + 2, kP); mbar_init(s_bar + 3, kP);
         mbar_init(s_bar + 4, kP); mbar_init(s_bar + 5, kP);
         mbar_init(s_bar + 6, kC); mbar_init(s_bar + 7, kC);
@@ -818,8 +849,8 @@ __global__ void __launch_bounds__(ws_block_threads(kFuse), 1) logmel_ws_kernel(c
         if (tid < kWsThreads) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kWsComputeRegs));
         else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kWsHelperRegs));
     }
-    if (tid < kWsRoleThreads) ws_producer<XT, kHelper>(a, &tmap, smem, s_x0, s_e0, s_desc, s_bar, tid, n_my);
-    else if (tid < kWsThreads) ws_consumer<XT, kHelper>(a, &tmap, smem, s_x0, s_e0, s_p0, s_y0, s_desc, s_bar, tid - kWsRoleThreads, n_my);
+    if (tid < kWsProdThreads) ws_producer<XT, kHelper>(a, &tmap, smem, s_x0, s_e0, s_desc, s_bar, tid, n_my);
+    else if (tid < kWsThreads) ws_consumer<XT, kHelper>(a, &tmap, smem, s_x0, s_e0, s_p0, s_y0, s_desc, s_bar, tid - kWsProdThreads, n_my);
     else if (kHelper) ws_helper<XT>(a, &tmap, s_x0, s_y0, s_desc, s_bar, tid - kWsThreads, n_my);
     if (kFuse) {                                                       // the exchange buffers are free now: scratch for the reduction
         const WsNormArgs na{a.partials, a.grid_bar, a.norm_count, a.stats_out, a.out, a.out_row_stride, a.batch};
