@@ -427,6 +427,25 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const KernelArgs a)
 // One block per statistics block (1 for batch-wide, B for per-row).  Fixed-order tree in shared
 // memory: the result does not depend on scheduling.
 constexpr int kReduceThreads = 1024;
+constexpr int kReduceSplit = 64;                 // blocks per row of the first level when a row has many slots
+constexpr long long kReduceSplitMin = 16384;     // rows with fewer slots are reduced by one block, as before
+// First level for long rows: block (row, g) sums slots [g * slice, (g + 1) * slice) of the row in a fixed order.
+__global__ void __launch_bounds__(256) reduce_slices_kernel(const double2* __restrict__ partials, long long slots_per_row, long long slice,
+                                                            double2* __restrict__ out) {
+    __shared__ double s_a[256], s_b[256];
+    const long long row = blockIdx.x, g = blockIdx.y;
+    const long long lo = g * slice, hi = min(lo + slice, slots_per_row);
+    const double2* p = partials + row * slots_per_row;
+    double a = 0.0, b = 0.0;
+    for (long long i = lo + threadIdx.x; i < hi; i += 256) { const double2 v = p[i]; a += v.x; b += v.y; }
+    s_a[threadIdx.x] = a; s_b[threadIdx.x] = b;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) { s_a[threadIdx.x] += s_a[threadIdx.x + o]; s_b[threadIdx.x] += s_b[threadIdx.x + o]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[row * gridDim.y + g] = make_double2(s_a[0], s_b[0]);
+}
 __global__ void __launch_bounds__(kReduceThreads) reduce_partials_kernel(const double2* __restrict__ partials, long long slots_per_block,
                                                               const long long* __restrict__ lens, long long total_len,
                                                               long long frame0, long long n_frames, long long rows_per_block,
@@ -462,14 +481,17 @@ __global__ void __launch_bounds__(kReduceThreads) reduce_partials_kernel(const d
 __global__ void __launch_bounds__(320) colstats_kernel(const float* __restrict__ feats, long long out_row_stride, int out_layout,
                                                        long long n_frames, int n_mels, const long long* __restrict__ lens,
                                                        long long total_len, long long frame0, double* __restrict__ colpart,
-                                                       const long long* __restrict__ out_offsets, int hop, int nfft) {
+                                                       const long long* __restrict__ out_offsets, int hop, int nfft, int chunks_per_block) {
+    // block (row, g) sums the frames of chunks [g * chunks_per_block, (g + 1) * chunks_per_block): one partial per block, so
+    // that the finishing kernel (ONE block per row) reads a few hundred partials even for an hour-long row (it used to read
+    // 1 407 of them through a single SM: 33 us, more than this pass itself)
     __shared__ double s_sum[16][kMaxMels], s_sq[16][kMaxMels];
     const long long row = blockIdx.x, chunk = blockIdx.y;
     const long long L = lens ? lens[row] : total_len;
     const long long T_row = frames_of(L, hop, nfft);
     long long valid = min(frame0 + n_frames, T_row) - frame0;
     if (valid < 0) valid = 0;
-    const long long f_lo = chunk * kColChunk, f_hi = min(f_lo + kColChunk, valid);
+    const long long f_lo = chunk * chunks_per_block * kColChunk, f_hi = min(f_lo + (long long)chunks_per_block * kColChunk, valid);
     const float* base = feats + (out_offsets ? out_offsets[row] * n_mels : row * out_row_stride);
     double* o = colpart + (row * gridDim.y + chunk) * 2 * kMaxMels;
     if (out_layout == TALFE_LAYOUT_TM && n_mels == kMaxMels && (reinterpret_cast<unsigned long long>(base) & 15ull) == 0) {
@@ -510,25 +532,25 @@ __global__ void __launch_bounds__(320) colstats_kernel(const float* __restrict__
     }
 }
 
-constexpr int kFinishLanes = 12;
-__global__ void __launch_bounds__(kFinishLanes * kMaxMels) colstats_finish_kernel(const double* __restrict__ colpart, int chunks, int n_mels,
-                                                                                   int accumulate, double* __restrict__ stats) {
-    // 80 mels x 12 chunk lanes (an hour-long row has 1 407 chunks): lane l sums chunks l, l + 12, ...; fixed order throughout
-    __shared__ double s_a[kFinishLanes][kMaxMels], s_b[kFinishLanes][kMaxMels];
+constexpr int kFinishLanes = 64, kFinishMels = 16;                   // block (row, y): mels [16 y, 16 y + 16) x 64 partial lanes
+__global__ void __launch_bounds__(kFinishLanes * kFinishMels) colstats_finish_kernel(const double* __restrict__ colpart, int chunks, int n_mels,
+                                                                                     int accumulate, double* __restrict__ stats) {
+    // lane l sums partials l, l + 64, ... of its mel; then a fixed-order sum over the 64 lanes (bit-reproducible)
+    __shared__ double s_a[kFinishLanes][kFinishMels], s_b[kFinishLanes][kFinishMels];
     const long long row = blockIdx.x;
-    const int m = threadIdx.x % kMaxMels, l = threadIdx.x / kMaxMels;
+    const int mi = threadIdx.x % kFinishMels, l = threadIdx.x / kFinishMels, m = blockIdx.y * kFinishMels + mi;
     double a = 0.0, b = 0.0;
     if (m < n_mels)
         for (int ch = l; ch < chunks; ch += kFinishLanes) {
             const double* o = colpart + (row * chunks + ch) * 2 * kMaxMels;
             a += o[m]; b += o[kMaxMels + m];
         }
-    s_a[l][m] = a; s_b[l][m] = b;
+    s_a[l][mi] = a; s_b[l][mi] = b;
     __syncthreads();
     if (l != 0 || m >= n_mels) return;
     a = 0.0; b = 0.0;
-#pragma unroll
-    for (int i = 0; i < kFinishLanes; ++i) { a += s_a[i][m]; b += s_b[i][m]; }
+#pragma unroll 8
+    for (int i = 0; i < kFinishLanes; ++i) { a += s_a[i][mi]; b += s_b[i][mi]; }
     double* s = stats + row * TALFE_STATS_DOUBLES(n_mels);
     if (accumulate) { s[3 + m] += a; s[3 + n_mels + m] += b; }
     else { s[3 + m] = a; s[3 + n_mels + m] = b; }
@@ -769,7 +791,7 @@ unsigned sweep_blocks(int sm_count, long long batch, long long dense_per_row) {
     return (unsigned)std::max<long long>(1, std::min<long long>(std::min(want, cap), 65535));   // rides on grid.y
 }
 
-struct WorkspaceLayout { size_t partials, colpart, scratch_stats, total; long long tiles_per_row, n_tiles; int chunks; };
+struct WorkspaceLayout { size_t partials, colpart, scratch_stats, partials2, total; long long tiles_per_row, n_tiles; int chunks; };
 
 WorkspaceLayout workspace_layout(int n_mels, long long batch, long long n_frames) {
     WorkspaceLayout w{};
@@ -783,6 +805,8 @@ WorkspaceLayout workspace_layout(int n_mels, long long batch, long long n_frames
     off += align_up((size_t)batch * w.chunks * 2 * kMaxMels * sizeof(double), 256);
     w.scratch_stats = off;
     off += align_up((size_t)batch * TALFE_STATS_DOUBLES(n_mels) * sizeof(double), 256);
+    w.partials2 = off;                                                  // first-level sums of long rows (reduce_slices_kernel)
+    off += align_up((size_t)batch * kReduceSplit * sizeof(double2), 256);
     w.total = off;
     return w;
 }
@@ -1282,15 +1306,30 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
     const long long blocks = per_row ? job->batch : 1;
     const long long rows_per_block = per_row ? 1 : job->batch;
     const long long slots_per_block = per_row ? w.tiles_per_row * kWarps : grid;
-    reduce_partials_kernel<<<(unsigned)blocks, kReduceThreads, 0, stream>>>(a.partials, slots_per_block, a.lens, a.total_len,
-                                                                  a.frame0, a.n_frames, rows_per_block, M, accumulate, stats, hop, nfft);
+    if (per_row && slots_per_block > kReduceSplitMin) {
+        // a long row (an hour-long episode has 112 510 slots = 1.8 MB): kReduceSplit blocks per row sum contiguous slices in
+        // a fixed order, the final block sums their kReduceSplit results (one block reading it all took 25 us)
+        double2* part2 = reinterpret_cast<double2*>(ws + w.partials2);
+        const long long slice = (slots_per_block + kReduceSplit - 1) / kReduceSplit;
+        reduce_slices_kernel<<<dim3((unsigned)job->batch, kReduceSplit), 256, 0, stream>>>(a.partials, slots_per_block, slice, part2);
+        TALFE_CUDA(cudaGetLastError());
+        reduce_partials_kernel<<<(unsigned)blocks, kReduceThreads, 0, stream>>>(part2, kReduceSplit, a.lens, a.total_len,
+                                                                      a.frame0, a.n_frames, rows_per_block, M, accumulate, stats, hop, nfft);
+    } else {
+        reduce_partials_kernel<<<(unsigned)blocks, kReduceThreads, 0, stream>>>(a.partials, slots_per_block, a.lens, a.total_len,
+                                                                      a.frame0, a.n_frames, rows_per_block, M, accumulate, stats, hop, nfft);
+    }
     TALFE_CUDA(cudaGetLastError());
     if (job->norm == TALFE_NORM_ROW_MEL_MEAN || job->norm == TALFE_NORM_ROW_MEL_MEANVAR) {
         double* colpart = reinterpret_cast<double*>(ws + w.colpart);
-        colstats_kernel<<<dim3((unsigned)job->batch, (unsigned)w.chunks), 320, 0, stream>>>(job->out, ors, job->out_layout, job->n_frames, M,
-                                                                                           a.lens, a.total_len, a.frame0, colpart, a.out_offsets, hop, nfft);
+        // about four blocks per SM over the whole batch, each covering a contiguous range of 256-frame chunks
+        const long long want_blocks = std::max<long long>(1, (long long)plan->sm_count * 4 / job->batch);
+        const int cpb = (int)std::max<long long>(1, (w.chunks + want_blocks - 1) / want_blocks);
+        const int col_blocks = (w.chunks + cpb - 1) / cpb;
+        colstats_kernel<<<dim3((unsigned)job->batch, (unsigned)col_blocks), 320, 0, stream>>>(job->out, ors, job->out_layout, job->n_frames, M,
+                                                                                             a.lens, a.total_len, a.frame0, colpart, a.out_offsets, hop, nfft, cpb);
         TALFE_CUDA(cudaGetLastError());
-        colstats_finish_kernel<<<(unsigned)job->batch, kFinishLanes * kMaxMels, 0, stream>>>(colpart, w.chunks, M, accumulate, stats);
+        colstats_finish_kernel<<<dim3((unsigned)job->batch, kMaxMels / kFinishMels), kFinishLanes * kFinishMels, 0, stream>>>(colpart, col_blocks, M, accumulate, stats);
         TALFE_CUDA(cudaGetLastError());
     }
     if (job->norm == TALFE_NORM_NONE || job->defer_normalise) return TALFE_OK;
