@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TALFE_VERSION 103 /* major * 100 + minor */
+#define TALFE_VERSION 104 /* major * 100 + minor */
 
 typedef enum talfe_status {
     TALFE_OK = 0,
@@ -104,6 +104,12 @@ typedef struct talfe_job {
                              /*   to 0 after normalisation like freq_mask(), tal/asr/models.py:531-548          */
     const int32_t* time_bands;  /* DEVICE [B, n_bands, 2] (first frame, end frame): time_mask(), models.py:550-566 */
     int32_t n_bands;         /* bands per row and axis, 0..16 (empty bands: first == end)                       */
+    const double* given_stats;  /* DEVICE or NULL: ONE statistics block (TALFE_STATS_DOUBLES(M) doubles, e.g. the      */
+                             /*   all-reduced sums of a corpus pass) to normalise EVERY row of this call with,       */
+                             /*   according to `norm`, instead of the call's own statistics: dataset-level CMVN in   */
+                             /*   the transform kernel itself, no sweep over the features (values identical to       */
+                             /*   norm = NONE followed by talfe_apply_stats with that block).  Requires norm != NONE,*/
+                             /*   n_bands == 0, defer_normalise == 0; `stats` is not written.                        */
 } talfe_job;
 
 int talfe_version(void);

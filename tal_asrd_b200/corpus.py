@@ -106,3 +106,16 @@ def corpus_pass(frontend, episodes: Iterable[torch.Tensor], norm: str = "row_mel
     for f in feats:
         frontend.apply_stats(f, total.block, norm=norm)
     return feats, total
+
+
+def corpus_second_pass(frontend, episodes: Iterable[torch.Tensor], total: CorpusStats, norm: str = "row_mel_var",
+                       layout: str = "tm"):
+    """Pass 2 for corpora whose features do NOT stay resident between the passes: every episode of this rank is
+    transformed again and normalised with the GLOBAL statistics (``total`` after its all-reduce) inside the transform
+    kernel itself (``talfe_job::given_stats``) — no sweep over the features.  Yields one [1, T, M] (or [1, M, T])
+    tensor per episode; the values are identical to ``corpus_pass(..., keep_features=True)``'s."""
+    device = torch.device("cuda", torch.cuda.current_device())
+    block = total.block.to(device).contiguous()
+    for ep in episodes:
+        x = ep.to(device, non_blocking=True)
+        yield frontend.features(x.reshape(1, -1), norm=norm, layout=layout, given_stats=block)

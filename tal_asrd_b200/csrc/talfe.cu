@@ -133,6 +133,9 @@ struct KernelArgs {
     unsigned* grid_bar;            // [0] arrivals of the current launch, [1] generation; self-resetting
     double norm_count;             // B * T * M
     double* stats_out;             // count, sum, sum of squares (or nullptr)
+    // dataset-level normalisation applied inside the ws kernel (talfe_job::given_stats): ONE statistics block for every row
+    const double* given_stats;
+    int given_norm;                // talfe_norm that selects which entries of given_stats are used
     unsigned* timeline;            // -DTALFE_TIMELINE development builds only (nullptr otherwise)
 };
 
@@ -240,6 +243,24 @@ __device__ __forceinline__ void load_tile(const KernelArgs& a, TileInfo& ti, XT*
 }
 
 }  // namespace
+// (mean, 1 / std) of mel m from a statistics block, as the normalisation mode defines them: the ONE place this is
+// computed, so that the sweep (apply_stats_kernel) and the in-kernel application (logmel_ws_kernel<.., kApply>) agree bitwise
+static __device__ __forceinline__ void stats_to_norm(const double* __restrict__ s, int norm, int n_mels, int m, float& mean, float& rstd) {
+    mean = 0.f; rstd = 1.f;
+    if (norm == TALFE_NORM_BATCH_MEAN || norm == TALFE_NORM_ROW_MEAN) {
+        mean = s[0] > 0.0 ? (float)(s[1] / s[0]) : 0.f;
+    } else if (norm == TALFE_NORM_ROW_MEL_MEAN || norm == TALFE_NORM_ROW_MEL_MEANVAR) {
+        const double n = s[0] / n_mels;
+        const double mu = n > 0.0 ? s[3 + m] / n : 0.0;
+        mean = (float)mu;
+        if (norm == TALFE_NORM_ROW_MEL_MEANVAR && n > 0.0) {
+            double var = s[3 + n_mels + m] / n - mu * mu;
+            if (var < 1e-10) var = 1e-10;
+            rstd = (float)rsqrt(var);
+        }
+    }
+}
+
 #include "talfe_ws.cuh"
 #include "talfe_fl.cuh"
 #include "talfe_generic.cuh"
@@ -563,11 +584,11 @@ __global__ void __launch_bounds__(256) apply_stats_kernel(float* __restrict__ fe
                                                           const long long* __restrict__ lens, long long frame0,
                                                           const long long* __restrict__ out_offsets,
                                                           const int* __restrict__ freq_bands, const int* __restrict__ time_bands,
-                                                          int n_bands, int hop, int nfft) {
+                                                          int n_bands, int hop, int nfft, int shared_block = 0) {
     __shared__ float s_mean[kMaxMels], s_rstd[kMaxMels];
     __shared__ int s_tb[2 * kMaxBands];
     const long long row = blockIdx.x;                  // batch on grid.x (no 65 535 limit), sweep blocks on grid.y
-    const double* s = stats + (norm == TALFE_NORM_BATCH_MEAN ? 0 : row * TALFE_STATS_DOUBLES(n_mels));
+    const double* s = stats + ((norm == TALFE_NORM_BATCH_MEAN || shared_block) ? 0 : row * TALFE_STATS_DOUBLES(n_mels));
     long long valid = n_frames;
     if (valid_frames) valid = min(valid_frames[row], n_frames);
     else if (lens) {
@@ -575,19 +596,8 @@ __global__ void __launch_bounds__(256) apply_stats_kernel(float* __restrict__ fe
         valid = max(0ll, min(frame0 + n_frames, frames_of(L, hop, nfft)) - frame0);
     }
     if (threadIdx.x < n_mels) {
-        float mean = 0.f, rstd = 1.f;
-        if (norm == TALFE_NORM_BATCH_MEAN || norm == TALFE_NORM_ROW_MEAN) {
-            mean = s[0] > 0.0 ? (float)(s[1] / s[0]) : 0.f;
-        } else if (norm == TALFE_NORM_ROW_MEL_MEAN || norm == TALFE_NORM_ROW_MEL_MEANVAR) {
-            const double n = s[0] / n_mels;
-            const double mu = n > 0.0 ? s[3 + threadIdx.x] / n : 0.0;
-            mean = (float)mu;
-            if (norm == TALFE_NORM_ROW_MEL_MEANVAR && n > 0.0) {
-                double var = s[3 + n_mels + threadIdx.x] / n - mu * mu;
-                if (var < 1e-10) var = 1e-10;
-                rstd = (float)rsqrt(var);
-            }
-        }
+        float mean, rstd;
+        stats_to_norm(s, norm, n_mels, (int)threadIdx.x, mean, rstd);
         // SpecAugment frequency bands (tal/asr/models.py:531-548 sets them to 0 AFTER the mean subtraction):
         // a masked mel keeps its mean but gets a zero scale, so (x - mean) * 0 = 0
         for (int k = 0; k < n_bands; ++k) {
@@ -768,7 +778,8 @@ logmel_kernel_t kernel_for(bool ref_layout, int dtype) {
 }
 
 typedef void (*logmel_ws_kernel_t)(const KernelArgs, const CUtensorMap);
-logmel_ws_kernel_t ws_kernel_for(int dtype, bool fuse = false) {
+logmel_ws_kernel_t ws_kernel_for(int dtype, bool fuse = false, bool apply = false) {
+    if (apply) return dtype == TALFE_F32 ? logmel_ws_kernel<float, false, true> : dtype == TALFE_F16 ? logmel_ws_kernel<__half, false, true> : logmel_ws_kernel<short, false, true>;
     if (fuse) return dtype == TALFE_F32 ? logmel_ws_kernel<float, true> : dtype == TALFE_F16 ? logmel_ws_kernel<__half, true> : logmel_ws_kernel<short, true>;
     return dtype == TALFE_F32 ? logmel_ws_kernel<float, false> : dtype == TALFE_F16 ? logmel_ws_kernel<__half, false> : logmel_ws_kernel<short, false>;
 }
@@ -1028,6 +1039,7 @@ int talfe_plan_create(talfe_plan** plan_out, int device, int n_mels, const float
         for (int dt = TALFE_F32; dt <= TALFE_I16 && e == cudaSuccess; ++dt) {
             e = cudaFuncSetAttribute(ws_kernel_for(dt, false), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->ws_smem);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(ws_kernel_for(dt, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->ws_smem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(ws_kernel_for(dt, false, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->ws_smem);
         }
     }
     if (p->fl && e == cudaSuccess) e = cudaFuncSetAttribute(logmel_fl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFlSmemBytes);
@@ -1147,6 +1159,8 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
     if (job->n_bands < 0 || job->n_bands > kMaxBands) return TALFE_ERR_INVALID;
     if (job->n_bands > 0 && (!job->freq_bands || !job->time_bands || job->norm == TALFE_NORM_NONE || job->defer_normalise))
         return TALFE_ERR_INVALID;                          // the masks ride on the normalisation sweep
+    const bool given = job->given_stats != nullptr;        // normalise with the caller's statistics block (dataset-level CMVN)
+    if (given && (job->norm == TALFE_NORM_NONE || job->n_bands > 0 || job->defer_normalise)) return TALFE_ERR_INVALID;
     const WorkspaceLayout w = workspace_layout(M, job->batch, job->n_frames);
     if (!job->workspace || job->workspace_bytes < w.total) return TALFE_ERR_WORKSPACE;
     if ((reinterpret_cast<uintptr_t>(job->workspace) & 15) != 0) return TALFE_ERR_WORKSPACE;
@@ -1203,13 +1217,17 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
     } else if (use_ws && plan->use_tma && a.dtype == TALFE_F32 && a.align_ok && job->row_stride < (1ll << 36))
         a.use_tma = encode_wave_map(&tmap, reinterpret_cast<const float*>(job->wave), (long long)kHop * job->frame0 - kHalf - job->origin,
                                     job->buf_len, job->row_stride, job->batch) ? 1 : 0;
-    const bool want_stats = job->stats != nullptr || job->norm != TALFE_NORM_NONE;
+    const bool want_stats = !given && (job->stats != nullptr || job->norm != TALFE_NORM_NONE);
     const bool per_row = job->norm >= TALFE_NORM_ROW_MEAN;
-    a.partials_per_tile = per_row ? 1 : 0;                // batch-wide sums: one slot per CTA is enough
-    a.want_sumsq = job->stats != nullptr ? 1 : 0;         // the sum of squares is only ever reported, never needed by K3
+    a.partials_per_tile = (per_row && !given) ? 1 : 0;    // batch-wide sums: one slot per CTA is enough
+    a.want_sumsq = (job->stats != nullptr && !given) ? 1 : 0;   // the sum of squares is only ever reported, never needed by K3
+    // given statistics are applied by the ws kernel's mel stage itself; the other kernels are followed by the sweep
+    const bool apply_in_kernel = given && use_ws && !use_fl && !plan->generic;
+    a.given_stats = apply_in_kernel ? job->given_stats : nullptr;
+    a.given_norm = job->norm;
     // The reference case — one scalar over a contiguous [B, T, M] tensor — CAN be normalised inside the ws kernel itself
     // (cooperative launch, grid barrier, flat sweep split evenly over the CTAs): one launch per LogMelSpec.forward.
-    const bool ref_norm = job->norm == TALFE_NORM_BATCH_MEAN && !a.lens && !(job->accumulate_stats && job->stats) &&
+    const bool ref_norm = !given && job->norm == TALFE_NORM_BATCH_MEAN && !a.lens && !(job->accumulate_stats && job->stats) &&
                           !job->defer_normalise && ors == dense && job->n_bands == 0 &&
                           (reinterpret_cast<uintptr_t>(job->out) & 15) == 0;
     unsigned* bar = nullptr;
@@ -1278,8 +1296,17 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
             TALFE_CUDA(e);
             return TALFE_OK;
         } else {
-            TALFE_CUDA(cudaLaunchKernelEx(&cfg, ws_kernel_for(a.dtype, false), (const KernelArgs)a, (const CUtensorMap)tmap));
+            TALFE_CUDA(cudaLaunchKernelEx(&cfg, ws_kernel_for(a.dtype, false, apply_in_kernel), (const KernelArgs)a, (const CUtensorMap)tmap));
         }
+    }
+    if (given) {
+        if (!apply_in_kernel) {                                         // legacy / frame-per-lane / generic kernel: the sweep applies the block
+            apply_stats_kernel<<<dim3((unsigned)job->batch, sweep_blocks(plan->sm_count, job->batch, dense)), 256, 0, stream>>>(
+                job->out, job->batch, job->n_frames, ors, job->out_layout, M, job->norm, job->given_stats, nullptr, a.lens, a.frame0,
+                a.out_offsets, nullptr, nullptr, 0, hop, nfft, 1);
+            TALFE_CUDA(cudaGetLastError());
+        }
+        return TALFE_OK;
     }
 
     if (!want_stats) return TALFE_OK;

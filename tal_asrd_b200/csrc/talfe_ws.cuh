@@ -504,9 +504,9 @@ __device__ __forceinline__ bool ws_store_tile(const KernelArgs& a, const WsDesc*
 // (measured against ONE group of 10 warps with one row per thread and one barrier per tile: 80.2 against 82.6 us;
 // the ablation switches 32 / 64 of that version went with it)
 constexpr int kCs2Threads = kWsRoleThreads / 2;                         // 160
-template <typename XT, bool kHelperCta>
+template <typename XT, bool kHelperCta, bool kApply>
 __device__ __forceinline__ void ws_consumer(const KernelArgs& a, const void* tmap, unsigned char* smem, XT* s_x0, const cf* s_e0, cf* s_p0, float* s_y0,
-                                                WsDesc* s_desc, unsigned long long* s_bar, const int tid, const int n_my) {
+                                                WsDesc* s_desc, unsigned long long* s_bar, const float2* s_norm, const int tid, const int n_my) {
     constexpr bool kHelper = kHelperCta && kWsHelperStores;           // full tiles leave through the storer warp
     const int grp = tid >= kCs2Threads ? 1 : 0;
     const int gtid = tid - grp * kCs2Threads;
@@ -546,7 +546,7 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, const void* tma
             stage2_ws_store_special(r == 18, pw, s_p + g);
         }
     };
-    auto mel_lane = [&](const float4* s_w4, const int (&lo)[kMelSlots], float* yb, const WsDesc* dp, int flags, float& sum, float& sumsq) {
+    auto mel_lane = [&](const float4* s_w4, const int (&lo)[kMelSlots], float* yb, const WsDesc* dp, int flags, float& sum, float& sumsq, const float2* nrm) {
         float w[kRefWStride];
 #pragma unroll
         for (int q = 0; q < kRefWStride / 4; ++q) {
@@ -555,6 +555,15 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, const void* tma
         }
         float y[2 * kMelSlots];
         mel_log_ws(s_p + g, w, lo, a.eps, y);
+        if (kApply) {
+            // given statistics (talfe_job::given_stats): (y - mean[mel]) * rstd[mel], the two roundings of apply_stats_kernel
+#pragma unroll
+            for (int i = 0; i < kMelSlots; ++i) {
+                const float2 nm = nrm[20 * i];                          // (mean, 1 / std) of mel r + 20 i
+                y[2 * i] = (y[2 * i] - nm.x) * nm.y;
+                y[2 * i + 1] = (y[2 * i + 1] - nm.x) * nm.y;
+            }
+        }
         if (!mt) {
 #pragma unroll
             for (int i = 0; i < kMelSlots; ++i) {
@@ -640,8 +649,8 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, const void* tma
         TL_MARK(10 + warp, k, 5);
         float sum = 0.f, sumsq = 0.f;
         if (active) {
-            mel_lane(s_w4a, lo0, yb_a, dp, flags, sum, sumsq);
-            mel_lane(s_w4b, lo1, yb_b, dp, flags, sum, sumsq);
+            mel_lane(s_w4a, lo0, yb_a, dp, flags, sum, sumsq, s_norm + r0);
+            mel_lane(s_w4b, lo1, yb_b, dp, flags, sum, sumsq, s_norm + r1);
         }
         fence_proxy_async();                                            // Y[grp] writes -> visible to the bulk-copy engine
         if (kHelper) {
@@ -809,7 +818,7 @@ __device__ __noinline__ void ws_fused_batch_mean(const WsNormArgs a, unsigned ch
 
 __host__ __device__ constexpr size_t ws_x_offset(size_t table_bytes) { return (table_bytes + 127) & ~(size_t)127; }
 
-template <typename XT, bool kFuse>
+template <typename XT, bool kFuse, bool kApply = false>
 __global__ void __launch_bounds__(ws_block_threads(kFuse), 1) logmel_ws_kernel(const KernelArgs a, const __grid_constant__ CUtensorMap tmap) {
     constexpr bool kHelper = TALFE_WS_HELPER && !kFuse;
     constexpr int kNT = ws_block_threads(kFuse);
@@ -822,6 +831,7 @@ __global__ void __launch_bounds__(ws_block_threads(kFuse), 1) logmel_ws_kernel(c
     float* s_y0 = reinterpret_cast<float*>(s_p0 + 2 * kWsPCf);
     WsDesc* s_desc = reinterpret_cast<WsDesc*>(s_y0 + 2 * kWsYFloats);
     unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_desc + kWsDescRing);
+    float2* s_norm = reinterpret_cast<float2*>(s_bar + 16);           // [80] (mean, 1 / std) per mel: kApply only
 
     const int tid = threadIdx.x;
     if (tid == 0) {
@@ -844,13 +854,21 @@ __global__ void __launch_bounds__(ws_block_threads(kFuse), 1) logmel_ws_kernel(c
     }
     __syncthreads();
     cudaGridDependencySynchronize();
+    if (kApply) {                                                      // the block may come from the preceding kernel (an all-reduce)
+        if (tid < kMaxMels) {
+            float mean, rstd;
+            stats_to_norm(a.given_stats, a.given_norm, kMaxMels, tid, mean, rstd);
+            s_norm[tid] = make_float2(mean, rstd);
+        }
+        __syncthreads();
+    }
     const int n_my = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles blockIdx.x, + gridDim.x, ...
     if (kHelper) {                                                       // warpgroup-uniform: warps 0..19 compute, 20..23 help
         if (tid < kWsThreads) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kWsComputeRegs));
         else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kWsHelperRegs));
     }
     if (tid < kWsProdThreads) ws_producer<XT, kHelper>(a, &tmap, smem, s_x0, s_e0, s_desc, s_bar, tid, n_my);
-    else if (tid < kWsThreads) ws_consumer<XT, kHelper>(a, &tmap, smem, s_x0, s_e0, s_p0, s_y0, s_desc, s_bar, tid - kWsProdThreads, n_my);
+    else if (tid < kWsThreads) ws_consumer<XT, kHelper, kApply>(a, &tmap, smem, s_x0, s_e0, s_p0, s_y0, s_desc, s_bar, s_norm, tid - kWsProdThreads, n_my);
     else if (kHelper) ws_helper<XT>(a, &tmap, s_x0, s_y0, s_desc, s_bar, tid - kWsThreads, n_my);
     if (kFuse) {                                                       // the exchange buffers are free now: scratch for the reduction
         const WsNormArgs na{a.partials, a.grid_bar, a.norm_count, a.stats_out, a.out, a.out_row_stride, a.batch};
@@ -860,7 +878,7 @@ __global__ void __launch_bounds__(ws_block_threads(kFuse), 1) logmel_ws_kernel(c
 
 constexpr size_t ws_smem_bytes(size_t table_bytes) {
     return ws_x_offset(table_bytes) + 2 * (size_t)kWsXBufBytes + 2 * (size_t)kWsECf * sizeof(cf) + 2 * (size_t)kWsPCf * sizeof(cf) +
-           2 * (size_t)kWsYFloats * sizeof(float) + kWsDescRing * sizeof(WsDesc) + 16 * sizeof(unsigned long long);
+           2 * (size_t)kWsYFloats * sizeof(float) + kWsDescRing * sizeof(WsDesc) + 16 * sizeof(unsigned long long) + kMaxMels * sizeof(float2);
 }
 static_assert(kMaxMels * kWsFrames % kWsRoleThreads == 0 && kWsYFloats >= kWsFrames * kMaxMels + 4 * kWsGroups, "Y staging");
 static_assert(ws_smem_bytes(4160) <= 232448, "the ws kernel's shared memory must fit one SM (227 KB)");

@@ -152,13 +152,13 @@ def _run(plan: _Plan, audio: torch.Tensor, *, norm: int, layout: int, eps: float
          origin: int = 0, total_len: Optional[int] = None, frame0: int = 0, n_frames: Optional[int] = None,
          out: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None, accumulate: bool = False,
          defer: bool = False, out_offsets: Optional[torch.Tensor] = None, packed_frames: int = 0,
-         bands=None) -> torch.Tensor:
+         bands=None, given_stats: Optional[torch.Tensor] = None) -> torch.Tensor:
     device = audio.device
     if torch.cuda.current_device() != device.index:
         with torch.cuda.device(device):          # launches and allocations below need `device` current
             return _run(plan, audio, norm=norm, layout=layout, eps=eps, lens=lens, origin=origin, total_len=total_len,
                         frame0=frame0, n_frames=n_frames, out=out, stats=stats, accumulate=accumulate, defer=defer,
-                        out_offsets=out_offsets, packed_frames=packed_frames, bands=bands)
+                        out_offsets=out_offsets, packed_frames=packed_frames, bands=bands, given_stats=given_stats)
     B, buf_len = audio.shape
     if total_len is None:
         total_len = buf_len
@@ -199,6 +199,8 @@ def _run(plan: _Plan, audio: torch.Tensor, *, norm: int, layout: int, eps: float
     if bands is not None:
         fb, tb = bands
         job.freq_bands, job.time_bands, job.n_bands = fb.data_ptr(), tb.data_ptr(), fb.shape[1]
+    if given_stats is not None:
+        job.given_stats = given_stats.data_ptr()
     job.stream = stream_ptr
     rc = plan._run(plan.handle, job)
     if rc:
@@ -329,7 +331,7 @@ class LogMelSpec(nn.Module):
     @torch.jit.ignore
     def features(self, audio: torch.Tensor, audio_lens: Optional[torch.Tensor] = None, norm: str = "batch",
                  layout: str = "tm", out: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None,
-                 defer_normalise: bool = False, spec_augment=None) -> torch.Tensor:
+                 defer_normalise: bool = False, spec_augment=None, given_stats: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Extension surface on the same kernels.
 
         audio_lens  int64 [B] true lengths (what the collaters emit next to the padded batch,
@@ -342,6 +344,10 @@ class LogMelSpec(nn.Module):
         stats       optional float64 tensor receiving the statistics block(s) (see include/talfe.h)
         spec_augment (freq_bands, time_bands) from ``specaug.sample_masks``: zeroed in the normalisation sweep,
                     replacing ``time_mask(freq_mask(x))`` of tal/asr/models.py:159-161
+        given_stats optional float64 statistics block [1, 3 + 2 M] on the device (e.g. ``CorpusStats.block`` after its
+                    all-reduce): EVERY row is normalised with it, according to ``norm``, inside the transform kernel —
+                    dataset-level CMVN without a sweep over the features; the values are identical to
+                    ``features(norm='none')`` followed by ``apply_stats`` with that block
         """
         with torch.no_grad():
             audio = _prepare_audio(audio)
@@ -362,8 +368,14 @@ class LogMelSpec(nn.Module):
                 if fb.shape != tb.shape or fb.dim() != 3 or fb.shape[0] != audio.shape[0] or fb.shape[2] != 2 or fb.shape[1] > 16:
                     raise ValueError("spec_augment bands must be two int tensors [B, n_bands <= 16, 2]")
                 bands = (fb, tb)
+            if given_stats is not None:
+                if norm == "none" or defer_normalise or spec_augment is not None:
+                    raise ValueError("given_stats needs norm != 'none', no deferral and no spec_augment")
+                if (given_stats.dtype != torch.float64 or given_stats.device != device or not given_stats.is_contiguous()
+                        or given_stats.numel() < _lib.stats_doubles(self.n_mels)):
+                    raise ValueError(f"given_stats must be a contiguous float64 block of {_lib.stats_doubles(self.n_mels)} doubles on {device}")
             return _run(self.plan(device), audio, norm=_NORMS[norm], layout=_LAYOUTS[layout], eps=self.eps,
-                        lens=lens, out=out, stats=stats, defer=defer_normalise, bands=bands)
+                        lens=lens, out=out, stats=stats, defer=defer_normalise, bands=bands, given_stats=given_stats)
 
     @torch.jit.ignore
     def features_packed(self, audio: torch.Tensor, audio_lens: torch.Tensor, norm: str = "row"):

@@ -292,3 +292,50 @@ def test_config4_every_row_against_the_oracle(dev):
         # padded semantics (the reference's): the row as the collater hands it over, zero tail included
         refp = O.logmel_unnormalised_f64(xs[r:r + 1])[0]
         assert rel_err(padded_raw[r], refp) < TOL, r
+
+
+# ------------------------------------------------------------------------------------------ given statistics (dataset-level CMVN)
+@pytest.mark.parametrize("kernel", ["ws", "legacy", "fl"])
+@pytest.mark.parametrize("norm", ["row_mel_var", "row_mel", "batch"])
+def test_given_statistics_in_the_kernel_equal_the_sweep_bitwise(dev, kernel, norm):
+    """talfe_job::given_stats — corpus pass 2: every row normalised with ONE all-reduced statistics block inside the
+    transform kernel — against the two-step form (un-normalised transform, then talfe_apply_stats with that block), which
+    tests/test_streaming_corpus.py pins to the float64 oracle.  Same two roundings per value, hence the same bits: dense,
+    ragged (zero fill beyond a row's own length) and [B, 80, T] outputs, fp32 and int16 PCM."""
+    m = _module(dev, TALFE_KERNEL=kernel)
+    x = _fill(dev, 5, 16000 * 7 + 123, episode=3)
+    # a statistics block from a DIFFERENT batch (the corpus-level sums are not this call's own)
+    other = _fill(dev, 3, 16000 * 4, episode=11)
+    blocks = m.stats_block(dev, rows=3)
+    m.features(other, norm="row_mel_var", stats=blocks, defer_normalise=True)
+    block = blocks.sum(dim=0, keepdim=True).contiguous()
+    lens = torch.tensor([x.shape[1], 50000, 201, 99999, 16000], device=dev)
+    for layout in ("tm", "mt"):
+        for audio_lens in (None, lens):
+            for xx in (x, (x * 32767).round().to(torch.int16)):
+                want = m.features(xx, audio_lens=audio_lens, norm="none", layout=layout)
+                if norm == "batch":
+                    # apply_stats(batch) uses block 0 for every row as well
+                    m.apply_stats(want, block, norm="batch", layout=layout,
+                                  valid_frames=None if audio_lens is None else 1 + audio_lens // 160)
+                else:
+                    rows = block.expand(xx.shape[0], -1).contiguous()
+                    m.apply_stats(want, rows, norm=norm, layout=layout,
+                                  valid_frames=None if audio_lens is None else 1 + audio_lens // 160)
+                got = m.features(xx, audio_lens=audio_lens, norm=norm, layout=layout, given_stats=block)
+                assert torch.equal(got, want), (kernel, norm, layout, audio_lens is not None, xx.dtype)
+    with pytest.raises(ValueError):
+        m.features(x, norm="none", given_stats=block)
+
+
+def test_given_statistics_generic_geometry(dev):
+    """The same through the generic-geometry kernel (LogMelSpec(sr != 16000)): the sweep applies the block."""
+    from tal_asrd_b200 import LogMelSpec
+    m = LogMelSpec(sr=8000).to(dev)
+    x = _fill(dev, 3, 8000 * 5, episode=5)
+    blocks = m.stats_block(dev, rows=3)
+    m.features(x, norm="row_mel_var", stats=blocks, defer_normalise=True)
+    block = blocks.sum(dim=0, keepdim=True).contiguous()
+    want = m.features(x, norm="none")
+    m.apply_stats(want, block.expand(3, -1).contiguous(), norm="row_mel_var")
+    assert torch.equal(m.features(x, norm="row_mel_var", given_stats=block), want)

@@ -161,6 +161,11 @@ def test_corpus_pass_single_rank_global_cmvn():
     got = np.concatenate([f[0].cpu().numpy() for f in feats])
     want = (raw - raw.mean(0)) / raw.std(0)
     assert rel_err(got, want) < 5e-4
+    # pass 2 for corpora whose features do not stay resident: the global statistics applied inside the transform kernel
+    from tal_asrd_b200.corpus import corpus_second_pass
+    again = np.concatenate([f[0].cpu().numpy() for f in corpus_second_pass(mod, eps_, stats)])
+    assert rel_err(again, want) < 5e-4
+    assert np.abs(again - got).max() < 2e-5          # (streamed 2-s chunks vs one shot: chunk-edge tiles regroup the sums)
 
 
 def _nccl_corpus_worker(rank, world, port, q):
