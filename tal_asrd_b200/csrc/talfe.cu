@@ -1219,7 +1219,11 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
                                     job->buf_len, job->row_stride, job->batch) ? 1 : 0;
     const bool want_stats = !given && (job->stats != nullptr || job->norm != TALFE_NORM_NONE);
     const bool per_row = job->norm >= TALFE_NORM_ROW_MEAN;
-    a.partials_per_tile = (per_row && !given) ? 1 : 0;    // batch-wide sums: one slot per CTA is enough
+    // one slot per CTA is enough for batch-wide sums — and for per-row sums of a ONE-row call (an episode of a corpus pass,
+    // a streamed chunk): per-tile slots (a double shuffle tree per warp and tile in the consumers, 16 bytes x 10 per tile
+    // to reduce afterwards) cost 10 us per hour-long episode
+    const bool tile_slots = per_row && !given && job->batch > 1;
+    a.partials_per_tile = tile_slots ? 1 : 0;
     a.want_sumsq = (job->stats != nullptr && !given) ? 1 : 0;   // the sum of squares is only ever reported, never needed by K3
     // given statistics are applied by the ws kernel's mel stage itself; the other kernels are followed by the sweep
     const bool apply_in_kernel = given && use_ws && !use_fl && !plan->generic;
@@ -1332,8 +1336,8 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
     }
     const long long blocks = per_row ? job->batch : 1;
     const long long rows_per_block = per_row ? 1 : job->batch;
-    const long long slots_per_block = per_row ? w.tiles_per_row * kWarps : grid;
-    if (per_row && slots_per_block > kReduceSplitMin) {
+    const long long slots_per_block = tile_slots ? w.tiles_per_row * kWarps : grid;
+    if (tile_slots && slots_per_block > kReduceSplitMin) {
         // a long row (an hour-long episode has 112 510 slots = 1.8 MB): kReduceSplit blocks per row sum contiguous slices in
         // a fixed order, the final block sums their kReduceSplit results (one block reading it all took 25 us)
         double2* part2 = reinterpret_cast<double2*>(ws + w.partials2);
