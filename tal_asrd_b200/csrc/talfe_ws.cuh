@@ -146,6 +146,34 @@ __device__ __forceinline__ void mbar_wait_sleep(unsigned long long* bar, unsigne
     }
 }
 
+// The producers' wait for "E[buf] free" polls with mbarrier.test_wait and a FIXED nanosleep between polls instead of
+// try_wait's event-driven suspension.  The ncu source view of the try_wait form showed that loop running 8.6 iterations
+// per frame — 28 per producer warp and tile, two SYNCS operations each through the shared-memory instruction queue: a
+// suspended warp is woken by every mbarrier event of the CTA (the tile copy's transaction updates included), not only by
+// the arrivals it waits for.  Measured (profiles/r02_ab_wait_backoff.json, bit-identical): 76.4 us with try_wait, 75.5-75.9
+// with 20 / 50 / 100 ns, 76.0 with 200 ns; the same treatment of the consumers' wait for "E full" (TALFE_WS_EFULL_NS, 6
+// iterations per warp and tile) changes nothing.  0 = try_wait with the suspend-time hint.
+#ifndef TALFE_WS_EEMPTY_NS
+#define TALFE_WS_EEMPTY_NS 50
+#endif
+#ifndef TALFE_WS_EFULL_NS
+#define TALFE_WS_EFULL_NS 0
+#endif
+template <int kNs>
+__device__ __forceinline__ void mbar_wait_backoff(unsigned long long* bar, unsigned parity) {
+    if constexpr (kNs > 0) {
+        for (;;) {
+            unsigned done;
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+            if (done) break;
+            asm volatile("nanosleep.u32 %0;" ::"n"(kNs));
+        }
+    } else {
+        mbar_wait_sleep(bar, parity);
+    }
+}
+
 // Tile descriptor: written once per tile by the loader warp, read by the two compute roles (one LDS.128 + one LDS.64)
 // so that no compute warp spends instructions on tile bookkeeping.  Ring of 8: the loader is at most two tiles
 // ahead of the producers (x double buffer), the producers at most three ahead of the consumers' mel stage.
@@ -411,7 +439,7 @@ __device__ __forceinline__ void ws_producer(const KernelArgs& a, const void* tma
 #endif
         // every tile, active or not: a producer never runs more than one phase ahead of the consumers
 #if !TALFE_WS_LOADER_WAITS_E
-        if (k >= 2) mbar_wait_sleep(e_empty + buf, ((k - 2) >> 1) & 1); // consumers have loaded E[buf] of tile k-2
+        if (k >= 2) mbar_wait_backoff<TALFE_WS_EEMPTY_NS>(e_empty + buf, ((k - 2) >> 1) & 1); // consumers have loaded E[buf] of tile k-2
 #endif
         TL_MARK(warp, k, 3);
         if (active) {
@@ -623,7 +651,7 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, const void* tma
         }
         duty = duty == kWsRoleWarps / 2 - 1 ? 0 : duty + 1;
 #endif
-        mbar_wait_sleep(e_full, (k >> 1) & 1);
+        mbar_wait_backoff<TALFE_WS_EFULL_NS>(e_full, (k >> 1) & 1);
         TL_MARK(10 + warp, k, 2);
 #if TALFE_WS_CONSUMER_LOADS == 1
         // E[grp](k) is full: every producer warp has finished reading x[k & 1] -> tile k + 2 may travel into it
