@@ -136,6 +136,9 @@ struct KernelArgs {
     // dataset-level normalisation applied inside the ws kernel (talfe_job::given_stats): ONE statistics block for every row
     const double* given_stats;
     int given_norm;                // talfe_norm that selects which entries of given_stats are used
+    // packed ragged output, ws kernel: compact tile list (only tiles that hold frames of their row), built on the device
+    const int2* tile_map;          // [n_tiles_dev] (row, tile inside the row), or nullptr = the full batch x tiles_per_row grid
+    const int* n_tiles_dev;
     unsigned* timeline;            // -DTALFE_TIMELINE development builds only (nullptr otherwise)
 };
 
@@ -440,6 +443,76 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const KernelArgs a)
             double ts = 0.0, tq2 = 0.0;
             for (int w2 = 0; w2 < kWarps; ++w2) { ts += s_red[w2].x; tq2 += s_red[w2].y; }
             a.partials[blockIdx.x] = make_double2(ts, tq2);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ compact tile list
+// Packed ragged output: tiles of row r that hold frames of the row = ceil(T_r / 32), T_r from the row's own length.
+// tile_prefix_kernel (one block): exclusive prefix over the rows -> prefix[0 .. B], total -> prefix[B] and *n_tiles;
+// tile_map_kernel: compact tile t -> (row, tile inside the row) by binary search in the prefix.
+__global__ void __launch_bounds__(1024) tile_prefix_kernel(const long long* __restrict__ lens, int batch, int frame0, int frame_end, int hop,
+                                                           int nfft, int* __restrict__ prefix, int* __restrict__ n_tiles) {
+    __shared__ int s_part[1024];
+    const int per = (batch + 1023) / 1024, lo = min(batch, (int)threadIdx.x * per), hi = min(batch, lo + per);
+    auto tiles_of = [&](int r) {
+        const long long T_row = frames_of(min(lens[r], (long long)kMaxSamples), hop, nfft);
+        const long long v = min((long long)frame_end, T_row) - frame0;
+        return v > 0 ? (int)((v + kFramesPerTile - 1) / kFramesPerTile) : 0;
+    };
+    int sum = 0;
+    for (int r = lo; r < hi; ++r) sum += tiles_of(r);
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {                                            // 1 024 partial sums: a serial scan is a few microseconds
+        int run = 0;
+        for (int i = 0; i < 1024; ++i) { const int v = s_part[i]; s_part[i] = run; run += v; }
+        prefix[batch] = run;
+        *n_tiles = run;
+    }
+    __syncthreads();
+    int run = s_part[threadIdx.x];
+    for (int r = lo; r < hi; ++r) { prefix[r] = run; run += tiles_of(r); }
+}
+__global__ void __launch_bounds__(256) tile_map_kernel(const int* __restrict__ prefix, int batch, int2* __restrict__ map) {
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    if (t >= prefix[batch]) return;
+    int lo = 0, hi = batch;                                            // largest row with prefix[row] <= t
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (prefix[mid] <= t) lo = mid; else hi = mid;
+    }
+    map[t] = make_int2(lo, t - prefix[lo]);
+}
+
+// Per-row lengths with a PADDED output: the compact tile list never visits the tiles beyond a row's own frames, so their
+// zeros are written here, at streaming-store speed (block (row, y); frames from the end of the row's last tile onwards).
+__global__ void __launch_bounds__(256) zero_padding_kernel(float* __restrict__ out, long long out_row_stride, int out_layout, int n_mels,
+                                                           const long long* __restrict__ lens, int frame0, int n_frames, int hop, int nfft) {
+    const long long row = blockIdx.x;
+    const long long T_row = frames_of(min(lens[row], (long long)kMaxSamples), hop, nfft);
+    long long v = min((long long)frame0 + n_frames, T_row) - frame0;
+    if (v < 0) v = 0;
+    const long long f0 = min((long long)n_frames, (v + kFramesPerTile - 1) / kFramesPerTile * kFramesPerTile);
+    float* base = out + row * out_row_stride;
+    const long long tid = (long long)blockIdx.y * blockDim.x + threadIdx.x, nthr = (long long)gridDim.y * blockDim.x;
+    if (out_layout == TALFE_LAYOUT_TM) {
+        const long long lo = f0 * n_mels, hi = (long long)n_frames * n_mels;
+        float* p = base + lo;
+        long long n = hi - lo;
+        if (n <= 0) return;
+        const long long head = min(n, (long long)((16 - (reinterpret_cast<unsigned long long>(p) & 15ull)) & 15ull) / 4);
+        if (tid < head) p[tid] = 0.f;
+        p += head; n -= head;
+        float4* p4 = reinterpret_cast<float4*>(p);
+        const long long n4 = n / 4;
+        for (long long i = tid; i < n4; i += nthr) __stcs(p4 + i, make_float4(0.f, 0.f, 0.f, 0.f));
+        if (tid < n - 4 * n4) p[4 * n4 + tid] = 0.f;
+    } else {
+        const long long w = n_frames - f0;
+        for (long long i = tid; i < w * n_mels; i += nthr) {
+            const long long m = i / w, f = i - m * w;
+            base[m * n_frames + f0 + f] = 0.f;
         }
     }
 }
@@ -802,7 +875,7 @@ unsigned sweep_blocks(int sm_count, long long batch, long long dense_per_row) {
     return (unsigned)std::max<long long>(1, std::min<long long>(std::min(want, cap), 65535));   // rides on grid.y
 }
 
-struct WorkspaceLayout { size_t partials, colpart, scratch_stats, partials2, total; long long tiles_per_row, n_tiles; int chunks; };
+struct WorkspaceLayout { size_t partials, colpart, scratch_stats, partials2, tile_prefix, tile_map, total; long long tiles_per_row, n_tiles; int chunks; };
 
 WorkspaceLayout workspace_layout(int n_mels, long long batch, long long n_frames) {
     WorkspaceLayout w{};
@@ -818,6 +891,10 @@ WorkspaceLayout workspace_layout(int n_mels, long long batch, long long n_frames
     off += align_up((size_t)batch * TALFE_STATS_DOUBLES(n_mels) * sizeof(double), 256);
     w.partials2 = off;                                                  // first-level sums of long rows (reduce_slices_kernel)
     off += align_up((size_t)batch * kReduceSplit * sizeof(double2), 256);
+    w.tile_prefix = off;                                                // compact tile list of packed ragged calls: prefix[B + 1], count
+    off += align_up((size_t)(batch + 2) * sizeof(int), 256);
+    w.tile_map = off;
+    off += align_up((size_t)w.n_tiles * sizeof(int2), 256);
     w.total = off;
     return w;
 }
@@ -1217,6 +1294,26 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
     } else if (use_ws && plan->use_tma && a.dtype == TALFE_F32 && a.align_ok && job->row_stride < (1ll << 36))
         a.use_tma = encode_wave_map(&tmap, reinterpret_cast<const float*>(job->wave), (long long)kHop * job->frame0 - kHalf - job->origin,
                                     job->buf_len, job->row_stride, job->batch) ? 1 : 0;
+    // packed ragged output through the ws kernel: a compact tile list built on the device (rows' own tiles only)
+    static const int compact_ok = env_int("TALFE_COMPACT_TILES", 1);       // development: 0 = visit the full tile grid
+    const bool compact = compact_ok && use_ws && !use_fl && !plan->generic && a.lens;
+    if (compact) {
+        if (!a.out_offsets) {                                           // padded output: the padding frames' zeros
+            const unsigned zb = (unsigned)std::max<long long>(1, std::min<long long>(65535, (long long)plan->sm_count * 8 / job->batch));
+            zero_padding_kernel<<<dim3((unsigned)job->batch, zb), 256, 0, stream>>>(job->out, ors, job->out_layout, M, a.lens, a.frame0,
+                                                                                    a.n_frames, hop, nfft);
+            TALFE_CUDA(cudaGetLastError());
+        }
+        int* prefix = reinterpret_cast<int*>(ws + w.tile_prefix);
+        int2* map = reinterpret_cast<int2*>(ws + w.tile_map);
+        tile_prefix_kernel<<<1, 1024, 0, stream>>>(a.lens, a.batch, a.frame0, a.frame_end, hop, nfft, prefix, prefix + a.batch + 1);
+        TALFE_CUDA(cudaGetLastError());
+        tile_map_kernel<<<(unsigned)((w.n_tiles + 255) / 256), 256, 0, stream>>>(prefix, a.batch, map);
+        TALFE_CUDA(cudaGetLastError());
+        a.tile_map = map;
+        a.n_tiles_dev = prefix + a.batch + 1;
+        a.l2_prefetch = 0;
+    }
     const bool want_stats = !given && (job->stats != nullptr || job->norm != TALFE_NORM_NONE);
     const bool per_row = job->norm >= TALFE_NORM_ROW_MEAN;
     // one slot per CTA is enough for batch-wide sums — and for per-row sums of a ONE-row call (an episode of a corpus pass,
@@ -1224,6 +1321,8 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
     // to reduce afterwards) cost 10 us per hour-long episode
     const bool tile_slots = per_row && !given && job->batch > 1;
     a.partials_per_tile = tile_slots ? 1 : 0;
+    if (compact && tile_slots)                                          // tiles outside the compact list are never visited: their slots read as 0
+        TALFE_CUDA(cudaMemsetAsync(ws + w.partials, 0, (size_t)w.n_tiles * kWarps * sizeof(double2), stream));
     a.want_sumsq = (job->stats != nullptr && !given) ? 1 : 0;   // the sum of squares is only ever reported, never needed by K3
     // given statistics are applied by the ws kernel's mel stage itself; the other kernels are followed by the sweep
     const bool apply_in_kernel = given && use_ws && !use_fl && !plan->generic;

@@ -186,7 +186,7 @@ struct __align__(16) WsDesc {
     int pad;                       // tensor copy: first 320-sample row of the tile (16 * tile index in the row)
     float* out_tile;               // &out[row][t0 - frame0][0] for [.., T, 80] outputs
     const void* src;               // first sample of the tile in global memory (bulk tiles)
-    long long pad2;
+    long long pad2;                // index of the tile in the full (uncompacted) tile grid: its per-tile statistics slot
 };
 constexpr int kWsDescRing = 16;
 enum { kWsActive = 1, kWsFull = 2, kWsBulkX = 4, kWsBulkY = 8 };
@@ -216,7 +216,7 @@ __device__ __forceinline__ WsDesc ws_describe(const KernelArgs& a, int row, int 
                  (long long)(d.t0 - a.frame0) * kMaxMels;
     src_off = (long long)row * a.row_stride + b0;
     d.src = nullptr;
-    d.pad2 = 0;
+    d.pad2 = (long long)row * a.tiles_per_row + tq;                    // statistics slot of the tile: its index in the FULL tile grid
     return d;
 }
 
@@ -241,11 +241,25 @@ __device__ __forceinline__ void ws_advance(const KernelArgs& a, int& row, int& t
 #define TALFE_WS_CONSUMER_LOADS 0
 #endif
 
+// Tile index of this CTA's sequence -> (row, tile inside the row).  Packed ragged output (talfe_job::out_offsets): the
+// tile list is COMPACT — only the tiles that hold frames of their row, enumerated by tile_map_kernel — so that a batch of
+// 1 s .. 10 min utterances costs its own frames and not 64 x the longest row's worth of empty hand-offs.
+__device__ __forceinline__ void ws_tile_coords(const KernelArgs& a, const int tile, int& row, int& tq) {
+    if (a.tile_map) {
+        const int2 rq = __ldg(a.tile_map + tile);
+        row = rq.x; tq = rq.y;
+    } else {
+        row = tile / a.tiles_per_row;
+        tq = tile - row * a.tiles_per_row;
+    }
+}
+
 // Descriptor of tile kk of this CTA -> ring (all 32 lanes of ONE warp run this; nothing here touches an x buffer).
 template <typename XT>
 __device__ __forceinline__ WsDesc ws_describe_tile(const KernelArgs& a, WsDesc* s_desc, const int kk, const int lane) {
     const int tile = (int)blockIdx.x + kk * (int)gridDim.x;
-    const int row = tile / a.tiles_per_row, tq = tile - row * a.tiles_per_row;
+    int row, tq;
+    ws_tile_coords(a, tile, row, tq);
     long long src_off;
     WsDesc d = ws_describe(a, row, tq, src_off);
     d.src = reinterpret_cast<const XT*>(a.wave) + src_off;
@@ -321,7 +335,8 @@ __device__ __forceinline__ void ws_producer(const KernelArgs& a, const void* tma
     const int step = (int)gridDim.x;
     auto describe = [&](int kk) {
         const int tile = (int)blockIdx.x + kk * step;
-        const int row = tile / a.tiles_per_row, tq = tile - row * a.tiles_per_row;
+        int row, tq;
+        ws_tile_coords(a, tile, row, tq);
         long long src_off;
         WsDesc d = ws_describe(a, row, tq, src_off);
         d.src = reinterpret_cast<const XT*>(a.wave) + src_off;
@@ -378,7 +393,7 @@ __device__ __forceinline__ void ws_producer(const KernelArgs& a, const void* tma
         __syncwarp();
     };
 #if !TALFE_WS_CONSUMER_LOADS
-    if (!(kHelper && kWsHelperLoads) && warp == 0) load_duty(0);
+    if (!(kHelper && kWsHelperLoads) && warp == 0 && n_my > 0) load_duty(0);
 #endif
     for (int k = 0; k < n_my; ++k) {
         const int buf = k & 1;
@@ -696,7 +711,7 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, const void* tma
                 ds += __shfl_xor_sync(0xffffffffu, ds, o);
                 dq += __shfl_xor_sync(0xffffffffu, dq, o);
             }
-            const long long tile = (long long)blockIdx.x + (long long)k * gridDim.x;
+            const long long tile = dp->pad2;
             if (lane == 0) {                                            // 10 slots per tile: this group's 5 warps fill 5, zero the rest
                 a.partials[tile * kWsRoleWarps + (gtid >> 5)] = make_double2(ds, dq);
                 a.partials[tile * kWsRoleWarps + (gtid >> 5) + kWsRoleWarps / 2] = make_double2(0.0, 0.0);
@@ -893,7 +908,8 @@ __global__ void __launch_bounds__(ws_block_threads(kFuse), 1) logmel_ws_kernel(c
         }
         __syncthreads();
     }
-    const int n_my = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles blockIdx.x, + gridDim.x, ...
+    const int n_tiles = a.tile_map ? __ldg(a.n_tiles_dev) : a.n_tiles;   // (compact list: counted on the device by tile_prefix_kernel)
+    const int n_my = (int)blockIdx.x < n_tiles ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;   // tiles blockIdx.x, + gridDim.x, ...
     if (kHelper) {                                                       // warpgroup-uniform: warps 0..19 compute, 20..23 help
         if (tid < kWsThreads) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kWsComputeRegs));
         else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kWsHelperRegs));
