@@ -691,7 +691,12 @@ __global__ void __launch_bounds__(256) apply_stats_kernel(float* __restrict__ fe
     if (out_layout == TALFE_LAYOUT_TM && (n_mels & 3) == 0 && ((reinterpret_cast<unsigned long long>(base) & 15ull) == 0)) {
         float4* b4 = reinterpret_cast<float4*>(base);
         const int m4 = n_mels >> 2;
-        const long long n4 = total / 4, step = (long long)gridDim.y * blockDim.x;
+        // ragged rows: a row is swept by its SHARE of the grid's y extent (blocks beyond it leave), so that a 10-minute row next
+        // to 1-second rows is not left to the few blocks an even split would give it
+        const long long n4 = total / 4, n4_max = (long long)n_frames * m4;
+        const long long gy = (lens || valid_frames) ? max(1ll, ((long long)gridDim.y * n4 + n4_max - 1) / max(1ll, n4_max)) : (long long)gridDim.y;
+        if ((long long)blockIdx.y >= gy) return;
+        const long long step = gy * blockDim.x;
         long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x;
         if (!n_bands) {
             // HBM-sized sweeps (hour-long episodes, corpus passes): four independent 128-bit loads in flight per thread, and
@@ -869,9 +874,10 @@ int cuda_fail(cudaError_t e) { g_last_cuda_error = (int)e; return TALFE_ERR_CUDA
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // blocks along x for the in-place sweep: enough to fill the GPU ~8 deep across all rows
-unsigned sweep_blocks(int sm_count, long long batch, long long dense_per_row) {
+unsigned sweep_blocks(int sm_count, long long batch, long long dense_per_row, bool ragged = false) {
     long long want = (dense_per_row / 4 + 255) / 256;
     long long cap = std::max<long long>(1, (long long)sm_count * 8 / std::max<long long>(1, batch));
+    if (ragged) cap = std::max<long long>(cap, (long long)sm_count * 2);   // each row uses its share of y (apply_stats_kernel)
     return (unsigned)std::max<long long>(1, std::min<long long>(std::min(want, cap), 65535));   // rides on grid.y
 }
 
@@ -1464,7 +1470,7 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
     }
     if (job->norm == TALFE_NORM_NONE || job->defer_normalise) return TALFE_OK;
     // rows keep their zero fill beyond their own length: the sweep derives valid frames from lens
-    apply_stats_kernel<<<dim3((unsigned)job->batch, sweep_blocks(plan->sm_count, job->batch, dense)), 256, 0, stream>>>(
+    apply_stats_kernel<<<dim3((unsigned)job->batch, sweep_blocks(plan->sm_count, job->batch, dense, a.lens != nullptr)), 256, 0, stream>>>(
         job->out, job->batch, job->n_frames, ors, job->out_layout, M, job->norm, stats, nullptr, a.lens, a.frame0, a.out_offsets,
         job->freq_bands, job->time_bands, job->n_bands, hop, nfft);
     TALFE_CUDA(cudaGetLastError());
@@ -1512,7 +1518,7 @@ int talfe_apply_stats(const talfe_plan* plan, float* feats, int64_t batch, int64
     const long long dense = n_frames * M;
     const long long ors = out_row_stride ? out_row_stride : dense;
     if (ors < dense) return TALFE_ERR_INVALID;
-    apply_stats_kernel<<<dim3((unsigned)batch, sweep_blocks(plan->sm_count, batch, dense)), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+    apply_stats_kernel<<<dim3((unsigned)batch, sweep_blocks(plan->sm_count, batch, dense, valid_frames != nullptr)), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         feats, batch, n_frames, ors, out_layout, M, norm, stats, reinterpret_cast<const long long*>(valid_frames), nullptr, 0,
         nullptr, nullptr, nullptr, 0, plan->hop, plan->n_fft);
     TALFE_CUDA(cudaGetLastError());
