@@ -856,7 +856,8 @@ logmel_kernel_t kernel_for(bool ref_layout, int dtype) {
 }
 
 typedef void (*logmel_ws_kernel_t)(const KernelArgs, const CUtensorMap);
-logmel_ws_kernel_t ws_kernel_for(int dtype, bool fuse = false, bool apply = false) {
+logmel_ws_kernel_t ws_kernel_for(int dtype, bool fuse = false, bool apply = false, bool compact = false) {
+    if (compact) return dtype == TALFE_F32 ? logmel_ws_kernel<float, false, false, true> : dtype == TALFE_F16 ? logmel_ws_kernel<__half, false, false, true> : logmel_ws_kernel<short, false, false, true>;
     if (apply) return dtype == TALFE_F32 ? logmel_ws_kernel<float, false, true> : dtype == TALFE_F16 ? logmel_ws_kernel<__half, false, true> : logmel_ws_kernel<short, false, true>;
     if (fuse) return dtype == TALFE_F32 ? logmel_ws_kernel<float, true> : dtype == TALFE_F16 ? logmel_ws_kernel<__half, true> : logmel_ws_kernel<short, true>;
     return dtype == TALFE_F32 ? logmel_ws_kernel<float, false> : dtype == TALFE_F16 ? logmel_ws_kernel<__half, false> : logmel_ws_kernel<short, false>;
@@ -1123,6 +1124,7 @@ int talfe_plan_create(talfe_plan** plan_out, int device, int n_mels, const float
             e = cudaFuncSetAttribute(ws_kernel_for(dt, false), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->ws_smem);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(ws_kernel_for(dt, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->ws_smem);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(ws_kernel_for(dt, false, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->ws_smem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(ws_kernel_for(dt, false, false, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->ws_smem);
         }
     }
     if (p->fl && e == cudaSuccess) e = cudaFuncSetAttribute(logmel_fl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFlSmemBytes);
@@ -1302,7 +1304,7 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
                                     job->buf_len, job->row_stride, job->batch) ? 1 : 0;
     // packed ragged output through the ws kernel: a compact tile list built on the device (rows' own tiles only)
     static const int compact_ok = env_int("TALFE_COMPACT_TILES", 1);       // development: 0 = visit the full tile grid
-    const bool compact = compact_ok && use_ws && !use_fl && !plan->generic && a.lens;
+    const bool compact = compact_ok && use_ws && !use_fl && !plan->generic && a.lens && !given;   // (its own kernel instantiation)
     if (compact) {
         if (!a.out_offsets) {                                           // padded output: the padding frames' zeros
             const unsigned zb = (unsigned)std::max<long long>(1, std::min<long long>(65535, (long long)plan->sm_count * 8 / job->batch));
@@ -1405,7 +1407,7 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
             TALFE_CUDA(e);
             return TALFE_OK;
         } else {
-            TALFE_CUDA(cudaLaunchKernelEx(&cfg, ws_kernel_for(a.dtype, false, apply_in_kernel), (const KernelArgs)a, (const CUtensorMap)tmap));
+            TALFE_CUDA(cudaLaunchKernelEx(&cfg, ws_kernel_for(a.dtype, false, apply_in_kernel, compact), (const KernelArgs)a, (const CUtensorMap)tmap));
         }
     }
     if (given) {

@@ -186,7 +186,7 @@ struct __align__(16) WsDesc {
     int pad;                       // tensor copy: first 320-sample row of the tile (16 * tile index in the row)
     float* out_tile;               // &out[row][t0 - frame0][0] for [.., T, 80] outputs
     const void* src;               // first sample of the tile in global memory (bulk tiles)
-    long long pad2;                // index of the tile in the full (uncompacted) tile grid: its per-tile statistics slot
+    long long pad2;
 };
 constexpr int kWsDescRing = 16;
 enum { kWsActive = 1, kWsFull = 2, kWsBulkX = 4, kWsBulkY = 8 };
@@ -216,7 +216,7 @@ __device__ __forceinline__ WsDesc ws_describe(const KernelArgs& a, int row, int 
                  (long long)(d.t0 - a.frame0) * kMaxMels;
     src_off = (long long)row * a.row_stride + b0;
     d.src = nullptr;
-    d.pad2 = (long long)row * a.tiles_per_row + tq;                    // statistics slot of the tile: its index in the FULL tile grid
+    d.pad2 = 0;
     return d;
 }
 
@@ -244,8 +244,9 @@ __device__ __forceinline__ void ws_advance(const KernelArgs& a, int& row, int& t
 // Tile index of this CTA's sequence -> (row, tile inside the row).  Packed ragged output (talfe_job::out_offsets): the
 // tile list is COMPACT — only the tiles that hold frames of their row, enumerated by tile_map_kernel — so that a batch of
 // 1 s .. 10 min utterances costs its own frames and not 64 x the longest row's worth of empty hand-offs.
+template <bool kCompact>
 __device__ __forceinline__ void ws_tile_coords(const KernelArgs& a, const int tile, int& row, int& tq) {
-    if (a.tile_map) {
+    if (kCompact) {
         const int2 rq = __ldg(a.tile_map + tile);
         row = rq.x; tq = rq.y;
     } else {
@@ -255,11 +256,11 @@ __device__ __forceinline__ void ws_tile_coords(const KernelArgs& a, const int ti
 }
 
 // Descriptor of tile kk of this CTA -> ring (all 32 lanes of ONE warp run this; nothing here touches an x buffer).
-template <typename XT>
+template <typename XT, bool kCompact = false>
 __device__ __forceinline__ WsDesc ws_describe_tile(const KernelArgs& a, WsDesc* s_desc, const int kk, const int lane) {
     const int tile = (int)blockIdx.x + kk * (int)gridDim.x;
     int row, tq;
-    ws_tile_coords(a, tile, row, tq);
+    ws_tile_coords<kCompact>(a, tile, row, tq);
     long long src_off;
     WsDesc d = ws_describe(a, row, tq, src_off);
     d.src = reinterpret_cast<const XT*>(a.wave) + src_off;
@@ -307,7 +308,7 @@ __device__ __forceinline__ void ws_load_tile(const KernelArgs& a, const void* tm
 // (ONE group of 10 warps, one frame pair per thread.  Splitting the producers into two groups on alternate tiles like
 // the consumers — two pairs per thread, x[q] / E[q] per group — measured 91.7 us against 80.2 us: each group then holds
 // its exchange buffer for two pairs' worth of work and the consumers wait for it.)
-template <typename XT, bool kHelper>
+template <typename XT, bool kHelper, bool kCompact>
 __device__ __forceinline__ void ws_producer(const KernelArgs& a, const void* tmap, unsigned char* smem, XT* s_x0, cf* s_e0, WsDesc* s_desc,
                                             unsigned long long* s_bar, const int tid, const int n_my) {
     unsigned long long* x_full = s_bar;            // [2]
@@ -336,7 +337,7 @@ __device__ __forceinline__ void ws_producer(const KernelArgs& a, const void* tma
     auto describe = [&](int kk) {
         const int tile = (int)blockIdx.x + kk * step;
         int row, tq;
-        ws_tile_coords(a, tile, row, tq);
+        ws_tile_coords<kCompact>(a, tile, row, tq);
         long long src_off;
         WsDesc d = ws_describe(a, row, tq, src_off);
         d.src = reinterpret_cast<const XT*>(a.wave) + src_off;
@@ -393,7 +394,7 @@ __device__ __forceinline__ void ws_producer(const KernelArgs& a, const void* tma
         __syncwarp();
     };
 #if !TALFE_WS_CONSUMER_LOADS
-    if (!(kHelper && kWsHelperLoads) && warp == 0 && n_my > 0) load_duty(0);
+    if (!(kHelper && kWsHelperLoads) && warp == 0 && (!kCompact || n_my > 0)) load_duty(0);
 #endif
     for (int k = 0; k < n_my; ++k) {
         const int buf = k & 1;
@@ -711,7 +712,8 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, const void* tma
                 ds += __shfl_xor_sync(0xffffffffu, ds, o);
                 dq += __shfl_xor_sync(0xffffffffu, dq, o);
             }
-            const long long tile = dp->pad2;
+            // the tile's statistics slot = its index in the FULL tile grid (the tile list may be compact: tile_map_kernel)
+            const long long tile = (long long)dp->row * a.tiles_per_row + (dp->t0 - a.frame0) / kWsFrames;
             if (lane == 0) {                                            // 10 slots per tile: this group's 5 warps fill 5, zero the rest
                 a.partials[tile * kWsRoleWarps + (gtid >> 5)] = make_double2(ds, dq);
                 a.partials[tile * kWsRoleWarps + (gtid >> 5) + kWsRoleWarps / 2] = make_double2(0.0, 0.0);
@@ -864,7 +866,7 @@ __device__ __noinline__ void ws_fused_batch_mean(const WsNormArgs a, unsigned ch
 
 __host__ __device__ constexpr size_t ws_x_offset(size_t table_bytes) { return (table_bytes + 127) & ~(size_t)127; }
 
-template <typename XT, bool kFuse, bool kApply = false>
+template <typename XT, bool kFuse, bool kApply = false, bool kCompact = false>
 __global__ void __launch_bounds__(ws_block_threads(kFuse), 1) logmel_ws_kernel(const KernelArgs a, const __grid_constant__ CUtensorMap tmap) {
     constexpr bool kHelper = TALFE_WS_HELPER && !kFuse;
     constexpr int kNT = ws_block_threads(kFuse);
@@ -908,13 +910,13 @@ __global__ void __launch_bounds__(ws_block_threads(kFuse), 1) logmel_ws_kernel(c
         }
         __syncthreads();
     }
-    const int n_tiles = a.tile_map ? __ldg(a.n_tiles_dev) : a.n_tiles;   // (compact list: counted on the device by tile_prefix_kernel)
-    const int n_my = (int)blockIdx.x < n_tiles ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;   // tiles blockIdx.x, + gridDim.x, ...
+    const int n_tiles = kCompact ? __ldg(a.n_tiles_dev) : a.n_tiles;     // (compact list: counted on the device by tile_prefix_kernel)
+    const int n_my = (!kCompact || (int)blockIdx.x < n_tiles) ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;   // tiles blockIdx.x, + gridDim.x, ...
     if (kHelper) {                                                       // warpgroup-uniform: warps 0..19 compute, 20..23 help
         if (tid < kWsThreads) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kWsComputeRegs));
         else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kWsHelperRegs));
     }
-    if (tid < kWsProdThreads) ws_producer<XT, kHelper>(a, &tmap, smem, s_x0, s_e0, s_desc, s_bar, tid, n_my);
+    if (tid < kWsProdThreads) ws_producer<XT, kHelper, kCompact>(a, &tmap, smem, s_x0, s_e0, s_desc, s_bar, tid, n_my);
     else if (tid < kWsThreads) ws_consumer<XT, kHelper, kApply>(a, &tmap, smem, s_x0, s_e0, s_p0, s_y0, s_desc, s_bar, s_norm, tid - kWsProdThreads, n_my);
     else if (kHelper) ws_helper<XT>(a, &tmap, s_x0, s_y0, s_desc, s_bar, tid - kWsThreads, n_my);
     if (kFuse) {                                                       // the exchange buffers are free now: scratch for the reduction
