@@ -339,3 +339,27 @@ def test_given_statistics_generic_geometry(dev):
     want = m.features(x, norm="none")
     m.apply_stats(want, block.expand(3, -1).contiguous(), norm="row_mel_var")
     assert torch.equal(m.features(x, norm="row_mel_var", given_stats=block), want)
+
+
+def test_compact_tile_list_edge_cases(dev):
+    """Ragged calls through the compact tile list (ws kernel) against the legacy kernel, which visits the full tile grid:
+    rows without a single frame (length <= 200), rows that end inside a tile, one row that fills the whole buffer, a
+    batch whose first / last rows are empty, padded and [B, 80, T] outputs, un-normalised (bitwise) and per-row CMVN."""
+    ws, legacy = _module(dev, TALFE_KERNEL="ws"), _module(dev, TALFE_KERNEL="legacy")
+    x = _fill(dev, 7, 16000 * 6 + 55, episode=31)
+    L = x.shape[1]
+    for lens in ([100, L, 5120 + 200, 0, 201, 32 * 160 * 3, 150], [L] * 7, [200, 200, 200, 200, 200, 200, 4000]):
+        al = torch.tensor(lens, device=dev)
+        for layout in ("tm", "mt"):
+            a = ws.features(x, audio_lens=al, norm="none", layout=layout)
+            b = legacy.features(x, audio_lens=al, norm="none", layout=layout)
+            assert torch.isfinite(a).all() and torch.equal(a, b), (lens, layout)
+            a = ws.features(x, audio_lens=al, norm="row_mel", layout=layout)
+            b = legacy.features(x, audio_lens=al, norm="row_mel", layout=layout)
+            assert torch.isfinite(a).all() and float((a - b).abs().max()) < 1e-5, (lens, layout)
+    # the output buffer is reused: padding frames of a short row must be re-zeroed by the call itself
+    out = torch.full((7, 1 + L // 160, 80), 7.0, device=dev)
+    al = torch.tensor([16000, 100, L, 3000, 9000, 201, 48000], device=dev)
+    ws.features(x, audio_lens=al, norm="none", out=out)
+    want = legacy.features(x, audio_lens=al, norm="none")
+    assert torch.equal(out, want)
