@@ -647,7 +647,8 @@ def other_configs(mod, lib, _lib, dev):
     c2 = {"frames": T}
     c2["one_shot_ms"] = timeit(lambda: mod(ep[None]), 5)
     c2["streamed_device_resident_ms"] = timeit(lambda: stream_episode(mod, ep), 3)
-    c2["streamed_device_resident_30s_chunks_ms"] = timeit(lambda: stream_episode(mod, ep, 30.0), 3)
+    c2["streamed_device_resident_30s_chunks_ms"] = timeit(lambda: stream_episode(mod, ep, 30.0), 3)   # (coalesced: nothing to stage on the device)
+    c2["streamed_device_resident_30s_chunks_uncoalesced_ms"] = timeit(lambda: stream_episode(mod, ep, 30.0, coalesce_on_device=False), 3)
     eph = ep.cpu().pin_memory()
     c2["streamed_from_pinned_host_ms"] = timeit(lambda: stream_episode(mod, eph, device=dev), 3)
     pcm = (eph * 32768.0).round().to(torch.int16).pin_memory()

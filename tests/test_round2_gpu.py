@@ -67,8 +67,8 @@ def test_tensor_copy_tiles_are_bitwise_the_bulk_copy_path(dev):
     assert torch.equal(tma.features(view, norm="none"), bulk.features(view, norm="none"))
     from tal_asrd_b200.streaming import stream_episode
     ep = _fill(dev, 1, 16000 * 95, episode=6)[0]
-    a = stream_episode(tma, ep, chunk_seconds=13.0)
-    b = stream_episode(bulk, ep, chunk_seconds=13.0)
+    a = stream_episode(tma, ep, chunk_seconds=13.0, coalesce_on_device=False)
+    b = stream_episode(bulk, ep, chunk_seconds=13.0, coalesce_on_device=False)
     assert torch.equal(a, b)
     y64 = O.logmel_unnormalised_f64(ep[None].cpu().numpy())
     y64 = y64 - y64.mean()
@@ -234,7 +234,7 @@ def test_hour_long_episode_streamed_windows_against_the_oracle(dev):
     ep = _fill(dev, 1, L, episode=42)[0]
     host = ep.cpu().pin_memory()
     raw = stream_episode(mod, host, device=dev, normalise=False)           # from pinned host memory, default chunks
-    raw30 = stream_episode(mod, ep, 30.0, normalise=False)                 # device resident, 120 chunks
+    raw30 = stream_episode(mod, ep, 30.0, normalise=False, coalesce_on_device=False)                 # device resident, 120 chunks
     one = mod.features(ep[None], norm="none")
     # chunking never changes a bit of any frame that has its pair partner; the episode's LAST frame (T is odd) shares its
     # packed rows 18 / 19 with a partner frame that does not exist, whose (discarded) samples differ between the paths:

@@ -113,8 +113,14 @@ def test_streamed_episode_equals_one_shot():
         torch.cuda.synchronize()
         assert got.shape == one.shape
         assert float((got - one).abs().max()) < 2e-5, chunk_s            # only the summation order of the mean differs
-    got = stream_episode(mod, ep.to(dev), chunk_seconds=11.0)               # device-resident episode
+    got = stream_episode(mod, ep.to(dev), chunk_seconds=11.0, coalesce_on_device=False)               # device-resident episode
     assert float((got - one).abs().max()) < 2e-5
+    # device-resident episodes have nothing to stage: by default their chunks are coalesced (here: one launch); the
+    # un-normalised features do not depend on the chunking at all
+    raw_small = stream_episode(mod, ep.to(dev), chunk_seconds=11.0, normalise=False, coalesce_on_device=False)
+    raw_coalesced = stream_episode(mod, ep.to(dev), chunk_seconds=11.0, normalise=False)
+    assert torch.equal(raw_small, raw_coalesced)
+    assert torch.equal(stream_episode(mod, ep.to(dev), chunk_seconds=11.0), one)
     ref = O.logmel_f64(ep[None, :160 * 300].numpy())                         # oracle on a prefix (interior frames agree up to the mean)
     d = got[0, :250].cpu().numpy() - ref[0, :250]
     assert np.abs(d - d.mean()).max() < 1e-4
@@ -135,7 +141,7 @@ def test_hour_long_episode_streams():
     ep = torch.empty(L, device=dev)
     _lib.check(_lib.load().talfe_synth_fill(ep.data_ptr(), _lib.F32, 1, L, L, 2020, 1234, 0, None))
     one = mod(ep[None])
-    got = stream_episode(mod, ep, chunk_seconds=30.0)
+    got = stream_episode(mod, ep, chunk_seconds=30.0, coalesce_on_device=False)
     torch.cuda.synchronize()
     assert got.shape == (1, 360001, 80)
     assert float((got - one).abs().max()) < 2e-5
