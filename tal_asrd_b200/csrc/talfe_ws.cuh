@@ -103,8 +103,20 @@ __device__ __forceinline__ void mbar_arrive_counted(unsigned long long* bar, uns
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// -DTALFE_WS_STORE_HINT=1 (experiment): feature stores carry an L2 evict_last hint so that the whole output stays in L2 for
+// the normalisation sweep that follows (ncu: ~10 of the 61.5 MB have gone to DRAM by the end of K1).  Measured, no gain:
+// K1 76.1 against 75.7 us, forward 89.2 against 89.1 us.
+#ifndef TALFE_WS_STORE_HINT
+#define TALFE_WS_STORE_HINT 0
+#endif
 __device__ __forceinline__ void bulk_s2g(void* gmem_dst, unsigned smem_src, unsigned bytes) {
+#if TALFE_WS_STORE_HINT
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gmem_dst), "r"(smem_src), "r"(bytes), "l"(pol) : "memory");
+#else
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_src), "r"(bytes) : "memory");
+#endif
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
