@@ -341,7 +341,7 @@ def run_ours(args):
         host_in[i].copy_(waves[i].cpu())
     host_pcm = [(h * 32768.0).round().clamp_(-32768, 32767).to(torch.int16).pin_memory() for h in host_in]
     host_out = [torch.empty(BATCH, N_FRAMES, N_MELS, dtype=torch.float32).pin_memory() for _ in range(2)]
-    e2e_steps = max(3, min(args.steps, 50))            # (ramp-up and drain of the pipeline amortise over the run: tools/e2e_depth.py)
+    e2e_steps = min(50, max(30, args.steps))          # (ramp-up and drain of the pipeline amortise over the run: tools/e2e_depth.py)
 
     def timed_pipeline(inputs):
         pipe = HostPipeline(mod, dev, depth=2)
