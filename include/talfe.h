@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TALFE_VERSION 104 /* major * 100 + minor */
+#define TALFE_VERSION 105 /* major * 100 + minor */
 
 typedef enum talfe_status {
     TALFE_OK = 0,
@@ -110,6 +110,11 @@ typedef struct talfe_job {
                              /*   the transform kernel itself, no sweep over the features (values identical to       */
                              /*   norm = NONE followed by talfe_apply_stats with that block).  Requires norm != NONE,*/
                              /*   n_bands == 0, defer_normalise == 0; `stats` is not written.                        */
+    int32_t lens_are_padding_hint; /* nonzero (with `lens`): the rows keep the REFERENCE semantics (every row has the frames   */
+                             /*   of total_len, reflection at the padded end, padding frames count in the mean) and lens[r]   */
+                             /*   is the caller's guarantee that row r is zero from sample lens[r] on (what the collaters     */
+                             /*   produce, tal/asr/data/aligned.py:246-270): frames that cannot see a sample below lens[r]    */
+                             /*   are the constant log(eps) and are filled, not computed.  norm NONE / BATCH_MEAN only.       */
 } talfe_job;
 
 int talfe_version(void);

@@ -13,7 +13,7 @@ NORM_NONE, NORM_BATCH_MEAN, NORM_ROW_MEAN, NORM_ROW_MEL_MEAN, NORM_ROW_MEL_MEANV
 LAYOUT_TM, LAYOUT_MT = 0, 1
 ERR_TOO_SHORT = -2
 
-EXPECTED_VERSION = 104     # TALFE_VERSION of include/talfe.h this binding was written against
+EXPECTED_VERSION = 105     # TALFE_VERSION of include/talfe.h this binding was written against
 
 EXPORTED = [
     "talfe_version", "talfe_job_size", "talfe_probe_fp32_fma_rate", "talfe_launches_per_forward",
@@ -35,7 +35,7 @@ class Job(ctypes.Structure):
         ("eps", c_float), ("defer_normalise", c_int32), ("stats", c_void_p),
         ("workspace", c_void_p), ("workspace_bytes", c_size_t), ("stream", c_void_p),
         ("out_offsets", c_void_p), ("freq_bands", c_void_p), ("time_bands", c_void_p), ("n_bands", c_int32),
-        ("given_stats", c_void_p),
+        ("given_stats", c_void_p), ("lens_are_padding_hint", c_int32),
     ]
 
 

@@ -451,14 +451,28 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const KernelArgs a)
 // Packed ragged output: tiles of row r that hold frames of the row = ceil(T_r / 32), T_r from the row's own length.
 // tile_prefix_kernel (one block): exclusive prefix over the rows -> prefix[0 .. B], total -> prefix[B] and *n_tiles;
 // tile_map_kernel: compact tile t -> (row, tile inside the row) by binary search in the prefix.
+// Frames of [frame0, frame_end) that row r's tiles must COMPUTE.  Per-row semantics: the row's own frames.  Padding hint
+// (talfe_job::lens_are_padding_hint: reference semantics, the caller guarantees zeros beyond lens[r]): the frames whose
+// window can see a sample below lens[r] — frame t sees samples [hop t - half, hop t - half + n_fft), and the reflection
+// at the end of the PADDED row brings samples of its last n_fft / 2 back in, so a row that ends within n_fft of the padded
+// length counts as full.  Every other frame is the constant log(eps).
+__device__ __forceinline__ long long frames_to_compute(long long len, int hint, long long total_len, int frame0, int frame_end, int hop, int nfft) {
+    len = min(len, (long long)kMaxSamples);
+    long long t_row;
+    if (!hint) t_row = frames_of(len, hop, nfft);
+    else if (len <= 0) t_row = 0;
+    else if (len + nfft + 2 >= total_len) t_row = frame_end;
+    else t_row = (len + nfft / 2 + hop - 1) / hop;
+    const long long v = min((long long)frame_end, t_row) - frame0;
+    return v > 0 ? v : 0;
+}
 __global__ void __launch_bounds__(1024) tile_prefix_kernel(const long long* __restrict__ lens, int batch, int frame0, int frame_end, int hop,
-                                                           int nfft, int* __restrict__ prefix, int* __restrict__ n_tiles) {
+                                                           int nfft, int* __restrict__ prefix, int* __restrict__ n_tiles, int hint, long long total_len) {
     __shared__ int s_part[1024];
     const int per = (batch + 1023) / 1024, lo = min(batch, (int)threadIdx.x * per), hi = min(batch, lo + per);
     auto tiles_of = [&](int r) {
-        const long long T_row = frames_of(min(lens[r], (long long)kMaxSamples), hop, nfft);
-        const long long v = min((long long)frame_end, T_row) - frame0;
-        return v > 0 ? (int)((v + kFramesPerTile - 1) / kFramesPerTile) : 0;
+        const long long v = frames_to_compute(lens[r], hint, total_len, frame0, frame_end, hop, nfft);
+        return (int)((v + kFramesPerTile - 1) / kFramesPerTile);
     };
     int sum = 0;
     for (int r = lo; r < hi; ++r) sum += tiles_of(r);
@@ -487,13 +501,16 @@ __global__ void __launch_bounds__(256) tile_map_kernel(const int* __restrict__ p
 
 // Per-row lengths with a PADDED output: the compact tile list never visits the tiles beyond a row's own frames, so their
 // zeros are written here, at streaming-store speed (block (row, y); frames from the end of the row's last tile onwards).
+// (padding hint: the frames no tile computes are the constant log(eps) — the kernel's own expression for an all-zero frame —
+// and const_frames[row] tells the mean how many of them there are)
 __global__ void __launch_bounds__(256) zero_padding_kernel(float* __restrict__ out, long long out_row_stride, int out_layout, int n_mels,
-                                                           const long long* __restrict__ lens, int frame0, int n_frames, int hop, int nfft) {
+                                                           const long long* __restrict__ lens, int frame0, int n_frames, int hop, int nfft,
+                                                           int hint, long long total_len, float eps, long long* __restrict__ const_frames) {
     const long long row = blockIdx.x;
-    const long long T_row = frames_of(min(lens[row], (long long)kMaxSamples), hop, nfft);
-    long long v = min((long long)frame0 + n_frames, T_row) - frame0;
-    if (v < 0) v = 0;
+    const long long v = frames_to_compute(lens[row], hint, total_len, frame0, frame0 + n_frames, hop, nfft);
     const long long f0 = min((long long)n_frames, (v + kFramesPerTile - 1) / kFramesPerTile * kFramesPerTile);
+    const float fill = hint ? fast_log(0.f + eps) : 0.f;
+    if (const_frames && blockIdx.y == 0 && threadIdx.x == 0) const_frames[row] = n_frames - f0;
     float* base = out + row * out_row_stride;
     const long long tid = (long long)blockIdx.y * blockDim.x + threadIdx.x, nthr = (long long)gridDim.y * blockDim.x;
     if (out_layout == TALFE_LAYOUT_TM) {
@@ -502,18 +519,90 @@ __global__ void __launch_bounds__(256) zero_padding_kernel(float* __restrict__ o
         long long n = hi - lo;
         if (n <= 0) return;
         const long long head = min(n, (long long)((16 - (reinterpret_cast<unsigned long long>(p) & 15ull)) & 15ull) / 4);
-        if (tid < head) p[tid] = 0.f;
+        if (tid < head) p[tid] = fill;
         p += head; n -= head;
         float4* p4 = reinterpret_cast<float4*>(p);
         const long long n4 = n / 4;
-        for (long long i = tid; i < n4; i += nthr) __stcs(p4 + i, make_float4(0.f, 0.f, 0.f, 0.f));
-        if (tid < n - 4 * n4) p[4 * n4 + tid] = 0.f;
+        for (long long i = tid; i < n4; i += nthr) __stcs(p4 + i, make_float4(fill, fill, fill, fill));
+        if (tid < n - 4 * n4) p[4 * n4 + tid] = fill;
     } else {
         const long long w = n_frames - f0;
         for (long long i = tid; i < w * n_mels; i += nthr) {
             const long long m = i / w, f = i - m * w;
-            base[m * n_frames + f0 + f] = 0.f;
+            base[m * n_frames + f0 + f] = fill;
         }
+    }
+}
+// Padding hint with the batch-mean normalisation: the padding frames are written ONCE, already normalised.  Block (row, y):
+// the scalar mean from the per-CTA partials + the constant frames' slot (fixed order), then x - mean over the frames the
+// tiles computed and log(eps) - mean over the rest of the row (the same two values "fill, then sweep" would leave).
+__global__ void __launch_bounds__(256) hint_count_kernel(const long long* __restrict__ lens, int batch, int frame0, int n_frames, int hop, int nfft,
+                                                         long long total_len, long long* __restrict__ const_frames) {
+    const int r = blockIdx.x * 256 + threadIdx.x;
+    if (r >= batch) return;
+    const long long v = frames_to_compute(lens[r], 1, total_len, frame0, frame0 + n_frames, hop, nfft);
+    const_frames[r] = n_frames - min((long long)n_frames, (v + kFramesPerTile - 1) / kFramesPerTile * kFramesPerTile);
+}
+__global__ void __launch_bounds__(256) hint_finish_kernel(float* __restrict__ out, long long out_row_stride, int out_layout, int n_mels,
+                                                          const long long* __restrict__ const_frames, int n_frames, float eps,
+                                                          const double2* __restrict__ partials, int n_partials, double count,
+                                                          double* __restrict__ stats_out) {
+    __shared__ double s_a[256], s_b[256];
+    double ra = 0.0, rb = 0.0;
+    for (int i = threadIdx.x; i < n_partials; i += 256) { const double2 v = partials[i]; ra += v.x; rb += v.y; }
+    s_a[threadIdx.x] = ra; s_b[threadIdx.x] = rb;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) { s_a[threadIdx.x] += s_a[threadIdx.x + o]; s_b[threadIdx.x] += s_b[threadIdx.x + o]; }
+        __syncthreads();
+    }
+    const float mean = count > 0.0 ? (float)(s_a[0] / count) : 0.f;
+    if (stats_out && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) { stats_out[0] = count; stats_out[1] = s_a[0]; stats_out[2] = s_b[0]; }
+    const float cm = fast_log(0.f + eps) - mean;
+    const long long row = blockIdx.x;
+    const long long f0 = n_frames - const_frames[row];                  // frames [0, f0) were computed, [f0, n_frames) are constant
+    float* base = out + row * out_row_stride;
+    const long long tid = (long long)blockIdx.y * blockDim.x + threadIdx.x, nthr = (long long)gridDim.y * blockDim.x;
+    if (out_layout == TALFE_LAYOUT_TM && (n_mels & 3) == 0 && (reinterpret_cast<unsigned long long>(base) & 15ull) == 0) {
+        float4* b4 = reinterpret_cast<float4*>(base);
+        const long long n4 = (long long)n_frames * n_mels / 4, c4 = f0 * n_mels / 4;   // f0 is a multiple of 32 frames (or n_frames)
+        const float4 fill = make_float4(cm, cm, cm, cm);
+        for (long long i = tid; i < n4; i += nthr) {
+            if (i < c4) {
+                float4 v = b4[i];
+                v.x -= mean; v.y -= mean; v.z -= mean; v.w -= mean;
+                b4[i] = v;
+            } else {
+                __stcs(b4 + i, fill);
+            }
+        }
+    } else if (out_layout == TALFE_LAYOUT_TM) {
+        const long long n = (long long)n_frames * n_mels, c = f0 * n_mels;
+        for (long long i = tid; i < n; i += nthr) base[i] = i < c ? base[i] - mean : cm;
+    } else {
+        const long long n = (long long)n_frames * n_mels;
+        for (long long i = tid; i < n; i += nthr) {
+            const long long f = i % n_frames;
+            base[i] = f < f0 ? base[i] - mean : cm;
+        }
+    }
+}
+// The constant frames' contribution to the batch sums, as one more partial slot: integer frame count (exact, any order) x
+// n_mels x c in double.
+__global__ void __launch_bounds__(256) const_partial_kernel(const long long* __restrict__ const_frames, int batch, int n_mels, float eps,
+                                                            double2* __restrict__ slot) {
+    __shared__ long long s_n[256];
+    long long n = 0;
+    for (int r = threadIdx.x; r < batch; r += 256) n += const_frames[r];
+    s_n[threadIdx.x] = n;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) s_n[threadIdx.x] += s_n[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const double c = (double)fast_log(0.f + eps), cnt = (double)s_n[0] * n_mels;
+        *slot = make_double2(cnt * c, cnt * c * c);
     }
 }
 
@@ -882,7 +971,7 @@ unsigned sweep_blocks(int sm_count, long long batch, long long dense_per_row, bo
     return (unsigned)std::max<long long>(1, std::min<long long>(std::min(want, cap), 65535));   // rides on grid.y
 }
 
-struct WorkspaceLayout { size_t partials, colpart, scratch_stats, partials2, tile_prefix, tile_map, total; long long tiles_per_row, n_tiles; int chunks; };
+struct WorkspaceLayout { size_t partials, colpart, scratch_stats, partials2, tile_prefix, tile_map, const_frames, total; long long tiles_per_row, n_tiles; int chunks; };
 
 WorkspaceLayout workspace_layout(int n_mels, long long batch, long long n_frames) {
     WorkspaceLayout w{};
@@ -902,6 +991,8 @@ WorkspaceLayout workspace_layout(int n_mels, long long batch, long long n_frames
     off += align_up((size_t)(batch + 2) * sizeof(int), 256);
     w.tile_map = off;
     off += align_up((size_t)w.n_tiles * sizeof(int2), 256);
+    w.const_frames = off;                                               // padding hint: frames per row that are the constant log(eps)
+    off += align_up((size_t)batch * sizeof(long long), 256);
     w.total = off;
     return w;
 }
@@ -1232,7 +1323,7 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
     if (job->row_stride < job->buf_len) return TALFE_ERR_INVALID;
     if (!(job->eps >= 1.1754944e-38f)) return TALFE_ERR_UNSUPPORTED;    // the log is the bare MUFU.LG2 (subnormals flush): eps keeps its argument normal
     const int hop = plan->hop, nfft = plan->n_fft, half = nfft / 2;    // 160 / 400 / 200 unless the plan is a generic one
-    if (!job->lens) {
+    if (!job->lens || job->lens_are_padding_hint) {
         if (job->total_len <= half) return TALFE_ERR_TOO_SHORT;
         if (job->frame0 + job->n_frames > frames_of(job->total_len, hop, nfft)) return TALFE_ERR_INVALID;
     }
@@ -1244,6 +1335,11 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
     if (job->n_bands < 0 || job->n_bands > kMaxBands) return TALFE_ERR_INVALID;
     if (job->n_bands > 0 && (!job->freq_bands || !job->time_bands || job->norm == TALFE_NORM_NONE || job->defer_normalise))
         return TALFE_ERR_INVALID;                          // the masks ride on the normalisation sweep
+    // lens as a PADDING HINT: reference (padded) semantics, rows guaranteed zero beyond lens[r]; scalar normalisations only
+    const bool hint = job->lens_are_padding_hint != 0 && job->lens != nullptr;
+    if (hint && (job->out_offsets || job->norm > TALFE_NORM_BATCH_MEAN || job->n_bands > 0 || job->given_stats || job->defer_normalise ||
+                 (job->accumulate_stats && job->stats)))
+        return TALFE_ERR_INVALID;
     const bool given = job->given_stats != nullptr;        // normalise with the caller's statistics block (dataset-level CMVN)
     if (given && (job->norm == TALFE_NORM_NONE || job->n_bands > 0 || job->defer_normalise)) return TALFE_ERR_INVALID;
     const WorkspaceLayout w = workspace_layout(M, job->batch, job->n_frames);
@@ -1258,7 +1354,7 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
         job->frame0 + job->n_frames > kMaxSamples / hop || job->batch > 0x7fffffffLL)
         return TALFE_ERR_UNSUPPORTED;                         // ~37 h of 16 kHz audio per row: stream it in chunks instead
     a.batch = (int)job->batch; a.row_stride = job->row_stride; a.buf_len = (int)job->buf_len; a.origin = (int)job->origin;
-    a.total_len = (int)job->total_len; a.lens = reinterpret_cast<const long long*>(job->lens);
+    a.total_len = (int)job->total_len; a.lens = job->lens_are_padding_hint ? nullptr : reinterpret_cast<const long long*>(job->lens);
     a.frame0 = (int)job->frame0; a.n_frames = (int)job->n_frames; a.frame_end = a.frame0 + a.n_frames;
     a.t_end_const = (int)std::min<long long>(a.frame_end, frames_of(job->total_len, hop, nfft));
     {
@@ -1304,17 +1400,31 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
                                     job->buf_len, job->row_stride, job->batch) ? 1 : 0;
     // packed ragged output through the ws kernel: a compact tile list built on the device (rows' own tiles only)
     static const int compact_ok = env_int("TALFE_COMPACT_TILES", 1);       // development: 0 = visit the full tile grid
-    const bool compact = compact_ok && use_ws && !use_fl && !plan->generic && a.lens && !given;   // (its own kernel instantiation)
+    const bool compact = compact_ok && use_ws && !use_fl && !plan->generic && (a.lens || hint) && !given;   // (its own kernel instantiation)
+    const bool hint_sum = compact && hint && job->norm == TALFE_NORM_BATCH_MEAN;       // the constant frames' share of the batch mean
     if (compact) {
-        if (!a.out_offsets) {                                           // padded output: the padding frames' zeros
+        const long long* lens_dev = reinterpret_cast<const long long*>(job->lens);
+        if (!a.out_offsets) {                                           // padded output: the frames no tile computes (zeros / log(eps))
             const unsigned zb = (unsigned)std::max<long long>(1, std::min<long long>(65535, (long long)plan->sm_count * 8 / job->batch));
-            zero_padding_kernel<<<dim3((unsigned)job->batch, zb), 256, 0, stream>>>(job->out, ors, job->out_layout, M, a.lens, a.frame0,
-                                                                                    a.n_frames, hop, nfft);
+            long long* const_frames = reinterpret_cast<long long*>(ws + w.const_frames);
+            if (hint_sum)                                               // the padding is written once, normalised, after the transform
+                hint_count_kernel<<<(unsigned)((job->batch + 255) / 256), 256, 0, stream>>>(lens_dev, a.batch, a.frame0, a.n_frames, hop, nfft,
+                                                                                            job->total_len, const_frames);
+            else
+                zero_padding_kernel<<<dim3((unsigned)job->batch, zb), 256, 0, stream>>>(job->out, ors, job->out_layout, M, lens_dev, a.frame0,
+                                                                                        a.n_frames, hop, nfft, hint ? 1 : 0, job->total_len, job->eps,
+                                                                                        nullptr);
             TALFE_CUDA(cudaGetLastError());
+            if (hint_sum) {                                             // one more partial slot behind the per-CTA ones
+                const_partial_kernel<<<1, 256, 0, stream>>>(const_frames, a.batch, M, job->eps,
+                                                            reinterpret_cast<double2*>(ws + w.partials) + grid);
+                TALFE_CUDA(cudaGetLastError());
+            }
         }
         int* prefix = reinterpret_cast<int*>(ws + w.tile_prefix);
         int2* map = reinterpret_cast<int2*>(ws + w.tile_map);
-        tile_prefix_kernel<<<1, 1024, 0, stream>>>(a.lens, a.batch, a.frame0, a.frame_end, hop, nfft, prefix, prefix + a.batch + 1);
+        tile_prefix_kernel<<<1, 1024, 0, stream>>>(lens_dev, a.batch, a.frame0, a.frame_end, hop, nfft, prefix, prefix + a.batch + 1, hint ? 1 : 0,
+                                                   job->total_len);
         TALFE_CUDA(cudaGetLastError());
         tile_map_kernel<<<(unsigned)((w.n_tiles + 255) / 256), 256, 0, stream>>>(prefix, a.batch, map);
         TALFE_CUDA(cudaGetLastError());
@@ -1348,7 +1458,7 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
     // from Python the two-launch path is ahead as well once the host is warm (13.4 vs 14.5 us per call).
     // TALFE_FUSED_NORM: 0 (default) never, 1 calls of at most kFuseMaxTilesPerCta tiles per CTA, 2 always.
     const bool fuse_pays = plan->fuse_norm >= 2 || w.n_tiles <= (long long)kFuseMaxTilesPerCta * plan->sm_count;
-    if (ref_norm && use_ws && !use_fl && plan->fuse_norm && fuse_pays && job->out_layout == TALFE_LAYOUT_TM && a.out_align_ok) {
+    if (ref_norm && use_ws && !use_fl && !compact && plan->fuse_norm && fuse_pays && job->out_layout == TALFE_LAYOUT_TM && a.out_align_ok) {
         talfe_plan* pl = const_cast<talfe_plan*>(plan);
         std::lock_guard<std::mutex> lock(*pl->bar_mutex);
         int slot = -1;
@@ -1423,6 +1533,15 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
     if (!want_stats) return TALFE_OK;
     double* stats = job->stats ? job->stats : reinterpret_cast<double*>(ws + w.scratch_stats);
     const int accumulate = (job->accumulate_stats && job->stats) ? 1 : 0;
+    if (hint_sum) {
+        const unsigned yb = (unsigned)std::max<long long>(1, std::min<long long>(65535, (long long)plan->sm_count * 8 / job->batch));
+        hint_finish_kernel<<<dim3((unsigned)job->batch, yb), 256, 0, stream>>>(job->out, ors, job->out_layout, M,
+                                                                              reinterpret_cast<const long long*>(ws + w.const_frames), a.n_frames, job->eps,
+                                                                              (const double2*)a.partials, (int)grid + 1, (double)dense * (double)job->batch,
+                                                                              job->stats);
+        TALFE_CUDA(cudaGetLastError());
+        return TALFE_OK;
+    }
     if (ref_norm) {
         // the reference case: one scalar over a contiguous [B, T, M] (or [B, M, T]) tensor; the sweep
         // derives the mean from the per-CTA partials itself (no separate reduction launch)
@@ -1438,7 +1557,7 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
         TALFE_CUDA(cudaLaunchKernelEx(&cfg, sub_scalar_flat_kernel, reinterpret_cast<float4*>(job->out), n4, job->out + 4 * n4,
-                                      (int)(total - 4 * n4), (const double2*)a.partials, (int)grid, (double)total, job->stats));
+                                      (int)(total - 4 * n4), (const double2*)a.partials, (int)grid + (hint_sum ? 1 : 0), (double)total, job->stats));
         return TALFE_OK;
     }
     const long long blocks = per_row ? job->batch : 1;

@@ -152,13 +152,13 @@ def _run(plan: _Plan, audio: torch.Tensor, *, norm: int, layout: int, eps: float
          origin: int = 0, total_len: Optional[int] = None, frame0: int = 0, n_frames: Optional[int] = None,
          out: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None, accumulate: bool = False,
          defer: bool = False, out_offsets: Optional[torch.Tensor] = None, packed_frames: int = 0,
-         bands=None, given_stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+         bands=None, given_stats: Optional[torch.Tensor] = None, padding_hint: bool = False) -> torch.Tensor:
     device = audio.device
     if torch.cuda.current_device() != device.index:
         with torch.cuda.device(device):          # launches and allocations below need `device` current
             return _run(plan, audio, norm=norm, layout=layout, eps=eps, lens=lens, origin=origin, total_len=total_len,
                         frame0=frame0, n_frames=n_frames, out=out, stats=stats, accumulate=accumulate, defer=defer,
-                        out_offsets=out_offsets, packed_frames=packed_frames, bands=bands, given_stats=given_stats)
+                        out_offsets=out_offsets, packed_frames=packed_frames, bands=bands, given_stats=given_stats, padding_hint=padding_hint)
     B, buf_len = audio.shape
     if total_len is None:
         total_len = buf_len
@@ -201,6 +201,7 @@ def _run(plan: _Plan, audio: torch.Tensor, *, norm: int, layout: int, eps: float
         job.freq_bands, job.time_bands, job.n_bands = fb.data_ptr(), tb.data_ptr(), fb.shape[1]
     if given_stats is not None:
         job.given_stats = given_stats.data_ptr()
+    job.lens_are_padding_hint = 1 if padding_hint else 0
     job.stream = stream_ptr
     rc = plan._run(plan.handle, job)
     if rc:
@@ -331,7 +332,8 @@ class LogMelSpec(nn.Module):
     @torch.jit.ignore
     def features(self, audio: torch.Tensor, audio_lens: Optional[torch.Tensor] = None, norm: str = "batch",
                  layout: str = "tm", out: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None,
-                 defer_normalise: bool = False, spec_augment=None, given_stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+                 defer_normalise: bool = False, spec_augment=None, given_stats: Optional[torch.Tensor] = None,
+                 lens_are_padding: bool = False) -> torch.Tensor:
         """Extension surface on the same kernels.
 
         audio_lens  int64 [B] true lengths (what the collaters emit next to the padded batch,
@@ -344,6 +346,10 @@ class LogMelSpec(nn.Module):
         stats       optional float64 tensor receiving the statistics block(s) (see include/talfe.h)
         spec_augment (freq_bands, time_bands) from ``specaug.sample_masks``: zeroed in the normalisation sweep,
                     replacing ``time_mask(freq_mask(x))`` of tal/asr/models.py:159-161
+        lens_are_padding  with ``audio_lens``: keep the REFERENCE semantics (every row padded to L, the padding frames count
+                    in the mean) and take ``audio_lens`` as the collater's guarantee that row r is zero from sample
+                    ``audio_lens[r]`` on: frames that cannot see a real sample are the constant log(eps) and are filled,
+                    not computed — the reference's result at the cost of the real audio (norm 'batch' / 'none')
         given_stats optional float64 statistics block [1, 3 + 2 M] on the device (e.g. ``CorpusStats.block`` after its
                     all-reduce): EVERY row is normalised with it, according to ``norm``, inside the transform kernel —
                     dataset-level CMVN without a sweep over the features; the values are identical to
@@ -368,6 +374,9 @@ class LogMelSpec(nn.Module):
                 if fb.shape != tb.shape or fb.dim() != 3 or fb.shape[0] != audio.shape[0] or fb.shape[2] != 2 or fb.shape[1] > 16:
                     raise ValueError("spec_augment bands must be two int tensors [B, n_bands <= 16, 2]")
                 bands = (fb, tb)
+            if lens_are_padding:
+                if lens is None or norm not in ("batch", "none") or defer_normalise or spec_augment is not None or given_stats is not None or stats is not None:
+                    raise ValueError("lens_are_padding needs audio_lens, norm 'batch' or 'none', and none of stats / defer / spec_augment / given_stats")
             if given_stats is not None:
                 if norm == "none" or defer_normalise or spec_augment is not None:
                     raise ValueError("given_stats needs norm != 'none', no deferral and no spec_augment")
@@ -375,7 +384,8 @@ class LogMelSpec(nn.Module):
                         or given_stats.numel() < _lib.stats_doubles(self.n_mels)):
                     raise ValueError(f"given_stats must be a contiguous float64 block of {_lib.stats_doubles(self.n_mels)} doubles on {device}")
             return _run(self.plan(device), audio, norm=_NORMS[norm], layout=_LAYOUTS[layout], eps=self.eps,
-                        lens=lens, out=out, stats=stats, defer=defer_normalise, bands=bands, given_stats=given_stats)
+                        lens=lens, out=out, stats=stats, defer=defer_normalise, bands=bands, given_stats=given_stats,
+                        padding_hint=lens_are_padding)
 
     @torch.jit.ignore
     def features_packed(self, audio: torch.Tensor, audio_lens: torch.Tensor, norm: str = "row"):

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in talfe.h but not exported"
     assert sorted(_lib.EXPORTED) == declared
-    assert lib.talfe_version() == _lib.EXPECTED_VERSION == 104
+    assert lib.talfe_version() == _lib.EXPECTED_VERSION == 105
     assert lib.talfe_job_size() == __import__("ctypes").sizeof(_lib.Job)
     assert lib.talfe_strerror(-2).decode().startswith("waveform too short")
 

@@ -363,3 +363,33 @@ def test_compact_tile_list_edge_cases(dev):
     ws.features(x, audio_lens=al, norm="none", out=out)
     want = legacy.features(x, audio_lens=al, norm="none")
     assert torch.equal(out, want)
+
+
+@pytest.mark.parametrize("kernel", ["ws", "legacy"])
+def test_lens_as_padding_hint_is_the_reference_result(dev, kernel):
+    """talfe_job::lens_are_padding_hint: a zero-padded ragged batch (what the reference's collaters hand over) with the
+    REFERENCE semantics — every row has the padded length's frames, the padding frames are log(eps) and count in the mean —
+    computed only where a frame can see a real sample.  Un-normalised: bitwise the plain call on the same buffer (the constant
+    fill is the kernel's own expression for an all-zero frame); batch mean: to rounding.  Rows that end just short of the
+    padded length are reached by the reflection at the padded end and must be computed in full."""
+    m = _module(dev, TALFE_KERNEL=kernel)
+    L = 16000 * 9 + 37
+    x = _fill(dev, 8, L, episode=41)
+    lens = [L, 16000, 0, L - 1, L - 150, L - 450, 5000, 777]
+    for r, n in enumerate(lens):
+        x[r, n:] = 0.0
+    al = torch.tensor(lens, device=dev)
+    for xx in (x, (x * 32767).round().to(torch.int16)):
+        for layout in ("tm", "mt"):
+            want = m.features(xx, norm="none", layout=layout)
+            got = m.features(xx, audio_lens=al, lens_are_padding=True, norm="none", layout=layout)
+            assert torch.equal(got, want), (layout, xx.dtype)
+            want = m.features(xx, norm="batch", layout=layout)
+            got = m.features(xx, audio_lens=al, lens_are_padding=True, norm="batch", layout=layout)
+            assert float((got - want).abs().max()) < 2e-6, (layout, xx.dtype)
+    # and against the float64 oracle of the reference semantics
+    ref = O.logmel_f64(x.cpu().numpy())
+    got = m.features(x, audio_lens=al, lens_are_padding=True).cpu().numpy()
+    assert rel_err(got, ref) < TOL
+    with pytest.raises(ValueError):
+        m.features(x, audio_lens=al, lens_are_padding=True, norm="row")

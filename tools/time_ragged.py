@@ -25,6 +25,10 @@ valid = int((1 + lens // 160).sum())
 print("valid frames", valid, "padded frames", B * (1 + L // 160))
 out = torch.empty(B, 1 + L // 160, 80, dtype=torch.float32, device=dev)
 print("padded (reference) ms", round(t(lambda: mod.features(x, out=out)), 4))
+xz = x.clone()
+for r in range(B):
+    xz[r, int(lens[r]):] = 0
+print("padded, lens as padding hint ms", round(t(lambda: mod.features(xz, audio_lens=lens_d, lens_are_padding=True, out=out)), 4), " (plain call on the same zero-padded buffer:", round(t(lambda: mod.features(xz, out=out)), 4), ")")
 print("per-row            ms", round(t(lambda: mod.features(x, audio_lens=lens_d, norm="row", out=out)), 4))
 print("packed row         ms", round(t(lambda: mod.features_packed(x, lens, norm="row")), 4))
 print("packed row_mel_var ms", round(t(lambda: mod.features_packed(x, lens, norm="row_mel_var")), 4))
