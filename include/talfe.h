@@ -205,6 +205,13 @@ int talfe_allreduce_stats(double* stats_dev, int64_t count, void* nccl_comm, voi
  * Allocates, launches and synchronises: never call it on a hot path. */
 int talfe_probe_fp32_fma_rate(int device, double* fma_per_second);
 
+/* The collaters' zero padding (tal/asr/data/aligned.py:246-270) found on the device: lens[r] (DEVICE int64[batch]) = 1 + index
+ * of row r's last non-zero sample, 0 for an all-zero row — the `lens` to pass with talfe_job::lens_are_padding_hint when the
+ * caller has no lengths at hand (LogMelSpec.forward(audio) only gets the padded batch).  One backwards scan per row that stops
+ * at the first non-zero sample: an unpadded batch costs one small launch. */
+int talfe_detect_padding(const void* wave, int wave_dtype, int64_t batch, int64_t n_samples, int64_t row_stride, int64_t* lens,
+                         void* stream);
+
 /* Deterministic synthetic audio (bench / tests): fills wave[rows, n_samples] with episode
  * (first_episode + r), samples [start, start + n_samples); bit-identical to tal_asrd_b200/synth.py. */
 int talfe_synth_fill(void* wave, int wave_dtype, int64_t rows, int64_t n_samples, int64_t row_stride,

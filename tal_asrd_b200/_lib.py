@@ -20,7 +20,7 @@ EXPORTED = [
     "talfe_strerror", "talfe_last_cuda_error", "talfe_num_frames", "talfe_plan_create", "talfe_plan_create_ex",
     "talfe_plan_geometry", "talfe_plan_num_frames", "talfe_resample",
     "talfe_plan_destroy", "talfe_plan_n_mels", "talfe_workspace_bytes", "talfe_run", "talfe_logmel_forward",
-    "talfe_apply_stats", "talfe_allreduce_stats", "talfe_synth_fill", "talfe_stream_staging_bytes",
+    "talfe_apply_stats", "talfe_allreduce_stats", "talfe_synth_fill", "talfe_detect_padding", "talfe_stream_staging_bytes",
     "talfe_stream_episode",
 ]
 
@@ -118,6 +118,8 @@ def _finish_binding(lib, optional: bool = False):
                                          c_float, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p]
     lib.talfe_allreduce_stats.restype = c_int
     lib.talfe_allreduce_stats.argtypes = [c_void_p, c_int64, c_void_p, c_void_p]
+    lib.talfe_detect_padding.restype = c_int
+    lib.talfe_detect_padding.argtypes = [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p]
     lib.talfe_synth_fill.restype = c_int
     lib.talfe_synth_fill.argtypes = [c_void_p, c_int, c_int64, c_int64, c_int64, c_uint64, c_int64, c_int64, c_void_p]
     _LIB = lib

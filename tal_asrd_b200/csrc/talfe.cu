@@ -606,6 +606,42 @@ __global__ void __launch_bounds__(256) const_partial_kernel(const long long* __r
     }
 }
 
+// Collater padding found on the device: lens[r] = 1 + index of row r's last non-zero sample (0 for an all-zero row; lens is
+// zeroed first).  Block (row, segment) scans ITS segment of the row backwards, every thread its own stride of samples until it
+// meets a non-zero one: a thread inside the audio stops after one load, the padding is read once at memory speed (instead
+// of being transformed), and the row's result is the maximum over its segments (atomicMax: order-independent).
+constexpr int kPadSegments = 32, kPadThreads = 256;
+template <typename XT>
+__global__ void __launch_bounds__(kPadThreads) detect_padding_kernel(const XT* __restrict__ wave, long long row_stride, long long n_samples,
+                                                                     unsigned long long* __restrict__ lens) {
+    __shared__ long long s_last[kPadThreads / 32];
+    const XT* row = wave + (long long)blockIdx.x * row_stride;
+    const long long seg = (n_samples + kPadSegments - 1) / kPadSegments;
+    const long long lo = (long long)blockIdx.y * seg, hi = min(n_samples, lo + seg);
+    long long last = -1;
+    long long i = hi - 1 - threadIdx.x;                                 // this thread's samples: hi-1-t, hi-1-t-256, ...
+    if (i >= lo && x_to_float(row[i]) != 0.f) last = i;
+    i -= kPadThreads;
+    while (last < 0 && i >= lo) {
+        constexpr int kU = 8;
+        XT v[kU];
+#pragma unroll
+        for (int q = 0; q < kU; ++q) { const long long j = i - (long long)q * kPadThreads; v[q] = j >= lo ? row[j] : XT(0.f); }
+#pragma unroll
+        for (int q = kU - 1; q >= 0; --q) if (x_to_float(v[q]) != 0.f) last = max(last, i - (long long)q * kPadThreads);
+        i -= (long long)kU * kPadThreads;
+    }
+    for (int o = 16; o > 0; o >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+    if ((threadIdx.x & 31) == 0) s_last[threadIdx.x >> 5] = last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long best = s_last[0];
+#pragma unroll
+        for (int w2 = 1; w2 < kPadThreads / 32; ++w2) best = max(best, s_last[w2]);
+        if (best >= 0) atomicMax(lens + blockIdx.x, (unsigned long long)(best + 1));
+    }
+}
+
 // ------------------------------------------------------------------------------------------ K2
 // One block per statistics block (1 for batch-wide, B for per-row).  Fixed-order tree in shared
 // memory: the result does not depend on scheduling.
@@ -1783,6 +1819,20 @@ int talfe_allreduce_stats(double* stats_dev, int64_t count, void* nccl_comm, voi
     // ncclDouble = 8 (ncclFloat64), ncclSum = 0 in every NCCL 2.x release
     const int rc = g_nccl_allreduce(stats_dev, stats_dev, (size_t)count, 8, 0, nccl_comm, reinterpret_cast<cudaStream_t>(stream));
     return rc == 0 ? TALFE_OK : TALFE_ERR_NCCL;
+}
+
+int talfe_detect_padding(const void* wave, int wave_dtype, int64_t batch, int64_t n_samples, int64_t row_stride, int64_t* lens, void* stream) {
+    if (!wave || !lens || batch < 1 || batch > 0x7fffffffLL || n_samples < 1 || row_stride < n_samples) return TALFE_ERR_INVALID;
+    if (wave_dtype < TALFE_F32 || wave_dtype > TALFE_I16) return TALFE_ERR_INVALID;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    unsigned long long* out = reinterpret_cast<unsigned long long*>(lens);
+    TALFE_CUDA(cudaMemsetAsync(out, 0, (size_t)batch * sizeof(unsigned long long), st));
+    const dim3 grid((unsigned)batch, kPadSegments);
+    if (wave_dtype == TALFE_F32) detect_padding_kernel<float><<<grid, kPadThreads, 0, st>>>(reinterpret_cast<const float*>(wave), row_stride, n_samples, out);
+    else if (wave_dtype == TALFE_F16) detect_padding_kernel<__half><<<grid, kPadThreads, 0, st>>>(reinterpret_cast<const __half*>(wave), row_stride, n_samples, out);
+    else detect_padding_kernel<short><<<grid, kPadThreads, 0, st>>>(reinterpret_cast<const short*>(wave), row_stride, n_samples, out);
+    TALFE_CUDA(cudaGetLastError());
+    return TALFE_OK;
 }
 
 int talfe_synth_fill(void* wave, int wave_dtype, int64_t rows, int64_t n_samples, int64_t row_stride, uint64_t seed,

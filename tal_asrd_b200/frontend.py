@@ -271,8 +271,13 @@ class LogMelSpec(nn.Module):
     rounded buffers are kept for ``state_dict`` compatibility only); the cast happens once at the end.
     """
 
-    def __init__(self, sr: int = DEFAULT_SR, n_mels: int = 80, eps: float = 1e-6):
+    def __init__(self, sr: int = DEFAULT_SR, n_mels: int = 80, eps: float = 1e-6, detect_padding: bool = False):
         super().__init__()
+        # detect_padding (extension, off by default = the reference's constructor): forward() first finds each row's last
+        # non-zero sample on the device (talfe_detect_padding: the collaters zero-pad, tal/asr/data/aligned.py:246-270) and
+        # then computes only the frames that can see a real sample — the same result, faster on heavily padded batches,
+        # one small extra launch on dense ones
+        self.detect_padding = bool(detect_padding)
         # sr = 16000 (n_fft 400, hop 160: the only rate the reference runs at, tal/asr/data/__init__.py:6) is served by the
         # specialised kernels; any other rate by the generic kernel (same C ABI, same semantics, csrc/talfe_generic.cuh)
         self.n_fft, self.hop = geometry(sr)
@@ -326,8 +331,25 @@ class LogMelSpec(nn.Module):
             audio = _prepare_audio(audio)
             device = _require_cuda(audio)
             num_frames(audio.shape[1], self.n_fft, self.hop)
-            y = _forward_fast(self.plan(device), audio, self.eps)
+            if self.detect_padding:
+                y = self.features(audio, audio_lens=self.padding_lens(audio), lens_are_padding=True)
+            else:
+                y = _forward_fast(self.plan(device), audio, self.eps)
             return y if self._out_dtype(audio) == torch.float32 else y.half()
+
+    @torch.jit.ignore
+    def padding_lens(self, audio: torch.Tensor) -> torch.Tensor:
+        """int64 [B] on the device: 1 + index of every row's last non-zero sample (0 for an all-zero row)."""
+        audio = _prepare_audio(audio)
+        device = _require_cuda(audio)
+        plan = self.plan(device)
+        lens = torch.empty(audio.shape[0], dtype=torch.int64, device=device)
+        with torch.cuda.device(device):
+            _lib.check(plan.lib.talfe_detect_padding(audio.data_ptr(), _DTYPES[audio.dtype], audio.shape[0], audio.shape[1],
+                                                     audio.stride(0) if audio.shape[0] > 1 else max(audio.stride(0), audio.shape[1]),
+                                                     lens.data_ptr(), torch.cuda.current_stream(device).cuda_stream),
+                       "talfe_detect_padding")
+        return lens
 
     @torch.jit.ignore
     def features(self, audio: torch.Tensor, audio_lens: Optional[torch.Tensor] = None, norm: str = "batch",

@@ -393,3 +393,24 @@ def test_lens_as_padding_hint_is_the_reference_result(dev, kernel):
     assert rel_err(got, ref) < TOL
     with pytest.raises(ValueError):
         m.features(x, audio_lens=al, lens_are_padding=True, norm="row")
+
+
+def test_drop_in_with_detected_padding(dev):
+    """LogMelSpec(detect_padding=True): forward(audio) finds the collater's zero padding itself (talfe_detect_padding) and
+    computes only what can see a real sample — the reference's result with the reference's call."""
+    from tal_asrd_b200 import LogMelSpec
+    plain, fast = LogMelSpec().to(dev), LogMelSpec(detect_padding=True).to(dev)
+    L = 16000 * 8 + 3
+    x = _fill(dev, 6, L, episode=51)
+    lens = [L, 12345, 0, L - 100, 64000, 1]
+    for r, n in enumerate(lens):
+        x[r, n:] = 0.0
+    x[4, 100:200] = 0.0                                                  # zeros inside a row are not padding
+    for xx in (x, x.half(), (x * 32767).round().to(torch.int16)):
+        got_lens = fast.padding_lens(xx).cpu().tolist()
+        want_lens = [int(torch.nonzero(row).max()) + 1 if bool((row != 0).any()) else 0 for row in xx]
+        assert got_lens == want_lens
+        assert float((fast(xx) - plain(xx)).abs().max()) < 2e-6
+    dense = _fill(dev, 4, 48000, episode=52)
+    assert float((fast(dense) - plain(dense)).abs().max()) < 2e-6
+    assert copy.deepcopy(fast).detect_padding

@@ -29,6 +29,11 @@ xz = x.clone()
 for r in range(B):
     xz[r, int(lens[r]):] = 0
 print("padded, lens as padding hint ms", round(t(lambda: mod.features(xz, audio_lens=lens_d, lens_are_padding=True, out=out)), 4), " (plain call on the same zero-padded buffer:", round(t(lambda: mod.features(xz, out=out)), 4), ")")
+fast = LogMelSpec(detect_padding=True).to(dev)
+print("drop-in forward(), detect_padding=True ms", round(t(lambda: fast(xz)), 4), " (scan alone:", round(t(lambda: fast.padding_lens(xz)), 4), ")")
+dense = torch.empty(64, 480000, dtype=torch.float32, device=dev)
+_lib.check(lib.talfe_synth_fill(dense.data_ptr(), _lib.F32, 64, 480000, 480000, 2020, 9, 0, None))
+print("dense 64 x 30 s: plain forward ms", round(t(lambda: mod(dense), 20), 4), " with detect_padding ms", round(t(lambda: fast(dense), 20), 4))
 print("per-row            ms", round(t(lambda: mod.features(x, audio_lens=lens_d, norm="row", out=out)), 4))
 print("packed row         ms", round(t(lambda: mod.features_packed(x, lens, norm="row")), 4))
 print("packed row_mel_var ms", round(t(lambda: mod.features_packed(x, lens, norm="row_mel_var")), 4))
