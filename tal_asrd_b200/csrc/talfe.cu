@@ -1516,7 +1516,7 @@ int talfe_run(const talfe_plan* plan, const talfe_job* job) {
 #endif
     {
         cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(use_ws ? ws_block_threads(a.fuse_norm != 0) : kThreads);
+        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(use_ws ? kWsThreads : kThreads);
         cfg.dynamicSmemBytes = use_ws ? plan->ws_smem : plan->smem_bytes; cfg.stream = stream;
         cudaLaunchAttribute attr[2];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;

@@ -25,36 +25,18 @@ namespace {
 
 constexpr int kWsRoleThreads = kWsGroups * kGroup;          // 320
 constexpr int kWsRoleWarps = kWsRoleThreads / 32;           // 10
-// -DTALFE_WS_P2=1 (experiment): FIVE producer warps, every producer thread running stage 1 of TWO frame pairs (g1 and g1 + 8)
-// per tile as independent instruction streams — 15 warps at 136 registers instead of 20 at 96: more registers and
-// instruction-level parallelism per warp, half the twiddle loads and barrier arrivals, against fewer warps per scheduler.
-// Measured and NOT adopted (profiles/r02_ab_p2_five_producer_warps.json): 94.5 us against 76.5 us, bit-identical.
-#ifndef TALFE_WS_P2
-#define TALFE_WS_P2 0
-#endif
-constexpr int kWsProdThreads = TALFE_WS_P2 ? kWsRoleThreads / 2 : kWsRoleThreads;   // 160 / 320
-constexpr int kWsProdWarps = kWsProdThreads / 32;                                     // 5 / 10
-constexpr int kWsThreads = kWsProdThreads + kWsRoleThreads;  // 640: 10 producer warps, 10 consumer warps (5 per scheduler: 96 registers each)
-// Helper warpgroup (round 2, -DTALFE_WS_HELPER=1): four more warps, one per scheduler, launched with the rest at 80 registers
-// per thread.  `setmaxnreg` then moves registers from the helpers (40) to the twenty compute warps (88): 640 x 88 + 128 x 40
-// = 768 x 80.  Helper warp 0 is the LOADER (tile descriptors, x_empty waits, tensor copies of the waveform tiles — the duty
-// that made one of the ten producer warps the straggler of every tile), helper warp 1 the STORER (bulk copies of the staged
-// feature tiles to global memory, which cost an issuing consumer warp ~270 cycles each); helper warps 2 and 3 exit.
-// Measured and NOT adopted (profiles/r02_ab_helper_warpgroup.json, all bit-identical): against the helpers-idle build the
-// loader warp saves 2.6 us and the storer 0.4 us, but 88 instead of 96 registers for the compute warps costs 5.0 us (81.2 us
-// with idle helpers, 78.6 with the loader, 79.9 with both, 76.2 shipped).  768 x 80 registers is the whole pool a launch of
-// 24 warps can get (allocation granularity 8 per thread), so 96 + a helper warpgroup does not exist on this register file.
-#ifndef TALFE_WS_HELPER
-#define TALFE_WS_HELPER 0
-#endif
-#ifndef TALFE_WS_HELPER_MODE
-#define TALFE_WS_HELPER_MODE 3        // bit 0: the loader duty moves to the helpers, bit 1: the bulk feature stores do
-#endif
-constexpr bool kWsHelperLoads = (TALFE_WS_HELPER_MODE & 1) != 0, kWsHelperStores = (TALFE_WS_HELPER_MODE & 2) != 0;
-constexpr int kWsHelperThreads = 128;
-constexpr int kWsComputeRegs = 88, kWsHelperRegs = 40;
-static_assert(!TALFE_WS_HELPER || kWsThreads * kWsComputeRegs + kWsHelperThreads * kWsHelperRegs == (kWsThreads + kWsHelperThreads) * 80, "register pool");
-__host__ __device__ constexpr int ws_block_threads(bool fuse) { return (TALFE_WS_HELPER && !fuse) ? kWsThreads + kWsHelperThreads : kWsThreads; }
+constexpr int kWsThreads = 2 * kWsRoleThreads;              // 640: 10 producer warps, 10 consumer warps (5 per scheduler: 96 registers each)
+// Other role / register splits that were built and measured against this one (all bit-identical; code in the history at the
+// commits named in DESIGN.md §4, results under profiles/):
+//   * a helper warpgroup behind `setmaxnreg` (768 threads launched at 80 registers, compute warps raised to 88, helpers at
+//     40; a loader warp and a storer warp): the loader warp saves 2.6 us, the storer 0.4 us, 88 registers instead of 96 cost
+//     5.0 us -> 79.9 us (r02_ab_helper_warpgroup.json);
+//   * five producer warps with two frame pairs per thread (15 warps x 128 registers): 94.5 us (r02_ab_p2_five_producer_warps.json);
+//   * the loader duty on a consumer warp, after or before its wait for the exchange buffer: 78.0 / 78.4 us
+//     (r02_ab_consumer_loads*.json);
+//   * one mbarrier arrival per phase through a shared-memory counter: 80.7 us (r02_ab_single_arrive.json); only the loader
+//     waiting for a free exchange buffer: 77.9 us (r02_ab_loader_waits_e.json); an L2 evict_last hint on the feature stores:
+//     no gain for the sweep that follows (76.1 / 89.2 us against 75.7 / 89.1).
 constexpr int kWsTileSamples = kHop * kWsFrames + (kNfft - kHop);   // 5360
 // fp32 tiles travel as ONE tensor copy (cp.async.bulk.tensor, SASS UTMALDG): the waveform is described to the copy engine
 // as rows of 340 samples that start every 320 samples (a 4-D tensor map [68][5][rows][batch] with strides 272 B, 1 280 B,
@@ -73,50 +55,11 @@ static_assert(kWsTileSamples == kTileSamples && kWsRoleWarps == kWarps, "tile ge
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// Experiment (round 2, measured and NOT adopted: 80.7 us against 76.4 us, profiles/r02_ab_single_arrive.json): one mbarrier
-// arrival per PHASE instead of one per warp — the warps of a role count themselves in on a shared-memory counter (acq_rel)
-// and the last one arrives, so that the sleeping waiters (NANOSLEEP.SYNCS wakes on every arrival; ~40 warp-instructions per
-// frame go into re-checking incomplete phases) wake once.  The atomic's round trip on every hand-off costs more than the
-// re-checks it saves.  -DTALFE_WS_SINGLE_ARRIVE=1 builds it.
-// Experiment (round 2, measured and NOT adopted: 77.9 us against 76.2 us, profiles/r02_ab_loader_waits_e.json): only the
-// loader waits for "E[buf] free", before it lets the next tile's waveform travel, so that x_full implies it and no producer
-// warp pays a second completed try_wait per tile.  It makes the warp with loader duty the straggler of its tile, and the
-// slowest of the ten producer warps is what every consumer waits for.  -DTALFE_WS_LOADER_WAITS_E=1 builds it.
-#ifndef TALFE_WS_LOADER_WAITS_E
-#define TALFE_WS_LOADER_WAITS_E 0
-#endif
-#ifndef TALFE_WS_SINGLE_ARRIVE
-#define TALFE_WS_SINGLE_ARRIVE 0
-#endif
-__device__ __forceinline__ void mbar_arrive_counted(unsigned long long* bar, unsigned* counter, unsigned n_warps) {
-#if TALFE_WS_SINGLE_ARRIVE
-    unsigned old;
-    asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(counter)) : "memory");
-    if (old == n_warps - 1) {
-        asm volatile("st.relaxed.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(counter)), "r"(0u) : "memory");
-        mbar_arrive(bar);
-    }
-#else
-    mbar_arrive(bar);
-#endif
-}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
-// -DTALFE_WS_STORE_HINT=1 (experiment): feature stores carry an L2 evict_last hint so that the whole output stays in L2 for
-// the normalisation sweep that follows (ncu: ~10 of the 61.5 MB have gone to DRAM by the end of K1).  Measured, no gain:
-// K1 76.1 against 75.7 us, forward 89.2 against 89.1 us.
-#ifndef TALFE_WS_STORE_HINT
-#define TALFE_WS_STORE_HINT 0
-#endif
 __device__ __forceinline__ void bulk_s2g(void* gmem_dst, unsigned smem_src, unsigned bytes) {
-#if TALFE_WS_STORE_HINT
-    unsigned long long pol;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gmem_dst), "r"(smem_src), "r"(bytes), "l"(pol) : "memory");
-#else
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_src), "r"(bytes) : "memory");
-#endif
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
@@ -237,22 +180,6 @@ __device__ __forceinline__ void ws_advance(const KernelArgs& a, int& row, int& t
     while (tq >= a.tiles_per_row) { tq -= a.tiles_per_row; ++row; }
 }
 
-// Who fetches the waveform tiles.  0: the producer warps in turn (tile k by warp k % 10, one tile ahead, after waiting for
-// x_empty).  1: the CONSUMER group that has just seen "E[k & 1] full": every producer warp has then finished reading
-// x[k & 1] (it arrives on e_full after its last read), so the buffer is free without any further barrier, the fetch of tile
-// k + 2 gets ~4 000 cycles of lead instead of ~2 600, and the producers — the role that sets the kernel's pace — lose the
-// loader duty that made one of their ten warps the straggler of every tile (and the x_empty arrivals with it).
-// Measured and NOT adopted (profiles/r02_ab_consumer_loads.json): 78.0 us against 76.1 us, bit-identical — the consumer warp
-// with loader duty becomes the straggler of its group at barrier A2; the consumers have less slack than the timeline suggests.
-// 2: a consumer warp again, but in the group's IDLE window: at the top of its iteration for tile k — before it waits for
-// "E[k & 1] full", which the producers complete ~1 000 cycles after their last read of x[k & 1] — the duty warp (the group's
-// five warps in turn) describes tile k + 2, waits for x_empty(k) and lets the tile travel.  The producers keep their
-// x_empty arrivals and lose the loader duty; the consumers pay for it with time they would have spent waiting.
-// Measured and NOT adopted either (profiles/r02_ab_consumer_loads_idle_window.json): 78.4 us against 76.2 us.
-#ifndef TALFE_WS_CONSUMER_LOADS
-#define TALFE_WS_CONSUMER_LOADS 0
-#endif
-
 // Tile index of this CTA's sequence -> (row, tile inside the row).  Packed ragged output (talfe_job::out_offsets): the
 // tile list is COMPACT — only the tiles that hold frames of their row, enumerated by tile_map_kernel — so that a batch of
 // 1 s .. 10 min utterances costs its own frames and not 64 x the longest row's worth of empty hand-offs.
@@ -267,67 +194,17 @@ __device__ __forceinline__ void ws_tile_coords(const KernelArgs& a, const int ti
     }
 }
 
-// Descriptor of tile kk of this CTA -> ring (all 32 lanes of ONE warp run this; nothing here touches an x buffer).
-template <typename XT, bool kCompact = false>
-__device__ __forceinline__ WsDesc ws_describe_tile(const KernelArgs& a, WsDesc* s_desc, const int kk, const int lane) {
-    const int tile = (int)blockIdx.x + kk * (int)gridDim.x;
-    int row, tq;
-    ws_tile_coords<kCompact>(a, tile, row, tq);
-    long long src_off;
-    WsDesc d = ws_describe(a, row, tq, src_off);
-    d.src = reinterpret_cast<const XT*>(a.wave) + src_off;
-    if (lane == 0) s_desc[kk & (kWsDescRing - 1)] = d;
-    __syncwarp();
-    return d;
-}
-// The fetch of described tile kk into x[kk & 1], which the caller guarantees to be free (same warp, all 32 lanes).
-template <typename XT>
-__device__ __forceinline__ void ws_issue_tile(const KernelArgs& a, const void* tmap, XT* s_x0, unsigned long long* x_full, const int kk,
-                                              const int flags, const int pad, const int row, const void* src_v, const int lane) {
-    constexpr int kXG = XLayout<XT>::kGroup;
-    const XT* src = reinterpret_cast<const XT*>(src_v);
-    const int lbuf = kk & 1;
-#if defined(TALFE_ABLATE) && (TALFE_ABLATE & 16)
-    const int fetch = 0;                                                 // timing experiment only: no waveform fetch
-#else
-    const int fetch = flags & kWsBulkX;
-#endif
-    if (fetch && sizeof(XT) == 4 && a.use_tma) {
-        if (lane == 0) {
-            mbar_expect_tx(x_full + lbuf, kWsTmaBytes);                                    // release: publishes the descriptor too
-            tma_load_4d(smem_u32(s_x0) + lbuf * kWsXBufBytes, tmap, 0, 0, pad, row, x_full + lbuf, l2_evict_first_policy());
-        }
-    } else if (fetch) {
-        if (lane == 0) mbar_expect_tx(x_full + lbuf, kWsTileSamples * (int)sizeof(XT));   // release: publishes the descriptor too
-        __syncwarp();
-        if (lane * kXBlock < kWsTileSamples)
-            bulk_g2s_u32(smem_u32(s_x0 + lane * kXG) + lbuf * kWsXBufBytes, src + lane * kXBlock,
-                         (unsigned)(min(kXBlock, kWsTileSamples - lane * kXBlock) * (int)sizeof(XT)), x_full + lbuf,
-                         l2_evict_first_policy());
-    } else if (lane == 0) {
-        mbar_arrive(x_full + lbuf);                                                      // nothing in flight: descriptor only
-    }
-    __syncwarp();
-}
-template <typename XT>
-__device__ __forceinline__ void ws_load_tile(const KernelArgs& a, const void* tmap, XT* s_x0, WsDesc* s_desc, unsigned long long* x_full,
-                                             const int kk, const int lane) {
-    const WsDesc d = ws_describe_tile<XT>(a, s_desc, kk, lane);
-    ws_issue_tile<XT>(a, tmap, s_x0, x_full, kk, d.flags, d.pad, d.row, d.src, lane);
-}
-
 // ------------------------------------------------------------------------------------------ producers
 // (ONE group of 10 warps, one frame pair per thread.  Splitting the producers into two groups on alternate tiles like
 // the consumers — two pairs per thread, x[q] / E[q] per group — measured 91.7 us against 80.2 us: each group then holds
 // its exchange buffer for two pairs' worth of work and the consumers wait for it.)
-template <typename XT, bool kHelper, bool kCompact>
+template <typename XT, bool kCompact>
 __device__ __forceinline__ void ws_producer(const KernelArgs& a, const void* tmap, unsigned char* smem, XT* s_x0, cf* s_e0, WsDesc* s_desc,
                                             unsigned long long* s_bar, const int tid, const int n_my) {
     unsigned long long* x_full = s_bar;            // [2]
     unsigned long long* x_empty = s_bar + 2;       // [2]
     unsigned long long* e_full = s_bar + 4;        // [2]
     unsigned long long* e_empty = s_bar + 6;       // [2]
-    unsigned* s_cnt = reinterpret_cast<unsigned*>(s_bar + 8);           // [0..1] x_empty, [2..3] e_full, [4..5] e_empty
     const int warp = tid >> 5, lane = tid & 31;
     const int g1 = tid / kGroup, j = tid - g1 * kGroup;
     constexpr int kXG = XLayout<XT>::kGroup;
@@ -388,13 +265,6 @@ __device__ __forceinline__ void ws_producer(const KernelArgs& a, const void* tma
         const int row = tile / a.tiles_per_row, tq = tile - row * a.tiles_per_row;
         describe(kk);
         if (kk >= 2) mbar_wait_sleep(x_empty + (kk & 1), ((kk - 2) >> 1) & 1);           // tile kk-2 has left x[kk & 1]
-#if TALFE_WS_LOADER_WAITS_E
-        // ... and E[kk & 1]: the consumers have loaded tile kk-2's rows.  The loader alone waits for it, BEFORE it lets tile
-        // kk's waveform travel: "x_full(kk) complete" then implies "E[kk & 1] free" for every producer warp (release /
-        // acquire chain consumer -> e_empty -> loader -> x_full -> producers), and none of the ten warps pays the ~300
-        // cycles of a second completed try_wait per tile.
-        if (kk >= 2) mbar_wait_sleep(e_empty + (kk & 1), ((kk - 2) >> 1) & 1);
-#endif
         issue(kk);
         if (a.l2_prefetch && lane == 0 && tile + 2 * step < a.n_tiles) {                 // tile kk+2: HBM -> L2
             int r2 = row, q2 = tq;
@@ -405,14 +275,10 @@ __device__ __forceinline__ void ws_producer(const KernelArgs& a, const void* tma
         }
         __syncwarp();
     };
-#if !TALFE_WS_CONSUMER_LOADS
-    if (!(kHelper && kWsHelperLoads) && warp == 0 && (!kCompact || n_my > 0)) load_duty(0);
-#endif
+    if (warp == 0 && (!kCompact || n_my > 0)) load_duty(0);
     for (int k = 0; k < n_my; ++k) {
         const int buf = k & 1;
-#if !TALFE_WS_CONSUMER_LOADS
-        if (!(kHelper && kWsHelperLoads) && k + 1 < n_my && (k + 1) % kWsProdWarps == warp) load_duty(k + 1);
-#endif
+        if (k + 1 < n_my && (k + 1) % kWsRoleWarps == warp) load_duty(k + 1);
         TL_MARK(warp, k, 0);
         mbar_wait_backoff<TALFE_WS_XFULL_NS>(x_full + buf, (k >> 1) & 1);   // descriptor published, bulk tile landed
         TL_MARK(warp, k, 1);
@@ -427,7 +293,7 @@ __device__ __forceinline__ void ws_producer(const KernelArgs& a, const void* tma
                 XT* s_x = reinterpret_cast<XT*>(reinterpret_cast<unsigned char*>(s_x0) + buf * kXBufBytes);
                 const int s0 = kHop * d.t0 - kHalf;
                 const XT* rowp = reinterpret_cast<const XT*>(a.wave) + (long long)d.row * a.row_stride;
-                for (int i = tid; i < kWsTileSamples; i += kWsProdThreads) {
+                for (int i = tid; i < kWsTileSamples; i += kWsRoleThreads) {
                     int g = s0 + i;
                     if (g < 0) g = -g;                                  // reflect, no edge repeat
                     if (g >= d.L) g = 2 * (d.L - 1) - g;
@@ -437,41 +303,16 @@ __device__ __forceinline__ void ws_producer(const KernelArgs& a, const void* tma
                     s_x[xskew<XT>(i)] = v;
                 }
                 fence_proxy_async();                                    // these generic writes before the next tensor copy into x[buf]
-                named_bar_sync(2, kWsProdThreads);
+                named_bar_sync(2, kWsRoleThreads);
             }
             stage1_ws_fft<XT>(reinterpret_cast<const XT*>(reinterpret_cast<const unsigned char*>(xg) + buf * kXBufBytes), win, re, im);
         }
-#if TALFE_WS_P2
-        // second pair of this thread (g1 + 8): pair A's exchange stores and pair B's transform are independent streams
-        if (k >= 2) mbar_wait_sleep(e_empty + buf, ((k - 2) >> 1) & 1); // consumers have loaded E[buf] of tile k-2
-        TL_MARK(warp, k, 3);
-        cf re2[11], im2[11];
-        if (active) {
-#pragma unroll
-            for (int h = 0; h < 5; ++h) {
-                const float4 tt = reinterpret_cast<const float4*>(s_tw)[h];
-                tw[2 * h] = make_float2(tt.x, tt.y);
-                tw[2 * h + 1] = make_float2(tt.z, tt.w);
-            }
-            stage1_ws_store(re, im, tw, col0 + buf * kWsECf);
-            stage1_ws_fft<XT>(reinterpret_cast<const XT*>(reinterpret_cast<const unsigned char*>(xg + (kWsGroups / 2) * kXG) + buf * kXBufBytes), win, re2, im2);
-        }
         __syncwarp();
         TL_MARK(warp, k, 2);
-        if (lane == 0) mbar_arrive_counted(x_empty + buf, s_cnt + buf, kWsProdWarps);   // this warp no longer reads x[buf]
+        if (lane == 0) mbar_arrive(x_empty + buf);   // this warp no longer reads x[buf]
         __syncwarp();
-        if (active) stage1_ws_store(re2, im2, tw, col0 + (ws_e_base(g1 + kWsGroups / 2) - ws_e_base(g1)) + buf * kWsECf);
-#else
-        __syncwarp();
-        TL_MARK(warp, k, 2);
-#if TALFE_WS_CONSUMER_LOADS != 1
-        if (lane == 0) mbar_arrive_counted(x_empty + buf, s_cnt + buf, kWsProdWarps);   // this warp no longer reads x[buf]
-        __syncwarp();
-#endif
         // every tile, active or not: a producer never runs more than one phase ahead of the consumers
-#if !TALFE_WS_LOADER_WAITS_E
         if (k >= 2) mbar_wait_backoff<TALFE_WS_EEMPTY_NS>(e_empty + buf, ((k - 2) >> 1) & 1); // consumers have loaded E[buf] of tile k-2
-#endif
         TL_MARK(warp, k, 3);
         if (active) {
 #pragma unroll
@@ -482,9 +323,8 @@ __device__ __forceinline__ void ws_producer(const KernelArgs& a, const void* tma
             }
             stage1_ws_store(re, im, tw, col0 + buf * kWsECf);
         }
-#endif
         __syncwarp();
-        if (lane == 0) mbar_arrive_counted(e_full + buf, s_cnt + 2 + buf, kWsProdWarps);
+        if (lane == 0) mbar_arrive(e_full + buf);
         __syncwarp();
         TL_MARK(warp, k, 4);
     }
@@ -563,17 +403,13 @@ __device__ __forceinline__ bool ws_store_tile(const KernelArgs& a, const WsDesc*
 // (measured against ONE group of 10 warps with one row per thread and one barrier per tile: 80.2 against 82.6 us;
 // the ablation switches 32 / 64 of that version went with it)
 constexpr int kCs2Threads = kWsRoleThreads / 2;                         // 160
-template <typename XT, bool kHelperCta, bool kApply>
-__device__ __forceinline__ void ws_consumer(const KernelArgs& a, const void* tmap, unsigned char* smem, XT* s_x0, const cf* s_e0, cf* s_p0, float* s_y0,
-                                                WsDesc* s_desc, unsigned long long* s_bar, const float2* s_norm, const int tid, const int n_my) {
-    constexpr bool kHelper = kHelperCta && kWsHelperStores;           // full tiles leave through the storer warp
+template <typename XT, bool kApply>
+__device__ __forceinline__ void ws_consumer(const KernelArgs& a, unsigned char* smem, const cf* s_e0, cf* s_p0, float* s_y0,
+                                                const WsDesc* s_desc, unsigned long long* s_bar, const float2* s_norm, const int tid, const int n_my) {
     const int grp = tid >= kCs2Threads ? 1 : 0;
     const int gtid = tid - grp * kCs2Threads;
     unsigned long long* e_full = s_bar + 4 + grp;
     unsigned long long* e_empty = s_bar + 6 + grp;
-    unsigned long long* y_full = s_bar + 12 + grp;                      // (helper build) Y[grp] staged -> the storer
-    unsigned long long* y_empty = s_bar + 14 + grp;                     // (helper build) the storer has read Y[grp]
-    unsigned* s_cnt_empty = reinterpret_cast<unsigned*>(s_bar + 8) + 4 + grp;
     const int warp = tid >> 5, lane = tid & 31;
     const int g = gtid & (kWsGroups - 1), r0 = gtid >> 4, r1 = r0 + 10;  // rows / mel lanes r0 (0..9) and r1 (10..19)
     const bool special1 = r1 >= 18;                                     // the group's last warp: packed rows as its second item
@@ -658,37 +494,15 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, const void* tma
     };
 
     int k_last = -1;
-#if TALFE_WS_CONSUMER_LOADS
-    // the group's first tile: nothing has touched x[grp] yet (published to the rest of the group by barrier A1 below)
-    if (gtid < 32 && grp < n_my) ws_load_tile<XT>(a, tmap, s_x0, s_desc, s_bar, grp, lane);
-    int duty = 1;                                                       // the group's warp that fetches at this tile (in turn)
-#endif
     for (int k = grp; k < n_my; k += 2) {
         const WsDesc* dp = s_desc + (k & (kWsDescRing - 1));
         cf v[20];
         TL_MARK(10 + warp, k, 0);
         named_bar_sync(bar_id, kCs2Threads);                            // A1: mel(k-2) finished everywhere
         TL_MARK(10 + warp, k, 1);
-        if (k >= 2) {
-            const WsDesc* dprev = s_desc + ((k - 2) & (kWsDescRing - 1));
-            // helper build: full tiles leave through the storer warp; the group itself only handles the element-wise cases
-            if (!kHelper || !(dprev->flags & kWsBulkY)) ws_store_tile<kCs2Threads>(a, dprev, s_y, gtid);
-        }
-#if TALFE_WS_CONSUMER_LOADS == 2
-        if (k + 2 < n_my && (gtid >> 5) == duty) {
-            const WsDesc dn = ws_describe_tile<XT>(a, s_desc, k + 2, lane);
-            mbar_wait_sleep(s_bar + 2 + grp, (k >> 1) & 1);            // x_empty: every producer warp has read tile k out of x[k & 1]
-            ws_issue_tile<XT>(a, tmap, s_x0, s_bar, k + 2, dn.flags, dn.pad, dn.row, dn.src, lane);
-        }
-        duty = duty == kWsRoleWarps / 2 - 1 ? 0 : duty + 1;
-#endif
+        if (k >= 2) ws_store_tile<kCs2Threads>(a, s_desc + ((k - 2) & (kWsDescRing - 1)), s_y, gtid);
         mbar_wait_backoff<TALFE_WS_EFULL_NS>(e_full, (k >> 1) & 1);
         TL_MARK(10 + warp, k, 2);
-#if TALFE_WS_CONSUMER_LOADS == 1
-        // E[grp](k) is full: every producer warp has finished reading x[k & 1] -> tile k + 2 may travel into it
-        if (k + 2 < n_my && (gtid >> 5) == duty) ws_load_tile<XT>(a, tmap, s_x0, s_desc, s_bar, k + 2, lane);
-        duty = duty == kWsRoleWarps / 2 - 1 ? 0 : duty + 1;
-#endif
         const int flags = dp->flags;
         const bool active = flags & kWsActive;
         if (active) {
@@ -697,14 +511,13 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, const void* tma
             stage2_load(e_row1, v);
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive_counted(e_empty, s_cnt_empty, kWsRoleWarps / 2);    // both rows of E[grp] are in registers
+        if (lane == 0) mbar_arrive(e_empty);    // both rows of E[grp] are in registers
         __syncwarp();
         TL_MARK(10 + warp, k, 3);
         if (active) stage2_row(v, r1, special1);
         TL_MARK(10 + warp, k, 4);
-        if (!kHelper && lane == 0) bulk_wait_read<0>();                 // this lane's store of tile k-2 has finished reading Y[grp]
+        if (lane == 0) bulk_wait_read<0>();                             // this lane's store of tile k-2 has finished reading Y[grp]
         named_bar_sync(bar_id, kCs2Threads);                            // A2: P[grp](k) complete, Y[grp] free
-        if (kHelper && k >= 2) mbar_wait_sleep(y_empty, ((k - 2) >> 1) & 1);   // the storer is done with tile k-2 in Y[grp]
         TL_MARK(10 + warp, k, 5);
         float sum = 0.f, sumsq = 0.f;
         if (active) {
@@ -712,10 +525,6 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, const void* tma
             mel_lane(s_w4b, lo1, yb_b, dp, flags, sum, sumsq, s_norm + r1);
         }
         fence_proxy_async();                                            // Y[grp] writes -> visible to the bulk-copy engine
-        if (kHelper) {
-            __syncwarp();
-            if (lane == 0) mbar_arrive(y_full);                         // one arrival per warp of the group
-        }
         TL_MARK(10 + warp, k, 6);
         if (a.partials_per_tile) {
             double ds = (double)sum, dq = (double)sumsq;
@@ -737,8 +546,7 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, const void* tma
         k_last = k;
     }
     named_bar_sync(bar_id, kCs2Threads);
-    if (k_last >= 0 && (!kHelper || !(s_desc[k_last & (kWsDescRing - 1)].flags & kWsBulkY)))
-        ws_store_tile<kCs2Threads>(a, s_desc + (k_last & (kWsDescRing - 1)), s_y, gtid);
+    if (k_last >= 0) ws_store_tile<kCs2Threads>(a, s_desc + (k_last & (kWsDescRing - 1)), s_y, gtid);
     if (!a.partials_per_tile) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -755,42 +563,7 @@ __device__ __forceinline__ void ws_consumer(const KernelArgs& a, const void* tma
             a.partials[blockIdx.x] = make_double2(ts, tq2);
         }
     }
-    if (!kHelper && lane == 0) bulk_wait_all<0>();                      // shared memory must outlive the copies that read it
-}
-
-// ------------------------------------------------------------------------------------------ helper warpgroup
-// Helper warp 0: every tile's descriptor and waveform fetch, as far ahead as the two x buffers allow.
-// Helper warp 1: every full tile's staged features -> global memory (eight bulk copies of four frames, one per lane), then
-// "Y[q] free" for the consumer group that owns the buffer.  Both run at kWsHelperRegs registers.
-template <typename XT>
-__device__ __forceinline__ void ws_helper(const KernelArgs& a, const void* tmap, XT* s_x0, const float* s_y0, WsDesc* s_desc,
-                                          unsigned long long* s_bar, const int htid, const int n_my) {
-    const int hwarp = htid >> 5, lane = htid & 31;
-    if (hwarp == 0 && kWsHelperLoads) {
-        unsigned long long* x_full = s_bar;
-        unsigned long long* x_empty = s_bar + 2;
-#pragma unroll 1
-        for (int kk = 0; kk < n_my; ++kk) {
-            if (kk >= 2) mbar_wait_sleep(x_empty + (kk & 1), ((kk - 2) >> 1) & 1);       // tile kk-2 has left x[kk & 1]
-            ws_load_tile<XT>(a, tmap, s_x0, s_desc, x_full, kk, lane);
-        }
-    } else if (hwarp == 1 && kWsHelperStores) {
-#pragma unroll 1
-        for (int k = 0; k < n_my; ++k) {
-            const int q = k & 1;
-            mbar_wait_sleep(s_bar + 12 + q, (k >> 1) & 1);                               // Y[q] holds tile k
-            const WsDesc* dp = s_desc + (k & (kWsDescRing - 1));
-            if ((dp->flags & kWsBulkY) && lane < kWsFrames / kWsYChunk) {
-                bulk_s2g(dp->out_tile + kWsYChunk * lane * kMaxMels, smem_u32(s_y0 + q * kWsYFloats + ws_y_off(kWsYChunk * lane)),
-                         kWsYChunk * kMaxMels * (unsigned)sizeof(float));
-                bulk_commit();
-                bulk_wait_read<0>();
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(s_bar + 14 + q);                                  // Y[q] may be overwritten
-        }
-        bulk_wait_all<0>();                                             // shared memory must outlive the copies that read it
-    }
+    if (lane == 0) bulk_wait_all<0>();                                  // shared memory must outlive the copies that read it
 }
 
 // ------------------------------------------------------------------------------------------ fused normalisation
@@ -879,11 +652,9 @@ __device__ __noinline__ void ws_fused_batch_mean(const WsNormArgs a, unsigned ch
 __host__ __device__ constexpr size_t ws_x_offset(size_t table_bytes) { return (table_bytes + 127) & ~(size_t)127; }
 
 template <typename XT, bool kFuse, bool kApply = false, bool kCompact = false>
-__global__ void __launch_bounds__(ws_block_threads(kFuse), 1) logmel_ws_kernel(const KernelArgs a, const __grid_constant__ CUtensorMap tmap) {
-    constexpr bool kHelper = TALFE_WS_HELPER && !kFuse;
-    constexpr int kNT = ws_block_threads(kFuse);
+__global__ void __launch_bounds__(kWsThreads, 1) logmel_ws_kernel(const KernelArgs a, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(16) unsigned char smem[];              // (the dynamic window itself starts 1 KB aligned: no static shared memory)
-    // carve-up: tables (twiddles | mel weights | first bins) | x[2] (128-byte aligned) | E[2] | P[2] | Y[2] | descriptor ring | 8 mbarriers
+    // carve-up: tables (twiddles | mel weights | first bins) | x[2] (128-byte aligned) | E[2] | P[2] | Y[2] | descriptor ring | 8 mbarriers | (mean, 1/std) table
     const unsigned x_off = (unsigned)ws_x_offset((size_t)a.blob_bytes);
     XT* s_x0 = reinterpret_cast<XT*>(smem + x_off);
     cf* s_e0 = reinterpret_cast<cf*>(smem + x_off + 2 * kWsXBufBytes);
@@ -891,26 +662,22 @@ __global__ void __launch_bounds__(ws_block_threads(kFuse), 1) logmel_ws_kernel(c
     float* s_y0 = reinterpret_cast<float*>(s_p0 + 2 * kWsPCf);
     WsDesc* s_desc = reinterpret_cast<WsDesc*>(s_y0 + 2 * kWsYFloats);
     unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_desc + kWsDescRing);
-    float2* s_norm = reinterpret_cast<float2*>(s_bar + 16);           // [80] (mean, 1 / std) per mel: kApply only
+    float2* s_norm = reinterpret_cast<float2*>(s_bar + 8);            // [80] (mean, 1 / std) per mel: kApply only
 
     const int tid = threadIdx.x;
     if (tid == 0) {
         mbar_init(s_bar + 0, 1); mbar_init(s_bar + 1, 1);                               // x_full: the loader's arrival (+ bytes)
-        // x_empty / e_full: the ten producer warps; e_empty: the five warps of the buffer's consumer group — counted in
-        // shared memory, ONE mbarrier arrival per phase by the last of them (mbar_arrive_counted)
-        constexpr unsigned kP = TALFE_WS_SINGLE_ARRIVE ? 1 : kWsProdWarps, kC = TALFE_WS_SINGLE_ARRIVE ? 1 : kWsRoleWarps / 2;
+        // x_empty / e_full: one arrival per producer warp; e_empty: one per warp of the buffer's consumer group
+        constexpr unsigned kP = kWsRoleWarps, kC = kWsRoleWarps / 2;
         mbar_init(s_bar + 2, kP); mbar_init(s_bar + 3, kP);
         mbar_init(s_bar + 4, kP); mbar_init(s_bar + 5, kP);
         mbar_init(s_bar + 6, kC); mbar_init(s_bar + 7, kC);
-        for (int i = 0; i < 6; ++i) reinterpret_cast<unsigned*>(s_bar + 8)[i] = 0;
-        mbar_init(s_bar + 12, kWsRoleWarps / 2); mbar_init(s_bar + 13, kWsRoleWarps / 2);   // y_full: the five warps of a consumer group
-        mbar_init(s_bar + 14, 1); mbar_init(s_bar + 15, 1);                                 // y_empty: the storer
     }
     {
         const int4* src = reinterpret_cast<const int4*>(a.blob);
         int4* dst = reinterpret_cast<int4*>(smem);
-        for (int i = tid; i < a.blob_bytes / 16; i += kNT) dst[i] = __ldg(src + i);
-        for (int i = tid; i < 2 * kWsPCf; i += kNT) s_p0[i] = make_float2(0.f, 0.f);   // incl. the never-written read padding
+        for (int i = tid; i < a.blob_bytes / 16; i += kWsThreads) dst[i] = __ldg(src + i);
+        for (int i = tid; i < 2 * kWsPCf; i += kWsThreads) s_p0[i] = make_float2(0.f, 0.f);   // incl. the never-written read padding
     }
     __syncthreads();
     cudaGridDependencySynchronize();
@@ -924,13 +691,8 @@ __global__ void __launch_bounds__(ws_block_threads(kFuse), 1) logmel_ws_kernel(c
     }
     const int n_tiles = kCompact ? __ldg(a.n_tiles_dev) : a.n_tiles;     // (compact list: counted on the device by tile_prefix_kernel)
     const int n_my = (!kCompact || (int)blockIdx.x < n_tiles) ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;   // tiles blockIdx.x, + gridDim.x, ...
-    if (kHelper) {                                                       // warpgroup-uniform: warps 0..19 compute, 20..23 help
-        if (tid < kWsThreads) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kWsComputeRegs));
-        else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kWsHelperRegs));
-    }
-    if (tid < kWsProdThreads) ws_producer<XT, kHelper, kCompact>(a, &tmap, smem, s_x0, s_e0, s_desc, s_bar, tid, n_my);
-    else if (tid < kWsThreads) ws_consumer<XT, kHelper, kApply>(a, &tmap, smem, s_x0, s_e0, s_p0, s_y0, s_desc, s_bar, s_norm, tid - kWsProdThreads, n_my);
-    else if (kHelper) ws_helper<XT>(a, &tmap, s_x0, s_y0, s_desc, s_bar, tid - kWsThreads, n_my);
+    if (tid < kWsRoleThreads) ws_producer<XT, kCompact>(a, &tmap, smem, s_x0, s_e0, s_desc, s_bar, tid, n_my);
+    else ws_consumer<XT, kApply>(a, smem, s_e0, s_p0, s_y0, s_desc, s_bar, s_norm, tid - kWsRoleThreads, n_my);
     if (kFuse) {                                                       // the exchange buffers are free now: scratch for the reduction
         const WsNormArgs na{a.partials, a.grid_bar, a.norm_count, a.stats_out, a.out, a.out_row_stride, a.batch};
         ws_fused_batch_mean(na, smem + x_off + 2 * kWsXBufBytes);
@@ -939,7 +701,7 @@ __global__ void __launch_bounds__(ws_block_threads(kFuse), 1) logmel_ws_kernel(c
 
 constexpr size_t ws_smem_bytes(size_t table_bytes) {
     return ws_x_offset(table_bytes) + 2 * (size_t)kWsXBufBytes + 2 * (size_t)kWsECf * sizeof(cf) + 2 * (size_t)kWsPCf * sizeof(cf) +
-           2 * (size_t)kWsYFloats * sizeof(float) + kWsDescRing * sizeof(WsDesc) + 16 * sizeof(unsigned long long) + kMaxMels * sizeof(float2);
+           2 * (size_t)kWsYFloats * sizeof(float) + kWsDescRing * sizeof(WsDesc) + 8 * sizeof(unsigned long long) + kMaxMels * sizeof(float2);
 }
 static_assert(kMaxMels * kWsFrames % kWsRoleThreads == 0 && kWsYFloats >= kWsFrames * kMaxMels + 4 * kWsGroups, "Y staging");
 static_assert(ws_smem_bytes(4160) <= 232448, "the ws kernel's shared memory must fit one SM (227 KB)");
